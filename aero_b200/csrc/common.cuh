@@ -1,0 +1,40 @@
+// Shared helpers for libaero_b200 (sm_100a).  No torch / ATen types anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/aero_b200.h"
+
+namespace aero {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // bumps the launch counter, returns AERO_OK / AERO_ERR_LAUNCH
+
+#define AERO_REQUIRE(cond, ...)                         \
+    do {                                                \
+        if (!(cond)) {                                  \
+            aero::set_error(__VA_ARGS__);               \
+            return AERO_ERR_INVALID;                    \
+        }                                               \
+    } while (0)
+
+__device__ __forceinline__ float gelu_exact(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace aero

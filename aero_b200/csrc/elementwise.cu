@@ -1,0 +1,170 @@
+// HBM-bound normalisation / activation passes.  See include/aero_b200.h for contracts.
+// All kernels move 16 bytes per thread per access along the contiguous channel axis.
+#include "common.cuh"
+
+namespace aero {
+
+// ------------------------------------------------------------------------- sample_norm
+// reference aero.py:462-464: mean / unbiased std over (C,F,T); y = (x-mean)/(1e-5+std)
+__global__ void __launch_bounds__(256) sample_norm_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                          float* __restrict__ y, float* __restrict__ samp_affine,
+                                                          int64_t per_sample) {
+    const int b = blockIdx.y;
+    __shared__ float s_mean, s_inv;
+    if (threadIdx.x == 0) {
+        const double n = (double)per_sample;
+        const double mean = stats[2 * b] / n;
+        double var = (stats[2 * b + 1] - n * mean * mean) / (n - 1.0);
+        if (var < 0) var = 0;
+        const double sd = sqrt(var);
+        s_mean = (float)mean;
+        s_inv = (float)(1.0 / (1e-5 + sd));
+        if (blockIdx.x == 0 && samp_affine) {
+            samp_affine[2 * b] = (float)sd;
+            samp_affine[2 * b + 1] = (float)mean;
+        }
+    }
+    __syncthreads();
+    const float mean = s_mean, inv = s_inv;
+    const float* xb = x + (int64_t)b * per_sample;
+    float* yb = y + (int64_t)b * per_sample;
+    const int64_t n4 = per_sample >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(xb)[i];
+        v.x = (v.x - mean) * inv; v.y = (v.y - mean) * inv; v.z = (v.z - mean) * inv; v.w = (v.w - mean) * inv;
+        reinterpret_cast<float4*>(yb)[i] = v;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < per_sample; i += blockDim.x) yb[i] = (xb[i] - mean) * inv;
+}
+
+// ------------------------------------------------------------------------- norm_act
+constexpr int kMaxGroups = 8;
+
+template <int OP>
+__global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ snake_a, const float* __restrict__ scale,
+                                                       const float* __restrict__ residual, float* __restrict__ y,
+                                                       const aero_norm_act_params p, const int64_t seg4) {
+    constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
+    const int seg = blockIdx.x;                       // scope 1: b ; scope 2: b*F_in + f
+    __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+    if (threadIdx.x < p.groups) {
+        const double n = (p.scope == 1) ? (double)p.F_in * p.T * (p.C / p.groups) : (double)p.T * p.C;
+        const int64_t slot = (int64_t)seg * p.groups + threadIdx.x;
+        const double mean = stats[2 * slot] / n;
+        double var = stats[2 * slot + 1] / n - mean * mean;
+        if (var < 0) var = 0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+    __syncthreads();
+    const int Cout = GLU ? p.C / 2 : p.C;
+    const int c4n = Cout >> 2;
+    const int gw = p.C / p.groups;
+    int b, f_fixed;
+    if (p.scope == 1) { b = seg; f_fixed = -1; } else { b = seg / p.F_in; f_fixed = seg % p.F_in; }
+
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < seg4; i += (int64_t)gridDim.y * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        const int64_t r = i / c4n;
+        const int t = (int)(r % p.T);
+        const int fl = (p.scope == 1) ? (int)(r / p.T) : f_fixed;      // output row
+        const int fin = fl + p.f_off;
+        const float* xp = x + (((int64_t)b * p.F_in + fin) * p.T + t) * p.C;
+        const int64_t oidx = (((int64_t)b * p.F_out + fl) * p.T + t) * Cout + c;
+
+        const float4 v = *reinterpret_cast<const float4*>(xp + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 be = *reinterpret_cast<const float4*>(beta + c);
+        const int g0 = c / gw;
+        const float m0 = s_mean[g0], r0 = s_rstd[g0];
+        float a[4] = {(v.x - m0) * r0 * ga.x + be.x, (v.y - m0) * r0 * ga.y + be.y,
+                      (v.z - m0) * r0 * ga.z + be.z, (v.w - m0) * r0 * ga.w + be.w};
+        float o[4];
+        if (GLU) {
+            const int c2 = c + Cout;
+            const float4 v2 = *reinterpret_cast<const float4*>(xp + c2);
+            const float4 ga2 = *reinterpret_cast<const float4*>(gamma + c2);
+            const float4 be2 = *reinterpret_cast<const float4*>(beta + c2);
+            const int g1 = c2 / gw;
+            const float m1 = s_mean[g1], r1 = s_rstd[g1];
+            const float gt[4] = {(v2.x - m1) * r1 * ga2.x + be2.x, (v2.y - m1) * r1 * ga2.y + be2.y,
+                                 (v2.z - m1) * r1 * ga2.z + be2.z, (v2.w - m1) * r1 * ga2.w + be2.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = a[u] * sigmoid_f(gt[u]);
+            if (OP == AERO_NA_GLU_SCALE_RES) {
+                const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+                const float4 rs = *reinterpret_cast<const float4*>(residual + oidx);
+                o[0] = rs.x + sc.x * o[0]; o[1] = rs.y + sc.y * o[1];
+                o[2] = rs.z + sc.z * o[2]; o[3] = rs.w + sc.w * o[3];
+            }
+        } else if (OP == AERO_NA_GELU) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = gelu_exact(a[u]);
+        } else if (OP == AERO_NA_SNAKE) {
+            const float al = snake_a[fin];
+            const float ia = 1.0f / al;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float s = sinf(a[u] * al);
+                o[u] = a[u] + ia * s * s;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = a[u];
+        }
+        *reinterpret_cast<float4*>(y + oidx) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+}  // namespace aero
+
+extern "C" int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* samp_affine, int32_t B,
+                                    int64_t per_sample, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && stats && y && B >= 1 && per_sample >= 2, "aero_sample_norm_fwd: bad argument");
+    AERO_REQUIRE((per_sample & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
+                 "aero_sample_norm_fwd: per_sample must be a multiple of 4 and buffers 16-byte aligned");
+    const int chunks = (int)((per_sample / 4 + 256 * 8 - 1) / (256 * 8));
+    dim3 grid(chunks < 1 ? 1 : chunks, B);
+    sample_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, y, samp_affine, per_sample);
+    return check_launch("aero_sample_norm_fwd");
+}
+
+extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                                 const float* snake_a, const float* scale, const float* residual, float* y,
+                                 const aero_norm_act_params* p, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && stats && gamma && beta && y && p, "aero_norm_act_fwd: null argument");
+    AERO_REQUIRE(p->scope == 1 || p->scope == 2, "aero_norm_act_fwd: scope=%d", p->scope);
+    AERO_REQUIRE(p->groups >= 1 && p->groups <= kMaxGroups && p->C % p->groups == 0 && (p->C / p->groups) % 4 == 0,
+                 "aero_norm_act_fwd: C=%d groups=%d (group width must be a multiple of 4)", p->C, p->groups);
+    AERO_REQUIRE(p->scope == 1 || (p->groups == 1 && p->f_off == 0 && p->F_in == p->F_out),
+                 "aero_norm_act_fwd: per-row scope needs groups=1 and no crop");
+    AERO_REQUIRE(p->f_off >= 0 && p->f_off + p->F_out <= p->F_in, "aero_norm_act_fwd: crop out of range");
+    const bool glu = (p->op == AERO_NA_GLU || p->op == AERO_NA_GLU_SCALE_RES);
+    AERO_REQUIRE(!glu || p->C % 8 == 0, "aero_norm_act_fwd: GLU needs C %% 8 == 0");
+    AERO_REQUIRE(p->op != AERO_NA_SNAKE || snake_a, "aero_norm_act_fwd: snake needs a[]");
+    AERO_REQUIRE(p->op != AERO_NA_GLU_SCALE_RES || (scale && residual), "aero_norm_act_fwd: missing scale/residual");
+    const int Cout = glu ? p->C / 2 : p->C;
+    const int64_t seg4 = (p->scope == 1 ? (int64_t)p->F_out * p->T : (int64_t)p->T) * (Cout / 4);
+    const int nseg = p->scope == 1 ? p->B : p->B * p->F_in;
+    int chunks = (int)((seg4 + 256 * 4 - 1) / (256 * 4));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    dim3 grid(nseg, chunks);
+    cudaStream_t st = (cudaStream_t)stream;
+#define AERO_NA_LAUNCH(OP) norm_act_kernel<OP><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, residual, y, *p, seg4)
+    switch (p->op) {
+        case AERO_NA_NONE: AERO_NA_LAUNCH(AERO_NA_NONE); break;
+        case AERO_NA_GELU: AERO_NA_LAUNCH(AERO_NA_GELU); break;
+        case AERO_NA_GLU: AERO_NA_LAUNCH(AERO_NA_GLU); break;
+        case AERO_NA_SNAKE: AERO_NA_LAUNCH(AERO_NA_SNAKE); break;
+        case AERO_NA_GLU_SCALE_RES: AERO_NA_LAUNCH(AERO_NA_GLU_SCALE_RES); break;
+        default: set_error("aero_norm_act_fwd: op=%d", p->op); return AERO_ERR_INVALID;
+    }
+#undef AERO_NA_LAUNCH
+    return check_launch("aero_norm_act_fwd");
+}

@@ -1,0 +1,236 @@
+// Tap-GEMM, fp32 SIMT implementation (exact-fp32 accumulate; the parity anchor and the fallback
+// for shapes the tcgen05 path does not take).  See include/aero_b200.h for the operator contract.
+//
+// Tile: BM pixels (consecutive t inside one (b, f_out) row) x BN output columns, K consumed in
+// chunks of 16 channels per tap; 256 threads, TM x TN register tile per thread.
+#include "tapgemm.cuh"
+
+namespace aero {
+
+constexpr int kBK = 16;
+
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(const TapGemmArgs g) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int TX = BN / TN;
+    static_assert(NT == 256, "tile shape must give 256 threads");
+    __shared__ __align__(16) float As[kBK][BM + 4];
+    __shared__ __align__(16) float Bs[kBK][BN + 4];
+    __shared__ double sred[NT / 32][8][2];
+
+    const aero_tapgemm_params& p = g.p;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int tile = blockIdx.x;
+    const int tt = tile % g.tiles_t;
+    const int row = tile / g.tiles_t;
+    const int fo = row % p.F_out;
+    const int b = row / p.F_out;
+    const int t0 = tt * BM;
+    const int n0 = blockIdx.y * BN;
+    const int K = p.C1 + p.C2;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const float* wb = g.w + (int64_t)b * p.w_sb;
+
+    for (int tap = 0; tap < g.ntaps; ++tap) {
+        int fi, dt, slab;
+        if (p.mode == AERO_TAPS_CONV) {
+            const int jf = tap / p.kt, jt = tap - jf * p.kt;
+            fi = fo * p.stride_f + jf - p.pad_f;
+            dt = jt * p.dil_t - p.pad_t;
+            slab = tap;
+        } else {
+            const int fof = fo + p.f_out_offset;
+            const int kidx = fof % p.stride_f + tap * p.stride_f;
+            fi = fof / p.stride_f - tap;
+            dt = 0;
+            slab = kidx;
+        }
+        if (fi < 0 || fi >= p.F_in) continue;          // uniform across the CTA
+        const float* s1 = g.a1 ? g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf : nullptr;
+        const float* s2 = g.a2 ? g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf : nullptr;
+        const float* wslab = wb + (int64_t)slab * K * g.ldw;
+
+        for (int kc = 0; kc < K; kc += kBK) {
+            // ---- A tile: BM x 16, thread loads 4 consecutive channels of (BM*16/4)/256 pixels
+#pragma unroll
+            for (int it = 0; it < (BM * kBK / 4) / NT; ++it) {
+                const int e = tid + it * NT;
+                const int m = e >> 2, c4 = (e & 3) * 4;
+                const int ti = t0 + m + dt;
+                const int c = kc + c4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ti >= 0 && ti < p.T_in && (t0 + m) < p.T) {
+                    if (g.vec_a && c + 3 < p.C1) {
+                        const float4 q = *reinterpret_cast<const float4*>(s1 + (int64_t)ti * p.a1_st + c);
+                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    } else if (g.vec_a && c >= p.C1 && c + 3 < K) {
+                        const float4 q = *reinterpret_cast<const float4*>(s2 + (int64_t)ti * p.a2_st + (c - p.C1));
+                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int cc = c + u;
+                            if (cc < p.C1) v[u] = s1[(int64_t)ti * p.a1_st + cc];
+                            else if (cc < K) v[u] = s2[(int64_t)ti * p.a2_st + (cc - p.C1)];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) As[c4 + u][m] = v[u];
+            }
+            // ---- W tile: 16 x BN
+#pragma unroll
+            for (int it = 0; it < (kBK * BN / 4 + NT - 1) / NT; ++it) {
+                const int e = tid + it * NT;
+                if (e < kBK * BN / 4) {
+                    const int kk = e / (BN / 4), n4 = (e % (BN / 4)) * 4;
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kc + kk < K && n0 + n4 < g.ldw)
+                        q = *reinterpret_cast<const float4*>(wslab + (int64_t)(kc + kk) * g.ldw + n0 + n4);
+                    *reinterpret_cast<float4*>(&Bs[kk][n4]) = q;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < kBK; ++kk) {
+                float a[TM], bb[TN];
+#pragma unroll
+                for (int i = 0; i < TM; i += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+                    a[i] = q.x; a[i + 1] = q.y; a[i + 2] = q.z; a[i + 3] = q.w;
+                }
+                if (TN >= 4) {
+#pragma unroll
+                    for (int j = 0; j < TN; j += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
+                        bb[j] = q.x; bb[j + 1] = q.y; bb[j + 2] = q.z; bb[j + 3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) bb[j] = Bs[kk][tx * TN + j];
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ------------------------------------------------------------------ epilogue
+    const int Nout = p.glu ? p.N / 2 : p.N;
+    constexpr int TNO_MAX = TN;
+    float ssum = 0.f, ssq = 0.f;
+    const int gw = (p.stats_mode == 1) ? Nout / p.groups : Nout;
+    float sa = 1.f, sb = 0.f;
+    if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int t = t0 + ty * TM + i;
+        if (t >= p.T) continue;
+        float v[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            float x = acc[i][j];
+            if (n < p.N) {
+                if (g.bias) x += g.bias[n];
+                if (g.colscale) x *= g.colscale[(int64_t)b * p.cs_sb + (int64_t)t * p.cs_st + n];
+                if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+            }
+            v[j] = x;
+        }
+        float o[TNO_MAX];
+        int no0, cnt;
+        if (p.glu) {
+            // TN is even whenever glu is requested (host checks): pairs (2j, 2j+1)
+            no0 = (n0 + tx * TN) >> 1;
+            cnt = TN / 2;
+#pragma unroll
+            for (int j = 0; j < TN / 2; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
+        } else {
+            no0 = n0 + tx * TN;
+            cnt = TN;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) o[j] = v[j];
+        }
+        float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+        const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+#pragma unroll
+        for (int j = 0; j < TNO_MAX; ++j) {
+            if (j < cnt && no0 + j < Nout) {
+                float x = o[j];
+                if (g.addend_fn) x += g.addend_fn[(int64_t)fo * Nout + no0 + j];
+                if (rp) x += rp[no0 + j];
+                x = x * sa + sb;
+                o[j] = x;
+                ssum += x;
+                ssq += x * x;
+            }
+        }
+        if (g.vec_o && !p.glu && TN == 4 && no0 + 3 < Nout) {
+            *reinterpret_cast<float4*>(op + no0) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < TNO_MAX; ++j)
+                if (j < cnt && no0 + j < Nout) op[no0 + j] = o[j];
+        }
+    }
+
+    if (p.stats_mode != 0 && g.stats != nullptr) {
+        // all columns of a thread fall in one group (host guarantees gw % TN' == 0)
+        const int no_first = p.glu ? (n0 + tx * TN) >> 1 : n0 + tx * TN;
+        const int my_g = no_first < Nout ? no_first / gw : -1;
+        const int g_lo = (p.glu ? n0 >> 1 : n0) / gw;
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const float s = (my_g == g_lo + q) ? ssum : 0.f;
+            const float s2 = (my_g == g_lo + q) ? ssq : 0.f;
+            const double ds = warp_sum((double)s), dq = warp_sum((double)s2);
+            if (lane == 0) { sred[warp][q][0] = ds; sred[warp][q][1] = dq; }
+        }
+        __syncthreads();
+        if (tid < 8) {
+            double a = 0, c = 0;
+            for (int w = 0; w < NT / 32; ++w) { a += sred[w][tid][0]; c += sred[w][tid][1]; }
+            const int gi = g_lo + tid;
+            const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
+            if (gi < ngroups && (a != 0.0 || c != 0.0)) {
+                const int64_t slot = (p.stats_mode == 1) ? ((int64_t)b * p.groups + gi) : ((int64_t)b * p.F_out + fo);
+                atomicAdd(&g.stats[2 * slot], a);
+                atomicAdd(&g.stats[2 * slot + 1], c);
+            }
+        }
+    }
+}
+
+int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
+    const aero_tapgemm_params& p = g.p;
+    TapGemmArgs a = g;
+    const bool thin = p.N <= 16;
+    const int BM = 128;
+    a.tiles_t = cdiv(p.T, BM);
+    const int64_t tiles = (int64_t)p.B * p.F_out * a.tiles_t;
+    if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
+    if (thin) {
+        dim3 grid((unsigned)tiles, cdiv(p.N, 16));
+        tapgemm_simt_kernel<128, 16, 8, 1><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid((unsigned)tiles, cdiv(p.N, 64));
+        tapgemm_simt_kernel<128, 64, 8, 4><<<grid, 256, 0, st>>>(a);
+    }
+    return check_launch("aero_tapgemm_fwd(simt)");
+}
+
+}  // namespace aero

@@ -1,0 +1,520 @@
+"""Host side of the AERO forward: weight packing and the kernel launch sequence.
+
+Mirrors the control flow of reference ``src/models/aero.py:446-523`` (``Aero.forward``),
+``:108-135`` (``HEncLayer.forward``), ``:189-215`` (``HDecLayer.forward``) and
+``src/models/modules.py`` (``FTB`` 304-325, ``DConv`` 221-249, ``BLSTM`` 32-65, ``LocalState``
+94-127), but every arithmetic step is a call into libaero_b200.so through the C ABI
+(``include/aero_b200.h``).  PyTorch is used for device memory and the stream only.
+
+Layout: activations are channels-last ``[B, F, T, C]``; see DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import cabi
+from .cabi import (ACT_GELU, ACT_NONE, ACT_RELU, NA_GELU, NA_GLU, NA_GLU_SCALE_RES, NA_SNAKE, TAPS_CONV,
+                   TAPS_CONVT)
+
+_LSTM_MAX_STEPS = 200      # reference modules.py:215 BLSTM(..., max_steps=200)
+_ATTN_HEADS, _ATTN_NDECAY = 4, 4   # reference modules.py:154 DConv(heads=4, ndecay=4)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _pad4(n):
+    return (n + 3) & ~3
+
+
+def pack_taps(w_nkt):
+    """[N, K, taps] -> contiguous [taps, K, pad4(N)] (N contiguous: the tap-GEMM weight layout)."""
+    n, k, taps = w_nkt.shape
+    out = w_nkt.new_zeros(taps, k, _pad4(n))
+    out[:, :, :n] = w_nkt.permute(2, 1, 0)
+    return out.contiguous()
+
+
+def glu_perm(n, device):
+    """Column order that puts GLU partners (j, j + n/2) next to each other."""
+    half = n // 2
+    return torch.stack([torch.arange(half, device=device), torch.arange(half, device=device) + half], 1).reshape(-1)
+
+
+class _Stats:
+    """Bump allocator over one fp64 buffer of {sum, sumsq} pairs, zeroed once per forward."""
+
+    def __init__(self, device, capacity=1 << 16):
+        self.buf = torch.zeros(capacity, 2, dtype=torch.float64, device=device)
+        self.used = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.used = 0
+
+    def take(self, slots):
+        if self.used + slots > self.buf.shape[0]:
+            raise RuntimeError("aero_b200: statistics workspace too small; raise _Stats capacity")
+        view = self.buf[self.used:self.used + slots]
+        self.used += slots
+        return view
+
+
+class AeroEngine:
+    def __init__(self, model):
+        self.model = model
+        self.geom = model.geom
+        self.lib = cabi.load()
+        self._packed = None
+        self._packed_key = None
+        self._bufs = {}
+        self._windows = {}
+        self._stats = None
+        self.precision = 0          # 0: fp32 SIMT tap-GEMM; 1: TF32 tcgen05 where eligible
+
+    # ------------------------------------------------------------------ plumbing
+    def invalidate(self):
+        self._packed = None
+        self._bufs = {}
+
+    def _device(self):
+        return next(self.model.parameters()).device
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _require(self, x):
+        dev = self._device()
+        if dev.type != "cuda" or not x.is_cuda:
+            raise RuntimeError(
+                "aero_b200.Aero runs on CUDA only (sm_100a kernels in libaero_b200.so); there is no CPU path. "
+                f"model on {dev}, input on {x.device}")
+        if x.device != dev:
+            raise RuntimeError(f"input on {x.device} but model on {dev}")
+        if x.dtype != torch.float32:
+            raise TypeError(f"aero_b200 computes in fp32; got {x.dtype}")
+
+    def _buf(self, name, *shape):
+        key = (name, shape)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.float32, device=self._device())
+            self._bufs[key] = t
+        return t
+
+    def _window(self, win):
+        key = (win, self._device())
+        w = self._windows.get(key)
+        if w is None:
+            # computed on the host in fp32 exactly as reference spec.py:15 does, then moved
+            w = torch.hann_window(win).to(self._device())
+            self._windows[key] = w
+        return w
+
+    def _weights(self):
+        key = tuple(p._version for p in self.model.parameters()) + tuple(b._version for b in self.model.buffers())
+        if self._packed is None or key != self._packed_key:
+            self._packed = self._pack()
+            self._packed_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ weight packing
+    @torch.no_grad()
+    def _pack(self):
+        sd = {k: v.detach() for k, v in self.model.state_dict().items()}
+        dev = self._device()
+        kw = self.geom.kw
+        W = {}
+
+        def fold_bn(w_nk, b, bn):
+            s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
+            return w_nk * s.view(-1, *([1] * (w_nk.dim() - 1))), (b - sd[bn + ".running_mean"]) * s + sd[bn + ".bias"]
+
+        for g in self.geom.layers:
+            p = f"encoder.{g.index}"
+            cin = g.enc_cin
+            if g.index == 0:
+                W[p + ".pre.w"] = pack_taps(sd[p + ".pre_conv.weight"][:, :, 0, 0][:, :, None])
+                W[p + ".pre.b"] = sd[p + ".pre_conv.bias"].contiguous()
+                cin = g.ch
+            if g.ftb:
+                q = p + ".freq_attn_block"
+                Fi = g.f_in
+                w, b = fold_bn(sd[q + ".conv1.0.weight"][:, :, 0, 0], sd[q + ".conv1.0.bias"], q + ".conv1.1")
+                W[p + ".ftb1.w"], W[p + ".ftb1.b"] = pack_taps(w[:, :, None]), b.contiguous()
+                r = w.shape[0]
+                w1d = sd[q + ".conv1d.0.weight"]                              # [C, r*F, 9], channel = j*F + f
+                w1d = w1d.view(cin, r, Fi, 9).permute(0, 2, 1, 3).reshape(cin, Fi * r, 9)   # -> f*r + j
+                w, b = fold_bn(w1d, sd[q + ".conv1d.0.bias"], q + ".conv1d.1")
+                W[p + ".ftb1d.w"], W[p + ".ftb1d.b"] = pack_taps(w), b.contiguous()
+                W[p + ".ftbfc.w"] = sd[q + ".freq_fc.weight"].contiguous()
+                w, b = fold_bn(sd[q + ".conv2.0.weight"][:, :, 0, 0], sd[q + ".conv2.0.bias"], q + ".conv2.1")
+                W[p + ".ftb2.w"], W[p + ".ftb2.b"] = pack_taps(w[:, :, None]), b.contiguous()
+            W[p + ".conv.w"] = pack_taps(sd[p + ".conv.weight"][:, :, :, 0])
+            W[p + ".conv.b"] = sd[p + ".conv.bias"].contiguous()
+            wr, br = sd[p + ".rewrite.weight"][:, :, 0, 0], sd[p + ".rewrite.bias"]
+            if g.norm:
+                for nm in ("norm1", "norm2"):
+                    W[f"{p}.{nm}.g"], W[f"{p}.{nm}.b"] = sd[f"{p}.{nm}.weight"].contiguous(), sd[f"{p}.{nm}.bias"].contiguous()
+            else:
+                perm = glu_perm(wr.shape[0], dev)
+                wr, br = wr[perm], br[perm]
+            W[p + ".rw.w"], W[p + ".rw.b"] = pack_taps(wr[:, :, None]), br.contiguous()
+            if g.index == 0 and kw["freq_emb"]:
+                W["emb"] = (sd["freq_emb.embedding.weight"] * (kw["emb_scale"] * kw["freq_emb"])).contiguous()
+            if g.dconv:
+                for d in range(kw["dconv_depth"]):
+                    q = f"{p}.dconv.layers.{d}"
+                    o = f"{p}.dc{d}"
+                    W[o + ".c1.w"], W[o + ".c1.b"] = pack_taps(sd[q + ".conv1.0.weight"]), sd[q + ".conv1.0.bias"].contiguous()
+                    W[o + ".n1.g"], W[o + ".n1.b"] = sd[q + ".conv1.1.weight"].contiguous(), sd[q + ".conv1.1.bias"].contiguous()
+                    W[o + ".a"] = sd[q + ".act.a"].reshape(-1).contiguous()
+                    W[o + ".c2.w"], W[o + ".c2.b"] = pack_taps(sd[q + ".conv2.0.weight"]), sd[q + ".conv2.0.bias"].contiguous()
+                    W[o + ".n2.g"], W[o + ".n2.b"] = sd[q + ".conv2.1.weight"].contiguous(), sd[q + ".conv2.1.bias"].contiguous()
+                    W[o + ".ls"] = sd[q + ".conv2.3.scale"].contiguous()
+                    if g.lstm:
+                        for l in range(2):
+                            wih = torch.cat([sd[f"{q}.lstm.lstm.weight_ih_l{l}"], sd[f"{q}.lstm.lstm.weight_ih_l{l}_reverse"]], 0)
+                            W[f"{o}.lstm{l}.wih"] = pack_taps(wih[:, :, None])
+                            W[f"{o}.lstm{l}.b"] = torch.cat([
+                                sd[f"{q}.lstm.lstm.bias_ih_l{l}"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}"],
+                                sd[f"{q}.lstm.lstm.bias_ih_l{l}_reverse"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}_reverse"]]).contiguous()
+                            W[f"{o}.lstm{l}.whh"] = torch.stack([sd[f"{q}.lstm.lstm.weight_hh_l{l}"],
+                                                                  sd[f"{q}.lstm.lstm.weight_hh_l{l}_reverse"]]).contiguous()
+                        W[o + ".lin.w"] = pack_taps(sd[q + ".lstm.linear.weight"][:, :, None])
+                        W[o + ".lin.b"] = sd[q + ".lstm.linear.bias"].contiguous()
+                    if g.attn:
+                        a = q + ".time_attn"
+                        names = ("query", "key", "content", "query_decay")
+                        W[o + ".qkvd.w"] = pack_taps(torch.cat([sd[f"{a}.{n}.weight"] for n in names], 0))
+                        W[o + ".qkvd.b"] = torch.cat([sd[f"{a}.{n}.bias"] for n in names]).contiguous()
+                        W[o + ".proj.w"] = pack_taps(sd[a + ".proj.weight"])
+                        W[o + ".proj.b"] = sd[a + ".proj.bias"].contiguous()
+
+        for j, g in enumerate(reversed(self.geom.layers)):
+            p = f"decoder.{j}"
+            wr, br = sd[p + ".rewrite.weight"], sd[p + ".rewrite.bias"]       # [4ch, 2ch, 3, 3]
+            wr = wr.reshape(wr.shape[0], wr.shape[1], -1)
+            if j == 0:
+                wr = wr[:, g.ch:]          # decoder input starts at zero (aero.py:484): keep the skip half only
+            if g.norm:
+                for nm in ("norm1", "norm2"):
+                    W[f"{p}.{nm}.g"], W[f"{p}.{nm}.b"] = sd[f"{p}.{nm}.weight"].contiguous(), sd[f"{p}.{nm}.bias"].contiguous()
+            else:
+                perm = glu_perm(wr.shape[0], dev)
+                wr, br = wr[perm], br[perm]
+            W[p + ".rw.w"], W[p + ".rw.b"] = pack_taps(wr), br.contiguous()
+            W[p + ".ct.w"] = pack_taps(sd[p + ".conv_tr.weight"][:, :, :, 0].permute(1, 0, 2))
+            W[p + ".ct.b"] = sd[p + ".conv_tr.bias"].contiguous()
+        return {k: v.to(device=dev, dtype=torch.float32) for k, v in W.items()}
+
+    # ------------------------------------------------------------------ kernel wrappers
+    def _gemm(self, out, w, *, B, F_out, T, N, C1, a1=None, a2=None, C2=0, F_in=None, T_in=None,
+              a1_s=None, a2_s=None, o_s=None, mode=TAPS_CONV, kf=1, kt=1, stride_f=1, pad_f=0, dil_t=1, pad_t=0,
+              f_off=0, bias=None, act=ACT_NONE, glu=0, stats=None, stats_mode=0, groups=1, addend=None,
+              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0):
+        F_in = F_out if F_in is None else F_in
+        T_in = T if T_in is None else T_in
+        n_out = N // 2 if glu else N
+
+        def cl(F, C_):
+            return (F * T_in * C_, T_in * C_, C_)
+        a1_s = a1_s or (cl(F_in, C1) if a1 is not None else (0, 0, 0))
+        a2_s = a2_s or (cl(F_in, C2) if a2 is not None else (0, 0, 0))
+        o_s = o_s or (F_out * T * n_out, T * n_out, n_out)
+        r_s = r_s or (o_s if residual is not None else (0, 0, 0))
+        p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
+                               act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, self.precision, 0)
+        rc = self.lib.aero_tapgemm_fwd(_ptr(a1), _ptr(a2), _ptr(w), _ptr(bias), _ptr(addend), _ptr(colscale),
+                                       _ptr(residual), _ptr(samp_affine), _ptr(out), _ptr(stats), C.byref(p),
+                                       self._stream())
+        cabi.check(rc, self.lib)
+        return out
+
+    def _gemm_flat(self, out, a, w, npix, K, N, **kw):
+        """1x1 layer over `npix` independent pixels (any leading shape flattened)."""
+        return self._gemm(out, w, a1=a, B=1, F_out=1, T=npix, N=N, C1=K, **kw)
+
+    def _norm_act(self, x, stats, gamma, beta, y, *, B, F_in, T, C_, groups, scope, op, F_out=None, f_off=0,
+                  snake_a=None, scale=None, residual=None):
+        p = cabi.NormActParams(B, F_in, F_in if F_out is None else F_out, f_off, T, C_, groups, scope, op, 1e-5)
+        rc = self.lib.aero_norm_act_fwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(snake_a), _ptr(scale),
+                                        _ptr(residual), _ptr(y), C.byref(p), self._stream())
+        cabi.check(rc, self.lib)
+        return y
+
+    def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed):
+        p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed)
+        cabi.check(self.lib.aero_lstm_rec_fwd(_ptr(gin), _ptr(bias_pad), _ptr(whh), _ptr(hout), C.byref(p),
+                                              self._stream()), self.lib)
+
+    def _attn(self, qkvd, out, *, rows, T, H, heads, ndecay, ld):
+        p = cabi.AttnParams(rows, T, H, heads, ndecay, ld)
+        cabi.check(self.lib.aero_local_attn_fwd(_ptr(qkvd), _ptr(out), C.byref(p), self._stream()), self.lib)
+
+    def _sample_norm(self, x, stats, y, affine, B, per_sample):
+        cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample,
+                                                 self._stream()), self.lib)
+
+    def stft_into(self, x, z, stats, *, n_fft, hop, win, channels, bins_out, strides):
+        n_sig, length = x.shape[0], x.shape[1]
+        frames = 1 + length // hop
+        p = cabi.StftParams(n_fft, hop, win, n_sig, channels, length, frames, bins_out, *strides)
+        rc = self.lib.aero_stft_fwd(_ptr(x), _ptr(self._window(win)), _ptr(z), _ptr(stats), C.byref(p), self._stream())
+        cabi.check(rc, self.lib)
+
+    def istft_into(self, z, y, *, n_fft, hop, win, channels, frames, bins_in, strides):
+        n_sig, out_len = y.shape
+        p = cabi.IstftParams(n_fft, hop, win, n_sig, channels, frames, bins_in, out_len, *strides)
+        rc = self.lib.aero_istft_fwd(_ptr(z), _ptr(self._window(win)), _ptr(y), C.byref(p), self._stream())
+        cabi.check(rc, self.lib)
+
+    # ------------------------------------------------------------------ public pieces
+    @torch.no_grad()
+    def spec(self, x, scale=False):
+        """reference aero.py:409-421 -> complex [..., nfft/2, frames]."""
+        self._require(x)
+        g = self.geom
+        *lead, length = x.shape
+        hop = g.hop_in
+        if length % hop:
+            x = torch.nn.functional.pad(x, (0, hop - length % hop))
+        hl, win = (g.hop_out, g.win_out) if scale else (hop, g.win_in)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        bins = g.nfft // 2
+        frames = 1 + x2.shape[1] // hl
+        z = torch.empty(x2.shape[0], bins, frames, 2, dtype=torch.float32, device=x.device)
+        self.stft_into(x2, z, None, n_fft=g.nfft, hop=hl, win=win, channels=1, bins_out=bins,
+                       strides=(bins * frames * 2, 0, frames * 2, 2))
+        return torch.view_as_complex(z).view(*lead, bins, frames)
+
+    @torch.no_grad()
+    def ispec(self, zc):
+        """reference aero.py:423-428: complex [..., nfft/2, frames] -> [..., hop_out*(frames-1)]."""
+        g = self.geom
+        *lead, bins, frames = zc.shape
+        z = torch.view_as_real(zc.reshape(-1, bins, frames).contiguous())
+        self._require(z)
+        y = torch.empty(z.shape[0], g.hop_out * (frames - 1), dtype=torch.float32, device=z.device)
+        self.istft_into(z, y, n_fft=g.nfft, hop=g.hop_out, win=g.win_out, channels=1, frames=frames, bins_in=bins,
+                        strides=(bins * frames * 2, 0, frames * 2, 2))
+        return y.view(*lead, y.shape[-1])
+
+    # ------------------------------------------------------------------ blocks
+    def _ftb(self, x, W, p, B, Fq, T, Cc, tag):
+        """reference modules.py:304-325 (eval BatchNorm folded into the convs at pack time)."""
+        r = 5
+        R = self._buf(tag + ".R", B, T, Fq * r)
+        self._gemm(R, W[p + ".ftb1.w"], a1=x, B=B, F_out=Fq, T=T, N=r, C1=Cc, bias=W[p + ".ftb1.b"], act=ACT_RELU,
+                   o_s=(T * Fq * r, r, Fq * r))
+        G = self._buf(tag + ".G", B, T, Cc)
+        self._gemm(G, W[p + ".ftb1d.w"], a1=R, B=B, F_out=1, T=T, N=Cc, C1=Fq * r, kt=9, pad_t=4,
+                   bias=W[p + ".ftb1d.b"], act=ACT_RELU, a1_s=(T * Fq * r, 0, Fq * r), o_s=(T * Cc, 0, Cc))
+        Y = self._buf(tag + ".Y", B, Fq, T, Cc)
+        # frequency mixing as a GEMM whose "weights" are the activations: out[f'] = sum_f Wfc[f',f] x[f], times the gate
+        self._gemm(Y, x, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq, a1_s=(0, 0, Fq),
+                   w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0))
+        out = self._buf(tag + ".out", B, Fq, T, Cc)
+        self._gemm(out, W[p + ".ftb2.w"], a1=Y, a2=x, B=1, F_out=1, T=B * Fq * T, N=Cc, C1=Cc, C2=Cc,
+                   bias=W[p + ".ftb2.b"], act=ACT_RELU)
+        return out
+
+    def _blstm(self, h, W, o, rows, T, H, tag):
+        """reference modules.py:32-65: framing, 2-layer BiLSTM, Linear, central-crop reassembly, skip."""
+        if T > _LSTM_MAX_STEPS:
+            steps, stride = _LSTM_MAX_STEPS, _LSTM_MAX_STEPS // 2
+            n_win = math.ceil(T / stride)
+        else:
+            steps, stride, n_win = T, 0, 1
+        n_seq = rows * n_win
+        gin1 = self._buf(tag + ".gin1", rows * T, 8 * H)
+        self._gemm_flat(gin1, h, W[o + ".lstm0.wih"], rows * T, H, 8 * H, bias=W[o + ".lstm0.b"])
+        h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H)
+        self._lstm_rec(gin1, W[o + ".lstm0.b"], W[o + ".lstm0.whh"], h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+                       stride=stride, in_windowed=0, out_windowed=1)
+        gin2 = self._buf(tag + ".gin2", n_seq * steps, 8 * H)
+        self._gemm_flat(gin2, h1, W[o + ".lstm1.wih"], n_seq * steps, 2 * H, 8 * H, bias=W[o + ".lstm1.b"])
+        h2 = self._buf(tag + ".h2", rows * T, 2 * H)
+        self._lstm_rec(gin2, W[o + ".lstm1.b"], W[o + ".lstm1.whh"], h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+                       stride=stride, in_windowed=1, out_windowed=0)
+        self._gemm_flat(h, h2, W[o + ".lin.w"], rows * T, 2 * H, H, bias=W[o + ".lin.b"], residual=h)
+        return h
+
+    def _local_attn(self, h, W, o, rows, T, H, tag):
+        """reference modules.py:94-127."""
+        ld = 3 * H + _ATTN_HEADS * _ATTN_NDECAY
+        qkvd = self._buf(tag + ".qkvd", rows * T, ld)
+        self._gemm_flat(qkvd, h, W[o + ".qkvd.w"], rows * T, H, ld, bias=W[o + ".qkvd.b"])
+        r = self._buf(tag + ".attn", rows * T, H)
+        self._attn(qkvd, r, rows=rows, T=T, H=H, heads=_ATTN_HEADS, ndecay=_ATTN_NDECAY, ld=ld)
+        self._gemm_flat(h, r, W[o + ".proj.w"], rows * T, H, H, bias=W[o + ".proj.b"], residual=h)
+        return h
+
+    def _dconv(self, y, W, g, B, T, tag):
+        """reference modules.py:221-249; rows are (b, f) pairs, which is just our memory order."""
+        kw = self.geom.kw
+        Fq, Cc = g.f_out, g.ch
+        hid = int(Cc / kw["dconv_comp"])
+        rows = B * Fq
+        for d in range(kw["dconv_depth"]):
+            o = f"encoder.{g.index}.dc{d}"
+            dil = 2 ** d
+            st1 = self._stats.take(rows)
+            h = self._buf(f"{tag}.h", B, Fq, T, hid)
+            self._gemm(h, W[o + ".c1.w"], a1=y, B=B, F_out=Fq, T=T, N=hid, C1=Cc, kt=3, dil_t=dil, pad_t=dil,
+                       bias=W[o + ".c1.b"], stats=st1, stats_mode=2)
+            self._norm_act(h, st1, W[o + ".n1.g"], W[o + ".n1.b"], h, B=B, F_in=Fq, T=T, C_=hid, groups=1, scope=2,
+                           op=NA_SNAKE, snake_a=W[o + ".a"])
+            if g.lstm:
+                self._blstm(h, W, o, rows, T, hid, f"{tag}.lstm")
+            if g.attn:
+                self._local_attn(h, W, o, rows, T, hid, f"{tag}.attn")
+            st2 = self._stats.take(rows)
+            u = self._buf(f"{tag}.u", B, Fq, T, 2 * Cc)
+            self._gemm(u, W[o + ".c2.w"], a1=h, B=B, F_out=Fq, T=T, N=2 * Cc, C1=hid, bias=W[o + ".c2.b"],
+                       stats=st2, stats_mode=2)
+            self._norm_act(u, st2, W[o + ".n2.g"], W[o + ".n2.b"], y, B=B, F_in=Fq, T=T, C_=2 * Cc, groups=1, scope=2,
+                           op=NA_GLU_SCALE_RES, scale=W[o + ".ls"], residual=y)
+        return y
+
+    def _encode(self, x, W, g, B, T):
+        """reference aero.py:108-135 (+ the frequency-embedding add aero.py:475-480 for layer 0)."""
+        kw = self.geom.kw
+        p = f"encoder.{g.index}"
+        tag = f"e{g.index}"
+        Fi, Fo, Cc = g.f_in, g.f_out, g.ch
+        cin = g.enc_cin
+        if g.index == 0:
+            pre = self._buf(tag + ".pre", B, Fi, T, Cc)
+            self._gemm_flat(pre, x, W[p + ".pre.w"], B * Fi * T, cin, Cc, bias=W[p + ".pre.b"])
+            x, cin = pre, Cc
+        if g.ftb:
+            x = self._ftb(x, W, p, B, Fi, T, cin, tag + ".ftb")
+        y = self._buf(tag + ".conv", B, Fo, T, Cc)
+        if g.norm:
+            st = self._stats.take(B * kw["norm_groups"])
+            self._gemm(y, W[p + ".conv.w"], a1=x, B=B, F_out=Fo, F_in=Fi, T=T, N=Cc, C1=cin, kf=g.kernel,
+                       stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], stats=st, stats_mode=1,
+                       groups=kw["norm_groups"])
+            self._norm_act(y, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fo, T=T, C_=Cc,
+                           groups=kw["norm_groups"], scope=1, op=NA_GELU)
+        else:
+            self._gemm(y, W[p + ".conv.w"], a1=x, B=B, F_out=Fo, F_in=Fi, T=T, N=Cc, C1=cin, kf=g.kernel,
+                       stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], act=ACT_GELU)
+        if g.dconv:
+            y = self._dconv(y, W, g, B, T, tag + ".dc")
+        out = self._buf(tag + ".out", B, Fo, T, Cc)
+        if g.norm:
+            st = self._stats.take(B * kw["norm_groups"])
+            raw = self._buf(tag + ".rw", B, Fo, T, 2 * Cc)
+            self._gemm(raw, W[p + ".rw.w"], a1=y, B=B, F_out=Fo, T=T, N=2 * Cc, C1=Cc, bias=W[p + ".rw.b"],
+                       stats=st, stats_mode=1, groups=kw["norm_groups"])
+            self._norm_act(raw, st, W[p + ".norm2.g"], W[p + ".norm2.b"], out, B=B, F_in=Fo, T=T, C_=2 * Cc,
+                           groups=kw["norm_groups"], scope=1, op=NA_GLU)
+        else:
+            self._gemm(out, W[p + ".rw.w"], a1=y, B=B, F_out=Fo, T=T, N=2 * Cc, C1=Cc, bias=W[p + ".rw.b"], glu=1,
+                       addend=W.get("emb") if g.index == 0 else None)
+        return out
+
+    def _decode(self, x, skip, W, g, j, B, T, last, samp_affine):
+        """reference aero.py:189-215."""
+        kw = self.geom.kw
+        p = f"decoder.{j}"
+        tag = f"d{j}"
+        Fq, Cc = g.f_out, g.ch
+        c1 = 0 if x is None else Cc
+        y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc)
+        common = dict(a1=x, a2=skip, B=B, F_out=Fq, T=T, N=4 * Cc, C1=c1, C2=Cc, kf=3, kt=3, pad_f=1, pad_t=1,
+                      bias=W[p + ".rw.b"])
+        if g.norm:
+            st = self._stats.take(B * kw["norm_groups"])
+            raw = self._buf(tag + ".rw", B, Fq, T, 4 * Cc)
+            self._gemm(raw, W[p + ".rw.w"], stats=st, stats_mode=1, groups=kw["norm_groups"], **common)
+            self._norm_act(raw, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fq, T=T, C_=4 * Cc,
+                           groups=kw["norm_groups"], scope=1, op=NA_GLU)
+        else:
+            self._gemm(y, W[p + ".rw.w"], glu=1, **common)
+        cout = g.dec_cout
+        f_full = (Fq - 1) * g.stride + g.kernel
+        f_keep = f_full - 2 * g.pad
+        z = self._buf(tag + ".out", B, f_keep, T, cout)
+        if g.norm:
+            st = self._stats.take(B * kw["norm_groups"])
+            raw = self._buf(tag + ".ct", B, f_full, T, cout)
+            self._gemm(raw, W[p + ".ct.w"], a1=y, B=B, F_out=f_full, F_in=Fq, T=T, N=cout, C1=2 * Cc, mode=TAPS_CONVT,
+                       kf=g.kernel, stride_f=g.stride, bias=W[p + ".ct.b"], stats=st, stats_mode=1,
+                       groups=kw["norm_groups"])
+            self._norm_act(raw, st, W[p + ".norm2.g"], W[p + ".norm2.b"], z, B=B, F_in=f_full, F_out=f_keep,
+                           f_off=g.pad, T=T, C_=cout, groups=kw["norm_groups"], scope=1,
+                           op=cabi.NA_NONE if last else NA_GELU)
+            if last and samp_affine is not None:
+                raise NotImplementedError("GroupNorm on the last decoder layer (norm_starts=0) is not supported")
+        else:
+            self._gemm(z, W[p + ".ct.w"], a1=y, B=B, F_out=f_keep, F_in=Fq, T=T, N=cout, C1=2 * Cc, mode=TAPS_CONVT,
+                       kf=g.kernel, stride_f=g.stride, f_off=g.pad, bias=W[p + ".ct.b"],
+                       act=ACT_NONE if last else ACT_GELU, samp_affine=samp_affine if last else None)
+        return z
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, mix, return_spec=False, return_lr_spec=False):
+        model = self.model
+        self._require(mix)
+        if model.training:
+            raise NotImplementedError(
+                "aero_b200: the CUDA path implements the inference forward (eval-mode BatchNorm, no autograd); "
+                "call model.eval().  Training kernels are SURVEY.md section 8f 'next'.")
+        g = self.geom
+        kw = g.kw
+        if mix.dim() != 3 or mix.shape[1] != kw["in_channels"]:
+            raise ValueError(f"expected input [B, {kw['in_channels']}, L], got {tuple(mix.shape)}")
+        W = self._weights()
+        if self._stats is None or self._stats.buf.device != mix.device:
+            self._stats = _Stats(mix.device)
+        self._stats.reset()
+
+        B, Cin, length = mix.shape
+        x = mix.contiguous()
+        if length % g.hop_in:
+            x = torch.nn.functional.pad(x, (0, g.hop_in - length % g.hop_in))
+        Lp = x.shape[-1]
+        T = 1 + Lp // g.hop_in
+        Fq = g.nfft // 2
+        C2 = 2 * Cin
+
+        # STFT straight into channels-last [B, F, T, 2*Cin]; channel 2c+{0,1} = {re,im} (aero.py:430-434)
+        z = self._buf("z", B, Fq, T, C2)
+        st_in = self._stats.take(B)
+        self.stft_into(x.view(B * Cin, Lp), z, st_in, n_fft=g.nfft, hop=g.hop_in, win=g.win_in, channels=Cin,
+                       bins_out=Fq, strides=(Fq * T * C2, 2, T * C2, C2))
+        xn = self._buf("xn", B, Fq, T, C2)
+        affine = self._buf("affine", B, 2)
+        self._sample_norm(z, st_in, xn, affine, B, Fq * T * C2)
+        h = xn
+        saved = []
+        for lg in g.layers:
+            h = self._encode(h, W, lg, B, T)
+            saved.append(h)
+        h = None
+        for j, lg in enumerate(reversed(g.layers)):
+            last = lg.index == 0
+            h = self._decode(h, saved.pop(), W, lg, j, B, T, last, affine)
+        Cout = kw["out_channels"]
+        assert h.shape == (B, Fq, T, 2 * Cout), (h.shape, (B, Fq, T, 2 * Cout))
+
+        out_len = min(int(length * g.scale), g.hop_out * (T - 1))
+        y = torch.empty(B * Cout, out_len, dtype=torch.float32, device=mix.device)
+        self.istft_into(h, y, n_fft=g.nfft, hop=g.hop_out, win=g.win_out, channels=Cout, frames=T, bins_in=Fq,
+                        strides=(Fq * T * 2 * Cout, 2, T * 2 * Cout, 2 * Cout))
+        y = y.view(B, Cout, out_len)
+        if not return_spec:
+            return y
+        zc = torch.view_as_complex(h.clone().view(B, Fq, T, Cout, 2)).permute(0, 3, 1, 2)
+        if not return_lr_spec:
+            return y, zc
+        zl = torch.view_as_complex(z.clone().view(B, Fq, T, Cin, 2)).permute(0, 3, 1, 2)
+        return y, zc, zl

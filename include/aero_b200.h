@@ -1,0 +1,199 @@
+/*
+ * aero_b200.h -- C ABI of libaero_b200.so: the sm_100a kernels behind the AERO generator forward.
+ *
+ * The reference (slp-rl/aero) has no FFI: its hot path is the Python class
+ * src/models/aero.py:218 `Aero`, whose arithmetic is dispatched to PyTorch library kernels.
+ * Each entry point below replaces the library call(s) made at the cited reference lines.  A
+ * binding needs nothing but device pointers, plain-old-data parameter blocks and a CUDA stream:
+ * no ATen / Python types cross this boundary (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - All tensors are fp32, device memory, owned by the caller.  Kernels never allocate, never
+ *     synchronise, and enqueue on `stream` only; entry points are re-entrant per stream.
+ *   - Activations are channels-last: X[b][f][t][c] ("rows" (b,f) of T frames of C channels),
+ *     the natural layout for this model: complex64 [B,F,T] *is* [B,F,T,2].
+ *   - Return value: 0 on success, negative aero_status on error; aero_last_error() gives the
+ *     text for the calling thread.  Launch errors are reported, asynchronous faults surface at
+ *     the caller's next synchronisation.
+ *   - Statistics buffers are fp64 pairs {sum, sum of squares} accumulated with atomics; the
+ *     caller zeroes them (cudaMemsetAsync) before the producing call.
+ */
+#ifndef AERO_B200_H
+#define AERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* aero_stream_t; /* cudaStream_t */
+
+enum aero_status {
+    AERO_OK = 0,
+    AERO_ERR_INVALID = -1,   /* bad parameter block */
+    AERO_ERR_UNSUPPORTED = -2,
+    AERO_ERR_LAUNCH = -3,    /* cudaGetLastError() after launch */
+    AERO_ERR_NO_DEVICE = -4
+};
+
+int aero_abi_version(void);
+const char* aero_last_error(void);
+/* compute capability of the current device as 10*major+minor (100 on B200); <0 if no device */
+int aero_device_arch(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
+uint64_t aero_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * STFT  (replaces torch.stft at reference src/models/spec.py:12-20, called from aero.py:420,
+ *        plus the Nyquist drop aero.py:420 `[..., :-1, :]`, the complex->channels permute
+ *        aero.py:430-434 and the moments for aero.py:462-463)
+ * x      : [n_signals][length]           real input, n_signals = B * channels
+ * window : [win]                         analysis window (torch.hann_window(win), spec.py:15)
+ * z      : element (sig, k, t) is the float2 at  z + (sig / channels) * z_stride_b
+ *              + (sig % channels) * z_stride_c + k * z_stride_k + t * z_stride_t   (strides in floats)
+ * stats  : optional [B][2] fp64 {sum, sumsq} over every float written for batch item b
+ * Semantics: centre=True reflect padding of n_fft/2, window zero-padded (centred) to n_fft,
+ * normalized=True (x n_fft^-1/2), onesided; bins 0 .. bins_out-1 are written
+ * (bins_out = n_fft/2 drops Nyquist, n_fft/2+1 keeps it).  frames must equal 1 + length / hop.
+ */
+typedef struct {
+    int32_t n_fft, hop, win;
+    int32_t n_signals, channels;
+    int32_t length, frames, bins_out;
+    int64_t z_stride_b, z_stride_c, z_stride_k, z_stride_t;
+} aero_stft_params;
+int aero_stft_fwd(const float* x, const float* window, float* z, double* stats,
+                  const aero_stft_params* p, aero_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * iSTFT (replaces torch.istft at reference src/models/spec.py:30-37, called from aero.py:427,
+ *        plus the Nyquist zero-pad aero.py:426 and the trim aero.py:513)
+ * z addressing as above (bins_in bins present; bins above are taken as zero).
+ * y : [n_signals][out_len],  y[n] = OLA(irfft(z * sqrt(n_fft)) * window)[n + n_fft/2] / sum(window^2)
+ * out_len <= hop * (frames - 1).
+ */
+typedef struct {
+    int32_t n_fft, hop, win;
+    int32_t n_signals, channels;
+    int32_t frames, bins_in, out_len;
+    int64_t z_stride_b, z_stride_c, z_stride_k, z_stride_t;
+} aero_istft_params;
+int aero_istft_fwd(const float* z, const float* window, float* y,
+                   const aero_istft_params* p, aero_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-GEMM: every convolution / linear layer of the model as one implicit GEMM
+ *   acc[b][fo][t][n] = sum_{tap} sum_{c < C1+C2}  A(b, fi(tap,fo), ti(tap,t), c) * W[slab(tap,fo)][c][n]
+ * with A read from up to two channels-last sources (channel concat, reference aero.py:195
+ * `torch.cat([x, skip], 1)`); out-of-range fi / ti contribute zero (zero padding).
+ *   mode AERO_TAPS_CONV  : fi = fo*stride_f + jf - pad_f,  ti = t + jt*dil_t - pad_t,
+ *                          slab = jf*kt + jt                      (nn.Conv2d / nn.Conv1d / nn.Linear)
+ *   mode AERO_TAPS_CONVT : fo' = fo + f_out_offset (row in the uncropped output),
+ *                          jf in [0, kf/stride_f): kf_idx = fo' % stride_f + jf*stride_f,
+ *                          fi = fo' / stride_f - jf,  slab = kf_idx  (nn.ConvTranspose2d [k,1]/[s,1])
+ * Replaces nn.Conv2d/ConvTranspose2d (aero.py:89,95,101,172,179), nn.Conv1d (modules.py:80-92,
+ * 206,209,292), nn.Linear (modules.py:29,296) and their cuDNN/cuBLAS kernels.
+ *
+ * Epilogue, in order:  v = acc + bias[n];  v *= colscale[b][t][n]  (FTB gate, modules.py:314);
+ *   act (none | exact GELU | ReLU);
+ *   GLU over adjacent column pairs (2j, 2j+1) -> channel j  (weights are stored pair-interleaved);
+ *   v += addend_fn[fo][n'] (frequency embedding, aero.py:475-480);
+ *   v = residual[b][fo][t][n'] + v  ;  v = v * samp_affine[b][0] + samp_affine[b][1] (aero.py:497-498);
+ *   statistics of the stored value:  stats_mode 1: per (b, group), group = n' / (N' / groups);
+ *   stats_mode 2: per (b, fo) row.   N' = N/2 with GLU, else N.
+ * Generic strides (in floats) let one kernel serve NCHW-free layouts: element (b,f,t,c) of a
+ * source is at  src + b*sb + f*sf + t*st + c.
+ */
+enum { AERO_TAPS_CONV = 0, AERO_TAPS_CONVT = 1 };
+enum { AERO_ACT_NONE = 0, AERO_ACT_GELU = 1, AERO_ACT_RELU = 2 };
+typedef struct {
+    int32_t B, F_out, T, N;
+    int32_t F_in, T_in;
+    int32_t C1, C2;
+    int32_t mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_out_offset;
+    int32_t act, glu, stats_mode, groups;
+    int64_t a1_sb, a1_sf, a1_st;
+    int64_t a2_sb, a2_sf, a2_st;
+    int64_t w_sb;                     /* weight batch stride (0: shared weights) */
+    int64_t o_sb, o_sf, o_st;
+    int64_t r_sb, r_sf, r_st;         /* residual strides */
+    int64_t cs_sb, cs_st;             /* colscale strides */
+    int32_t precision;                /* 0: fp32 SIMT, 1: TF32 tcgen05 (falls back to 0 when the shape is not eligible) */
+    int32_t reserved;
+} aero_tapgemm_params;
+int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w, const float* bias,
+                     const float* addend_fn, const float* colscale, const float* residual,
+                     const float* samp_affine, float* out, double* stats,
+                     const aero_tapgemm_params* p, aero_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalisation / activation passes (HBM-bound elementwise kernels)
+ *
+ * aero_sample_norm_fwd: per-sample standardisation of the input spectrogram (reference
+ *   aero.py:462-464): mean / unbiased std over `per_sample` floats from stats[b] = {sum, sumsq};
+ *   y = (x - mean) / (1e-5 + std); also writes samp_affine[b] = {std, mean} for the output
+ *   de-normalisation (aero.py:497-498).
+ */
+int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* samp_affine,
+                         int32_t B, int64_t per_sample, aero_stream_t stream);
+
+/* aero_norm_act_fwd: y = op(GroupNorm(x))   (replaces nn.GroupNorm + F.gelu / F.glu / Snake /
+ *   LayerScale + residual: aero.py:127,133,198,206-214; modules.py:189,210,232-244; snake.py:67)
+ * x : [B][F_in][T][C]; rows f_off .. f_off+F_out-1 are read (decoder crop, aero.py:209).
+ * stats : fp64 {sum, sumsq}; scope 1: [B][groups] over F_in*T*(C/groups) values (uncropped);
+ *         scope 2: [B*F_in][1] per row over T*C values (DConv's GroupNorm(1, C)).
+ * op: AERO_NA_NONE y=g; AERO_NA_GELU; AERO_NA_GLU y[c]=g[c]*sigmoid(g[c+C/2]) (C_out=C/2);
+ *     AERO_NA_SNAKE y = g + sin(a[f]*g)^2 / a[f];
+ *     AERO_NA_GLU_SCALE_RES y[c] = residual[c] + scale[c] * glu(g)[c].
+ */
+enum { AERO_NA_NONE = 0, AERO_NA_GELU = 1, AERO_NA_GLU = 2, AERO_NA_SNAKE = 3, AERO_NA_GLU_SCALE_RES = 4 };
+typedef struct {
+    int32_t B, F_in, F_out, f_off, T, C;
+    int32_t groups, scope, op;
+    float eps;
+} aero_norm_act_params;
+int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                      const float* snake_a, const float* scale, const float* residual, float* y,
+                      const aero_norm_act_params* p, aero_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Recurrent half of one bidirectional LSTM layer (replaces the cuDNN RNN behind nn.LSTM,
+ * reference modules.py:28,46, together with the overlapping-window framing modules.py:36-44,
+ * utils.py:22-35 and the central-crop reassembly modules.py:49-60).
+ * The input projections x_t W_ih^T + b_ih + b_hh for BOTH directions are computed beforehand by
+ * aero_tapgemm_fwd into `gin` (8H columns: [dir][i,f,g,o][H]).
+ *   in_windowed = 0 : gin is [rows][T][8H] over the un-windowed sequence; window k, step p reads
+ *                     frame k*win_stride + p; frames >= T are zero inputs, so their gate
+ *                     pre-activation is `bias_pad` ([8H] = b_ih + b_hh)   (first layer)
+ *   in_windowed = 1 : gin is [rows*n_win][steps][8H]                        (second layer)
+ *   out_windowed = 1: h written as [rows*n_win][steps][2H]                  (first layer)
+ *   out_windowed = 0: h written de-windowed as [rows][T][2H], keeping for window k the steps
+ *                     [keep_lo(k), keep_hi(k)) exactly as modules.py:53-59    (second layer)
+ * whh : [2][4H][H] (PyTorch layout weight_hh_l{k}, weight_hh_l{k}_reverse), gate order i,f,g,o.
+ */
+typedef struct {
+    int32_t rows, T, H;
+    int32_t n_win, steps, win_stride;
+    int32_t in_windowed, out_windowed;
+} aero_lstm_params;
+int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout,
+                      const aero_lstm_params* p, aero_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LocalState attention core (replaces the einsum/softmax/einsum chain reference
+ * modules.py:104-124; never materialises the T x T matrices).
+ * qkvd : [rows][T][ld]  columns: q [0,H) | k [H,2H) | v (content) [2H,3H) | decay logits [3H, 3H+heads*ndecay)
+ * out  : [rows][T][H],  out[s][h*d+c] = sum_t softmax_t( k_t.q_s/sqrt(d) - |t-s|*slope_s, diag=-100 ) * v_t[c]
+ *        slope_s = sum_{f=1..ndecay} f * sigmoid(decay[h*ndecay+f-1][s]) / 2 / sqrt(ndecay)
+ */
+typedef struct {
+    int32_t rows, T, H, heads, ndecay, ld;
+} aero_attn_params;
+int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AERO_B200_H */
