@@ -246,8 +246,8 @@ static int launch_istft(const float* z, const float* window, float* y, const aer
     using C = IstftCfg<LOGN>;
     const int halo = (C::N - 1) / p.hop;
     const int OB = C::NF - halo;
-    if (OB < C::NF / 4) {
-        set_error("aero_istft_fwd: hop %d too small for n_fft %d (needs hop >= n_fft/%d)", p.hop, p.n_fft, C::NF * 3 / 4);
+    if (OB < 1) {
+        set_error("aero_istft_fwd: hop %d too small for n_fft %d (needs hop >= n_fft/%d)", p.hop, p.n_fft, C::NF - 1);
         return AERO_ERR_UNSUPPORTED;
     }
     const size_t smem = sizeof(float2) * (C::NF * C::M + C::NF * (C::M + 1) + C::M) + sizeof(float) * C::N;

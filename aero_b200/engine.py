@@ -75,6 +75,7 @@ class AeroEngine:
         self._windows = {}
         self._stats = None
         self.precision = 0          # 0: fp32 SIMT tap-GEMM; 1: TF32 tcgen05 where eligible
+        self._prof, self._prof_tags = None, set()
 
     # ------------------------------------------------------------------ plumbing
     def invalidate(self):
@@ -216,7 +217,7 @@ class AeroEngine:
     def _gemm(self, out, w, *, B, F_out, T, N, C1, a1=None, a2=None, C2=0, F_in=None, T_in=None,
               a1_s=None, a2_s=None, o_s=None, mode=TAPS_CONV, kf=1, kt=1, stride_f=1, pad_f=0, dil_t=1, pad_t=0,
               f_off=0, bias=None, act=ACT_NONE, glu=0, stats=None, stats_mode=0, groups=1, addend=None,
-              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0):
+              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0, tag=None):
         F_in = F_out if F_in is None else F_in
         T_in = T if T_in is None else T_in
         n_out = N // 2 if glu else N
@@ -229,10 +230,33 @@ class AeroEngine:
         r_s = r_s or (o_s if residual is not None else (0, 0, 0))
         p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
                                act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, self.precision, 0)
+        timed = self._prof is not None and tag in self._prof_tags
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = self.lib.aero_tapgemm_fwd(_ptr(a1), _ptr(a2), _ptr(w), _ptr(bias), _ptr(addend), _ptr(colscale),
                                        _ptr(residual), _ptr(samp_affine), _ptr(out), _ptr(stats), C.byref(p),
                                        self._stream())
         cabi.check(rc, self.lib)
+        if timed:
+            e1.record()
+            ntaps = kf * kt if mode == TAPS_CONV else kf // stride_f
+            self._prof.append((tag, e0, e1, 2.0 * B * F_out * T * N * (C1 + C2) * ntaps))
+        return out
+
+    def start_profile(self, tags):
+        """Time the tap-GEMM launches whose tag is in `tags` with CUDA events on the launch stream."""
+        self._prof, self._prof_tags = [], set(tags)
+
+    def stop_profile(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, e0, e1, flops in self._prof or []:
+            d = out.setdefault(tag, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["launches"] += 1
+        self._prof = None
         return out
 
     def _gemm_flat(self, out, a, w, npix, K, N, **kw):
@@ -429,7 +453,7 @@ class AeroEngine:
         c1 = 0 if x is None else Cc
         y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc)
         common = dict(a1=x, a2=skip, B=B, F_out=Fq, T=T, N=4 * Cc, C1=c1, C2=Cc, kf=3, kt=3, pad_f=1, pad_t=1,
-                      bias=W[p + ".rw.b"])
+                      bias=W[p + ".rw.b"], tag=p + ".rw")
         if g.norm:
             st = self._stats.take(B * kw["norm_groups"])
             raw = self._buf(tag + ".rw", B, Fq, T, 4 * Cc)

@@ -1,0 +1,207 @@
+"""-m gpu: every C-ABI kernel against the CPU statement of its contract (tests/cpu_emu.py, itself
+checked against the reference's golden vectors in test_host_logic.py), on seeded random inputs,
+covering ragged sizes, two-source K, transposed taps, GLU, statistics and windowed LSTM."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cpu_emu import EmuEngine
+from util import SEED, rel_l2, white_noise
+
+from aero_b200 import Aero, aero_kwargs, cabi
+from aero_b200.engine import AeroEngine, pack_taps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    torch.manual_seed(SEED)
+    m = Aero(**aero_kwargs("aero_4-16_512_256")).eval()
+    emu = EmuEngine(m)
+    mg = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
+    return AeroEngine(mg), emu
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+GEMM_CASES = [
+    # name, dict(B,F_out,F_in,T,N,C1,C2, extra)
+    ("1x1_flat", dict(B=1, F_out=1, T=1000, N=96, C1=48)),
+    ("k2_thin_in", dict(B=1, F_out=1, T=777, N=48, C1=2)),
+    ("thin_out_relu", dict(B=2, F_out=8, T=131, N=5, C1=48, act=cabi.ACT_RELU)),
+    ("enc_k8s4_gelu", dict(B=2, F_out=4, F_in=16, T=140, N=96, C1=48, kf=8, stride_f=4, pad_f=2, act=cabi.ACT_GELU)),
+    ("enc_k8s2_stats", dict(B=2, F_out=4, F_in=8, T=130, N=192, C1=96, kf=8, stride_f=2, pad_f=3, stats_mode=1, groups=4)),
+    ("dconv_k3d2_rowstats", dict(B=2, F_out=3, T=257, N=12, C1=48, kt=3, dil_t=2, pad_t=2, stats_mode=2)),
+    ("dec_3x3_two_src_glu", dict(B=1, F_out=5, T=133, N=192, C1=48, C2=48, kf=3, kt=3, pad_f=1, pad_t=1, glu=1)),
+    ("dec_3x3_zero_half", dict(B=1, F_out=4, T=70, N=128, C1=0, C2=32, kf=3, kt=3, pad_f=1, pad_t=1, stats_mode=1, groups=4)),
+    ("convt_s2_full", dict(B=2, F_out=14, F_in=4, T=129, N=48, C1=96, mode=cabi.TAPS_CONVT, kf=8, stride_f=2, stats_mode=1, groups=4)),
+    ("convt_s4_crop_affine", dict(B=2, F_out=64, F_in=16, T=65, N=2, C1=24, mode=cabi.TAPS_CONVT, kf=8, stride_f=4, f_off=2, affine=True)),
+    ("convt_s4_crop_gelu", dict(B=1, F_out=16, F_in=4, T=200, N=48, C1=96, mode=cabi.TAPS_CONVT, kf=8, stride_f=4, f_off=2, act=cabi.ACT_GELU)),
+    ("residual_1x1", dict(B=1, F_out=1, T=500, N=48, C1=96, residual=True)),
+    ("glu_addend", dict(B=2, F_out=6, T=90, N=96, C1=48, glu=1, addend=True)),
+    ("k9_conv1d", dict(B=2, F_out=1, T=150, N=48, C1=80, kt=9, pad_t=4, act=cabi.ACT_RELU)),
+]
+
+
+@pytest.mark.parametrize("name,cfg", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
+def test_tapgemm_simt(engines, name, cfg):
+    gpu, emu = engines
+    cfg = dict(cfg)
+    B, F_out, T, N, C1 = cfg["B"], cfg["F_out"], cfg["T"], cfg["N"], cfg["C1"]
+    C2, F_in = cfg.get("C2", 0), cfg.get("F_in", F_out)
+    mode = cfg.get("mode", cabi.TAPS_CONV)
+    nslab = cfg.get("kf", 1) * cfg.get("kt", 1)
+    K = C1 + C2
+    w = pack_taps(rnd(N, K, nslab, seed=1) / math.sqrt(K * (nslab if mode == cabi.TAPS_CONV else 2)))
+    a1 = rnd(B, F_in, T, C1, seed=2) if C1 else None
+    a2 = rnd(B, F_in, T, C2, seed=3) if C2 else None
+    bias = rnd(N, seed=4)
+    glu = cfg.get("glu", 0)
+    n_out = N // 2 if glu else N
+    extra = {}
+    if cfg.pop("residual", False):
+        extra["residual"] = rnd(B, F_out, T, n_out, seed=5)
+    if cfg.pop("addend", False):
+        extra["addend"] = rnd(F_out, n_out, seed=6)
+    if cfg.pop("affine", False):
+        extra["samp_affine"] = rnd(B, 2, seed=7).abs() + 0.5
+    sm = cfg.get("stats_mode", 0)
+    nslots = {0: 0, 1: B * cfg.get("groups", 1), 2: B * F_out}[sm]
+    for k in ("B", "F_out", "T", "N", "C1"):
+        cfg.pop(k)
+    res = {}
+    for tag, eng, dev in (("cpu", emu, "cpu"), ("gpu", gpu, "cuda")):
+        def mv(t):
+            return None if t is None else t.to(dev)
+        out = torch.zeros(B, F_out, T, n_out, device=dev)
+        stats = torch.zeros(max(nslots, 1), 2, dtype=torch.float64, device=dev)
+        eng._gemm(out, mv(w), a1=mv(a1), a2=mv(a2), B=B, F_out=F_out, T=T, N=N, C1=C1, bias=mv(bias),
+                  stats=stats if sm else None, **{k: mv(v) for k, v in extra.items()}, **cfg)
+        res[tag] = (out.cpu(), stats.cpu())
+    assert rel_l2(res["gpu"][0], res["cpu"][0]) < 2e-6
+    if sm:
+        assert torch.allclose(res["gpu"][1], res["cpu"][1], rtol=1e-5, atol=1e-3)
+
+
+def test_freq_mix_gemm_with_activation_weights(engines):
+    """FTB frequency mixing: A = Wfc, 'weights' = the activations, batch-strided (include/aero_b200.h w_sb)."""
+    gpu, emu = engines
+    B, Fq, T, Cc = 2, 16, 37, 24
+    x, wfc, gate = rnd(B, Fq, T, Cc, seed=1), rnd(Fq, Fq, seed=2) / 4, rnd(B, T, Cc, seed=3)
+    outs = []
+    for eng, dev in ((emu, "cpu"), (gpu, "cuda")):
+        y = torch.zeros(B, Fq, T, Cc, device=dev)
+        eng._gemm(y, x.to(dev), a1=wfc.to(dev), B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq, a1_s=(0, 0, Fq),
+                  w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=gate.to(dev), cs_s=(T * Cc, 0))
+        outs.append(y.cpu())
+    ref = torch.einsum("gf,bftc->bgtc", wfc, x) * gate[:, None]
+    assert rel_l2(outs[0], ref) < 1e-6 and rel_l2(outs[1], ref) < 2e-6
+
+
+@pytest.mark.parametrize("op", [cabi.NA_NONE, cabi.NA_GELU, cabi.NA_GLU, cabi.NA_SNAKE, cabi.NA_GLU_SCALE_RES])
+@pytest.mark.parametrize("scope", [1, 2])
+def test_norm_act(engines, op, scope):
+    gpu, emu = engines
+    B, F_in, T, Cc = 2, 6, 77, 48
+    groups = 4 if scope == 1 else 1
+    f_off, F_out = (1, 4) if (scope == 1 and op in (cabi.NA_NONE, cabi.NA_GELU)) else (0, F_in)
+    x = rnd(B, F_in, T, Cc, seed=1) * 1.7 + 0.3
+    gamma, beta = 1 + 0.2 * rnd(Cc, seed=2), 0.1 * rnd(Cc, seed=3)
+    glu = op in (cabi.NA_GLU, cabi.NA_GLU_SCALE_RES)
+    co = Cc // 2 if glu else Cc
+    a = rnd(F_in, seed=4).abs() * 8 + 0.2
+    scale, resid = rnd(co, seed=5), rnd(B, F_out, T, co, seed=6)
+    xd = x.double()
+    if scope == 1:
+        g = xd.view(B, F_in * T, groups, Cc // groups)
+        stats = torch.stack([g.sum((1, 3)).reshape(-1), (g * g).sum((1, 3)).reshape(-1)], 1)
+    else:
+        g = xd.view(B * F_in, -1)
+        stats = torch.stack([g.sum(1), (g * g).sum(1)], 1)
+    outs = []
+    for eng, dev in ((emu, "cpu"), (gpu, "cuda")):
+        y = torch.zeros(B, F_out, T, co, device=dev)
+        eng._norm_act(x.to(dev), stats.to(dev), gamma.to(dev), beta.to(dev), y, B=B, F_in=F_in, F_out=F_out, f_off=f_off,
+                      T=T, C_=Cc, groups=groups, scope=scope, op=op, snake_a=a.to(dev), scale=scale.to(dev),
+                      residual=resid.to(dev))
+        outs.append(y.cpu())
+    assert rel_l2(outs[1], outs[0]) < 3e-6
+
+
+@pytest.mark.parametrize("H,T,rows", [(48, 251, 5), (96, 123, 3), (48, 501, 2), (12, 40, 20)])
+def test_lstm_layer_pair(engines, H, T, rows):
+    """Both recurrent calls of a BLSTM (windowed when T > 200) against the cell recurrence on CPU."""
+    gpu, emu = engines
+    steps, stride, n_win = (200, 100, math.ceil(T / 100)) if T > 200 else (T, 0, 1)
+    n_seq = rows * n_win
+    gin1, b1 = rnd(rows * T, 8 * H, seed=1), rnd(8 * H, seed=2) * 0.3
+    whh1, whh2 = rnd(2, 4 * H, H, seed=3) / math.sqrt(H), rnd(2, 4 * H, H, seed=4) / math.sqrt(H)
+    gin2 = rnd(n_seq * steps, 8 * H, seed=5)
+    outs = []
+    for eng, dev in ((emu, "cpu"), (gpu, "cuda")):
+        h1 = torch.zeros(n_seq * steps, 2 * H, device=dev)
+        eng._lstm_rec(gin1.to(dev), b1.to(dev), whh1.to(dev), h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+                      stride=stride, in_windowed=0, out_windowed=1)
+        h2 = torch.zeros(rows * T, 2 * H, device=dev)
+        eng._lstm_rec(gin2.to(dev), b1.to(dev), whh2.to(dev), h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+                      stride=stride, in_windowed=1, out_windowed=0)
+        outs.append((h1.cpu(), h2.cpu()))
+    assert rel_l2(outs[1][0], outs[0][0]) < 1e-5
+    assert rel_l2(outs[1][1], outs[0][1]) < 1e-5
+
+
+@pytest.mark.parametrize("H,T,rows", [(48, 501, 3), (96, 251, 2), (48, 700, 1), (12, 33, 4)])
+def test_local_attention(engines, H, T, rows):
+    gpu, emu = engines
+    ld = 3 * H + 16
+    qkvd = rnd(rows * T, ld, seed=1)
+    qkvd[:, 3 * H:] = qkvd[:, 3 * H:] * 1.5 - 1.0
+    outs = []
+    for eng, dev in ((emu, "cpu"), (gpu, "cuda")):
+        o = torch.zeros(rows * T, H, device=dev)
+        eng._attn(qkvd.to(dev), o, rows=rows, T=T, H=H, heads=4, ndecay=4, ld=ld)
+        outs.append(o.cpu())
+    assert rel_l2(outs[1], outs[0]) < 1e-5
+
+
+def test_sample_norm(engines):
+    gpu, emu = engines
+    B, n = 3, 4 * 257
+    x = rnd(B, n, seed=1) * 2.5 + 0.7
+    xd = x.double()
+    stats = torch.stack([xd.sum(1), (xd * xd).sum(1)], 1)
+    outs = []
+    for eng, dev in ((emu, "cpu"), (gpu, "cuda")):
+        y, aff = torch.zeros(B, n, device=dev), torch.zeros(B, 2, device=dev)
+        eng._sample_norm(x.to(dev), stats.to(dev), y, aff, B, n)
+        outs.append((y.cpu(), aff.cpu()))
+    assert rel_l2(outs[1][0], outs[0][0]) < 1e-6 and rel_l2(outs[1][1], outs[0][1]) < 1e-6
+    ref = (x - x.mean(1, keepdim=True)) / (1e-5 + x.std(1, keepdim=True))
+    assert rel_l2(outs[1][0], ref) < 1e-5
+
+
+def test_stft_istft_golden_and_roundtrip(golden_dir):
+    """spectro / ispectro drop-ins against the reference's own outputs; round trip <= 1e-5 (north_star)."""
+    from aero_b200 import ispectro, spectro
+    g = np.load(os.path.join(golden_dir, "stft_cases.npz"))
+    i = 0
+    while f"{i}/params" in g.files:
+        n_fft, hop, win, L, *lead = [int(v) for v in g[f"{i}/params"]]
+        x = white_noise((*lead, L), seed=SEED + i)
+        z = spectro(x.cuda(), n_fft, hop, win_length=win)
+        zr = torch.view_as_real(z).cpu().reshape(-1)[torch.from_numpy(g[f"{i}/z_idx"].astype(np.int64))]
+        assert rel_l2(zr, g[f"{i}/z_val"]) < 1e-5, (i, "stft")
+        y = ispectro(z, hop, win_length=win).cpu()
+        assert y.shape == g[f"{i}/y"].shape
+        assert rel_l2(y, g[f"{i}/y"]) < 1e-5, (i, "istft")
+        n = min(y.shape[-1], L)
+        if hop * 2 <= win:      # COLA holds: analysis->synthesis is the identity on the kept span
+            assert rel_l2(y[..., :n], x[..., :n]) < 1e-5, (i, "roundtrip")
+        i += 1
+    assert i >= 6
