@@ -37,21 +37,21 @@ class TapGemmParams(C.Structure):
                 ("o_sb", i64), ("o_sf", i64), ("o_st", i64),
                 ("r_sb", i64), ("r_sf", i64), ("r_st", i64),
                 ("cs_sb", i64), ("cs_st", i64),
-                ("precision", i32), ("reserved", i32)]
+                ("precision", i32), ("flags", i32)]
 
 
 class NormActParams(C.Structure):
     _fields_ = [("B", i32), ("F_in", i32), ("F_out", i32), ("f_off", i32), ("T", i32), ("C", i32),
-                ("groups", i32), ("scope", i32), ("op", i32), ("eps", f32)]
+                ("groups", i32), ("scope", i32), ("op", i32), ("eps", f32), ("round_tf32", i32)]
 
 
 class LstmParams(C.Structure):
     _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("n_win", i32), ("steps", i32), ("win_stride", i32),
-                ("in_windowed", i32), ("out_windowed", i32)]
+                ("in_windowed", i32), ("out_windowed", i32), ("round_tf32", i32)]
 
 
 class AttnParams(C.Structure):
-    _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32)]
+    _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32), ("round_tf32", i32)]
 
 
 TAPS_CONV, TAPS_CONVT = 0, 1
@@ -67,7 +67,8 @@ SYMBOLS = {
     "aero_stft_fwd": (C.c_int, [vp, vp, vp, vp, C.POINTER(StftParams), vp]),
     "aero_istft_fwd": (C.c_int, [vp, vp, vp, C.POINTER(IstftParams), vp]),
     "aero_tapgemm_fwd": (C.c_int, [vp] * 10 + [C.POINTER(TapGemmParams), vp]),
-    "aero_sample_norm_fwd": (C.c_int, [vp, vp, vp, vp, i32, i64, vp]),
+    "aero_tapgemm_tc_eligible": (C.c_int, [C.POINTER(TapGemmParams)]),
+    "aero_sample_norm_fwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i32, vp]),
     "aero_norm_act_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
     "aero_lstm_rec_fwd": (C.c_int, [vp, vp, vp, vp, C.POINTER(LstmParams), vp]),
     "aero_local_attn_fwd": (C.c_int, [vp, vp, C.POINTER(AttnParams), vp]),

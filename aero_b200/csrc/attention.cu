@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kQB) local_attn_kernel(const float* __restrict
         const float il = 1.0f / l;
         float* o = out + ((int64_t)row * p.T + s) * p.H + h * D;
 #pragma unroll
-        for (int c = 0; c < D; ++c) o[c] = acc[c] * il;
+        for (int c = 0; c < D; ++c) o[c] = p.round_tf32 ? round_tf32_rna(acc[c] * il) : acc[c] * il;
     }
 }
 

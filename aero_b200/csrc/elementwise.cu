@@ -8,7 +8,7 @@ namespace aero {
 // reference aero.py:462-464: mean / unbiased std over (C,F,T); y = (x-mean)/(1e-5+std)
 __global__ void __launch_bounds__(256) sample_norm_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                           float* __restrict__ y, float* __restrict__ samp_affine,
-                                                          int64_t per_sample) {
+                                                          int64_t per_sample, int rnd) {
     const int b = blockIdx.y;
     __shared__ float s_mean, s_inv;
     if (threadIdx.x == 0) {
@@ -32,10 +32,14 @@ __global__ void __launch_bounds__(256) sample_norm_kernel(const float* __restric
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(xb)[i];
         v.x = (v.x - mean) * inv; v.y = (v.y - mean) * inv; v.z = (v.z - mean) * inv; v.w = (v.w - mean) * inv;
+        if (rnd) { v.x = round_tf32_rna(v.x); v.y = round_tf32_rna(v.y); v.z = round_tf32_rna(v.z); v.w = round_tf32_rna(v.w); }
         reinterpret_cast<float4*>(yb)[i] = v;
     }
     if (blockIdx.x == 0)
-        for (int64_t i = (n4 << 2) + threadIdx.x; i < per_sample; i += blockDim.x) yb[i] = (xb[i] - mean) * inv;
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < per_sample; i += blockDim.x) {
+            const float v = (xb[i] - mean) * inv;
+            yb[i] = rnd ? round_tf32_rna(v) : v;
+        }
 }
 
 // ------------------------------------------------------------------------- norm_act
@@ -115,6 +119,10 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = a[u];
         }
+        if (p.round_tf32) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = round_tf32_rna(o[u]);
+        }
         *reinterpret_cast<float4*>(y + oidx) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
@@ -122,14 +130,14 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
 }  // namespace aero
 
 extern "C" int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* samp_affine, int32_t B,
-                                    int64_t per_sample, aero_stream_t stream) {
+                                    int64_t per_sample, int32_t round_tf32, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(x && stats && y && B >= 1 && per_sample >= 2, "aero_sample_norm_fwd: bad argument");
     AERO_REQUIRE((per_sample & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
                  "aero_sample_norm_fwd: per_sample must be a multiple of 4 and buffers 16-byte aligned");
     const int chunks = (int)((per_sample / 4 + 256 * 8 - 1) / (256 * 8));
     dim3 grid(chunks < 1 ? 1 : chunks, B);
-    sample_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, y, samp_affine, per_sample);
+    sample_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, y, samp_affine, per_sample, round_tf32);
     return check_launch("aero_sample_norm_fwd");
 }
 

@@ -104,15 +104,16 @@ __global__ void __launch_bounds__(4 * H) lstm_rec_kernel(const float* __restrict
             c_state[q] = c;
             const float h = og * tanhf(c);
             hs[j * NT + n] = h;
+            const float hw = p.round_tf32 ? round_tf32_rna(h) : h;
             if (seq_ok[q]) {
                 if (p.out_windowed) {
-                    hout[out_base[q] + (int64_t)pos * 2 * H + dir * H + j] = h;
+                    hout[out_base[q] + (int64_t)pos * 2 * H + dir * H + j] = hw;
                 } else {
                     const int frame = seq_k[q] * p.win_stride + pos;
                     const int lo = (seq_k[q] == 0) ? 0 : half;
                     const int hi = (seq_k[q] == p.n_win - 1) ? p.steps : p.steps - half;
                     if (pos >= lo && pos < hi && frame < p.T)
-                        hout[out_base[q] + (int64_t)frame * 2 * H + dir * H + j] = h;
+                        hout[out_base[q] + (int64_t)frame * 2 * H + dir * H + j] = hw;
                 }
             }
         }

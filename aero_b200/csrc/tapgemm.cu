@@ -49,5 +49,15 @@ extern "C" int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w
               (p.C2 == 0 || (al16(a2) && p.a2_sb % 4 == 0 && p.a2_sf % 4 == 0 && p.a2_st % 4 == 0));
     g.vec_o = al16(out) && p.o_sb % 4 == 0 && p.o_sf % 4 == 0 && p.o_st % 4 == 0 && Nout % 4 == 0;
     AERO_REQUIRE(al16(w) && p.w_sb % 4 == 0, "aero_tapgemm_fwd: weights must be 16-byte aligned");
+    if (p.precision == 1) {
+        if (!tapgemm_tc_eligible(p)) {
+            set_error("aero_tapgemm_fwd: precision=1 requested for a shape the tcgen05 path does not take (N=%d K=%d)", p.N, p.C1 + p.C2);
+            return AERO_ERR_UNSUPPORTED;
+        }
+        AERO_REQUIRE((p.C1 == 0 || al16(a1)) && (p.C2 == 0 || al16(a2)), "aero_tapgemm_fwd: TMA sources must be 16-byte aligned");
+        return tapgemm_tc_launch(g, (cudaStream_t)stream);
+    }
     return tapgemm_simt_launch(g, (cudaStream_t)stream);
 }
+
+extern "C" int aero_tapgemm_tc_eligible(const aero_tapgemm_params* p) { return p && aero::tapgemm_tc_eligible(*p) ? 1 : 0; }

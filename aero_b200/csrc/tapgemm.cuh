@@ -22,4 +22,6 @@ struct TapGemmArgs {
     int vec_o;        // 16-byte stores legal
 };
 int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st);
+int tapgemm_tc_launch(const TapGemmArgs& g, cudaStream_t st);
+bool tapgemm_tc_eligible(const aero_tapgemm_params& p);
 }  // namespace aero

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
                 if (g.addend_fn) x += g.addend_fn[(int64_t)fo * Nout + no0 + j];
                 if (rp) x += rp[no0 + j];
                 x = x * sa + sb;
+                if (p.flags & 1) x = round_tf32_rna(x);
                 o[j] = x;
                 ssum += x;
                 ssq += x * x;

@@ -1,0 +1,479 @@
+// Tap-GEMM on the 5th-generation tensor cores (sm_100a): TMA -> shared memory -> tcgen05.mma
+// (kind::tf32, fp32 accumulate in TMEM) -> tcgen05.ld epilogue.  Implicit GEMM, im2col-free:
+// every tap of a convolution is a shifted TMA box of the channels-last activation tensor; image
+// borders, channel tails and the K tail are TMA out-of-bounds zero fill.
+//
+//   A tile : 128 pixels (consecutive t of one (b, f) row) x 32 channels  = 128 rows x 128 B, SWIZZLE_128B
+//   B tile : BN output columns x 32 channels (weights stored K-major [slab][N][K]) = BN rows x 128 B
+//   D      : 128 lanes x BN fp32 columns of TMEM
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).  STAGES-deep mbarrier ring between
+// producer and MMA; tcgen05.commit frees a stage / publishes the accumulator.
+//
+// Operands are read as fp32 bit patterns with the low 13 mantissa bits ignored by the tensor core,
+// so producers round activations to TF32 (round-to-nearest) when they store them and the host
+// rounds the weights when it packs them: truncation would bias every dot product low.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+
+#include "tapgemm.cuh"
+
+namespace aero {
+
+constexpr int kBM = 128;
+constexpr int kBKc = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kATileBytes = kBM * 128;   // 16 KB
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        if (spin > (1u << 24)) {
+            printf("aero tapgemm_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) (8 rows x 128 B = 1024), version 1 [46,48),
+// layout type SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+struct TcShared {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t acc_full;
+    uint32_t tmem_base;
+    float stats[8][2];
+};
+
+// number of (tap, source, channel-chunk) iterations and their enumeration, shared by all roles
+struct TapIter {
+    int fi, dt, slab;
+};
+__device__ __forceinline__ bool tap_geometry(const aero_tapgemm_params& p, int tap, int fo, TapIter& it) {
+    if (p.mode == AERO_TAPS_CONV) {
+        const int jf = tap / p.kt, jt = tap - jf * p.kt;
+        it.fi = fo * p.stride_f + jf - p.pad_f;
+        it.dt = jt * p.dil_t - p.pad_t;
+        it.slab = tap;
+    } else {
+        const int fof = fo + p.f_out_offset;
+        it.fi = fof / p.stride_f - tap;
+        it.dt = 0;
+        it.slab = fof % p.stride_f + tap * p.stride_f;
+    }
+    return it.fi >= 0 && it.fi < p.F_in;
+}
+
+__global__ void __launch_bounds__(192, 1)
+tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                  const __grid_constant__ CUtensorMap mapW, const TapGemmArgs g, const int BN, const uint32_t idesc,
+                  const uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int stage_bytes = kATileBytes + BN * 128;
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + kStages * stage_bytes);
+
+    const aero_tapgemm_params& p = g.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tt = tile % g.tiles_t;
+    const int row = tile / g.tiles_t;
+    const int fo = row % p.F_out;
+    const int b = row / p.F_out;
+    const int t0 = tt * kBM;
+    const int n0 = blockIdx.y * BN;
+    const int nch1 = (p.C1 + kBKc - 1) / kBKc, nch2 = (p.C2 + kBKc - 1) / kBKc;
+
+    int n_iters = 0;
+    for (int tap = 0; tap < g.ntaps; ++tap) {
+        TapIter it;
+        if (tap_geometry(p, tap, fo, it)) n_iters += nch1 + nch2;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
+        mbar_init(&sh->acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 8; ++i) { sh->stats[i][0] = 0.f; sh->stats[i][1] = 0.f; }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = (uint32_t)stage_bytes;
+            for (int tap = 0; tap < g.ntaps; ++tap) {
+                TapIter it;
+                if (!tap_geometry(p, tap, fo, it)) continue;
+                for (int src = 0; src < 2; ++src) {
+                    const int nch = src ? nch2 : nch1;
+                    const CUtensorMap* mA = src ? &mapA2 : &mapA1;
+                    const int kw0 = src ? p.C1 : 0;
+                    for (int kc = 0; kc < nch; ++kc) {
+                        mbar_wait(&sh->empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * stage_bytes;
+                        mbar_expect_tx(&sh->full[stage], tx);
+                        tma_load_4d(sa, mA, &sh->full[stage], kc * kBKc, t0 + it.dt, it.fi, b);
+                        tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kw0 + kc * kBKc, n0, it.slab);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0 && n_iters > 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_iters; ++i) {
+                mbar_wait(&sh->full[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kATileBytes);
+#pragma unroll
+                for (int k = 0; k < kBKc / 8; ++k)      // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
+                    umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&sh->empty[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&sh->acc_full);
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5)
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const int t = t0 + m;
+        const bool row_ok = t < p.T;
+        if (n_iters > 0) {
+            mbar_wait(&sh->acc_full, 0);
+            tcgen05_fence_after();
+        }
+        const int Nout = p.glu ? p.N / 2 : p.N;
+        const int gw = (p.stats_mode == 1) ? Nout / p.groups : Nout;
+        float sa = 1.f, sb = 0.f;
+        if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
+        const bool rnd = p.flags & 1;
+        float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+        const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+        const float* csp = g.colscale ? g.colscale + (int64_t)b * p.cs_sb + (int64_t)t * p.cs_st : nullptr;
+        const float* adp = g.addend_fn ? g.addend_fn + (int64_t)fo * Nout : nullptr;
+        int cur_g = -1;
+        float ssum = 0.f, ssq = 0.f;
+        const int g_lo = (p.glu ? n0 >> 1 : n0) / gw;
+
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            if (n_iters > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            const int nb = n0 + c0;
+            if (nb >= p.N) continue;                   // uniform: padded columns of the last tile
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = nb + j;
+                float x = __uint_as_float(r[j]);
+                if (row_ok && n < p.N) {
+                    if (g.bias) x += g.bias[n];
+                    if (csp) x *= csp[n];
+                    if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                    else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                }
+                v[j] = x;
+            }
+            float o[16];
+            int no0, cnt;
+            if (p.glu) {
+                no0 = nb >> 1;
+                cnt = 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
+            } else {
+                no0 = nb;
+                cnt = 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = v[j];
+            }
+            // statistics bookkeeping is warp-uniform: groups depend on columns only
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                if (sub * 8 >= cnt) break;
+                const int ns = no0 + sub * 8;
+                if (p.stats_mode != 0 && ns < Nout) {
+                    const int gi = ns / gw;
+                    if (gi != cur_g) {
+                        if (cur_g >= 0) {
+                            const float a = warp_sum(ssum), c = warp_sum(ssq);
+                            if (lane == 0) { atomicAdd(&sh->stats[cur_g - g_lo][0], a); atomicAdd(&sh->stats[cur_g - g_lo][1], c); }
+                        }
+                        cur_g = gi; ssum = 0.f; ssq = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int jj = sub * 8 + j;
+                    const int nn = no0 + jj;
+                    if (row_ok && nn < Nout) {
+                        float x = o[jj];
+                        if (adp) x += adp[nn];
+                        if (rp) x += rp[nn];
+                        x = x * sa + sb;
+                        if (rnd) x = round_tf32_rna(x);
+                        o[jj] = x;
+                        ssum += x;
+                        ssq += x * x;
+                    }
+                }
+            }
+            if (row_ok) {
+                if (g.vec_o && no0 + cnt <= Nout) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (j < cnt) *reinterpret_cast<float4*>(op + no0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < cnt && no0 + j < Nout) op[no0 + j] = o[j];
+                }
+            }
+        }
+        if (p.stats_mode != 0) {
+            if (cur_g >= 0) {
+                const float a = warp_sum(ssum), c = warp_sum(ssq);
+                if (lane == 0) { atomicAdd(&sh->stats[cur_g - g_lo][0], a); atomicAdd(&sh->stats[cur_g - g_lo][1], c); }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int e = threadIdx.x - 64;
+            if (e < 8) {
+                const float a = sh->stats[e][0], c = sh->stats[e][1];
+                const int gi = g_lo + e;
+                const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
+                if (gi < ngroups && (a != 0.f || c != 0.f)) {
+                    const int64_t slot = (p.stats_mode == 1) ? ((int64_t)b * p.groups + gi) : ((int64_t)b * p.F_out + fo);
+                    atomicAdd(&g.stats[2 * slot], (double)a);
+                    atomicAdd(&g.stats[2 * slot + 1], (double)c);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* base;
+    uint64_t d[4], s[3];
+    uint32_t box[4], rank;
+    bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        size_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+        return h;
+    }
+};
+
+static int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.base = base;
+    key.rank = rank;
+    for (uint32_t i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.box[i] = box[i]; }
+    for (uint32_t i = 0; i + 1 < rank; ++i) key.s[i] = strides_bytes[i];
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return AERO_OK; }
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return AERO_ERR_UNSUPPORTED; }
+    cuuint64_t gd[4];
+    cuuint64_t gs[3];
+    cuuint32_t bx[4], es[4];
+    for (uint32_t i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (uint32_t i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %u dims %llu %llu %llu %llu", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  (unsigned long long)(rank > 3 ? dims[3] : 0));
+        return AERO_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return AERO_OK;
+}
+
+static int pick_bn(int N) {
+    const int ntiles = (N + 255) / 256;
+    const int per = (N + ntiles - 1) / ntiles;
+    return (per + 15) & ~15;
+}
+
+bool tapgemm_tc_eligible(const aero_tapgemm_params& p) {
+    if (p.w_sb != 0) return false;                                   // activations-as-weights (FTB frequency mix)
+    if (p.N < 8) return false;                                       // thin outputs stay on the SIMT path
+    const int K = p.C1 + p.C2;
+    if (K < 8 || (p.C1 % 4) || (p.C2 % 4)) return false;             // TMA needs 16-byte global strides
+    auto ok_strides = [](int64_t sb, int64_t sf, int64_t st) { return sb % 4 == 0 && sf % 4 == 0 && st % 4 == 0 && st > 0; };
+    if (p.C1 && !ok_strides(p.a1_sb, p.a1_sf, p.a1_st)) return false;
+    if (p.C2 && !ok_strides(p.a2_sb, p.a2_sf, p.a2_st)) return false;
+    if (p.stats_mode == 1) {
+        const int Nout = p.glu ? p.N / 2 : p.N;
+        if (p.groups < 1 || Nout % p.groups) return false;
+        const int gw = Nout / p.groups;
+        const int bn = pick_bn(p.N);
+        if (gw % 8 || (p.glu ? bn / 2 : bn) / gw + 2 > 8) return false;
+    }
+    return true;
+}
+
+static int make_a_map(CUtensorMap* m, const float* base, int C, const aero_tapgemm_params& p, int64_t sb, int64_t sf, int64_t st) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.T_in, (uint64_t)p.F_in, (uint64_t)p.B};
+    int64_t s1 = st, s2 = sf, s3 = sb;
+    if (s2 <= 0) s2 = s1 * p.T_in;              // size-1 dimensions: any legal stride
+    if (s3 <= 0) s3 = s2 * p.F_in;
+    uint64_t strides[3] = {(uint64_t)s1 * 4, (uint64_t)s2 * 4, (uint64_t)s3 * 4};
+    uint32_t box[4] = {(uint32_t)kBKc, (uint32_t)kBM, 1, 1};
+    return encode_map(m, base, 4, dims, strides, box);
+}
+
+int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
+    TapGemmArgs g = g0;
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1 + p.C2;
+    const int BN = pick_bn(p.N);
+    const int nslab = (p.mode == AERO_TAPS_CONV) ? p.kf * p.kt : p.kf;
+    CUtensorMap mA1, mA2, mW;
+    int rc;
+    if (p.C1) { if ((rc = make_a_map(&mA1, g.a1, p.C1, p, p.a1_sb, p.a1_sf, p.a1_st)) != AERO_OK) return rc; }
+    if (p.C2) { if ((rc = make_a_map(&mA2, g.a2, p.C2, p, p.a2_sb, p.a2_sf, p.a2_st)) != AERO_OK) return rc; }
+    if (!p.C1) mA1 = mA2;
+    if (!p.C2) mA2 = mA1;
+    {
+        const uint64_t npad = (uint64_t)((p.N + 3) & ~3);          // weights are stored W[slab][pad4(N)][K]
+        uint64_t dims[3] = {(uint64_t)K, npad, (uint64_t)nslab};
+        uint64_t strides[2] = {(uint64_t)K * 4, (uint64_t)K * npad * 4};
+        uint32_t box[3] = {(uint32_t)kBKc, (uint32_t)BN, 1};
+        if ((rc = encode_map(&mW, g.w, 3, dims, strides, box)) != AERO_OK) return rc;
+    }
+    g.tiles_t = cdiv(p.T, kBM);
+    const int64_t tiles = (int64_t)p.B * p.F_out * g.tiles_t;
+    if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    const size_t smem = (size_t)kStages * (kATileBytes + BN * 128) + sizeof(TcShared) + 1024;
+    cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    dim3 grid((unsigned)tiles, cdiv(p.N, BN));
+    tapgemm_tc_kernel<<<grid, 192, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols);
+    return check_launch("aero_tapgemm_fwd(tcgen05)");
+}
+
+}  // namespace aero

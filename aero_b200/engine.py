@@ -39,6 +39,12 @@ def pack_taps(w_nkt):
     return out.contiguous()
 
 
+def tf32_round(t):
+    """Round-to-nearest (ties away) to TF32's 10-bit mantissa, as cvt.rna.tf32.f32 does on the device."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def glu_perm(n, device):
     """Column order that puts GLU partners (j, j + n/2) next to each other."""
     half = n // 2
@@ -76,6 +82,7 @@ class AeroEngine:
         self._stats = None
         self.precision = 0          # 0: fp32 SIMT tap-GEMM; 1: TF32 tcgen05 where eligible
         self._prof, self._prof_tags = None, set()
+        self._wk = {}
 
     # ------------------------------------------------------------------ plumbing
     def invalidate(self):
@@ -211,13 +218,19 @@ class AeroEngine:
             W[p + ".rw.w"], W[p + ".rw.b"] = pack_taps(wr), br.contiguous()
             W[p + ".ct.w"] = pack_taps(sd[p + ".conv_tr.weight"][:, :, :, 0].permute(1, 0, 2))
             W[p + ".ct.b"] = sd[p + ".conv_tr.bias"].contiguous()
-        return {k: v.to(device=dev, dtype=torch.float32) for k, v in W.items()}
+        out = {k: v.to(device=dev, dtype=torch.float32) for k, v in W.items()}
+        # K-major TF32 twins of every tap-GEMM weight for the tcgen05 path: [taps, K, pad4(N)] -> [taps, pad4(N), K]
+        self._wk = {}
+        for k in [k for k in out if k.endswith(".w") and out[k].dim() == 3]:
+            out[k + "@k"] = tf32_round(out[k].permute(0, 2, 1).contiguous())
+            self._wk[out[k].data_ptr()] = out[k + "@k"]
+        return out
 
     # ------------------------------------------------------------------ kernel wrappers
     def _gemm(self, out, w, *, B, F_out, T, N, C1, a1=None, a2=None, C2=0, F_in=None, T_in=None,
               a1_s=None, a2_s=None, o_s=None, mode=TAPS_CONV, kf=1, kt=1, stride_f=1, pad_f=0, dil_t=1, pad_t=0,
               f_off=0, bias=None, act=ACT_NONE, glu=0, stats=None, stats_mode=0, groups=1, addend=None,
-              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0, tag=None):
+              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0, tag=None, rnd=False):
         F_in = F_out if F_in is None else F_in
         T_in = T if T_in is None else T_in
         n_out = N // 2 if glu else N
@@ -228,8 +241,13 @@ class AeroEngine:
         a2_s = a2_s or (cl(F_in, C2) if a2 is not None else (0, 0, 0))
         o_s = o_s or (F_out * T * n_out, T * n_out, n_out)
         r_s = r_s or (o_s if residual is not None else (0, 0, 0))
+        flags = 1 if (rnd and self.precision == 1) else 0
         p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
-                               act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, self.precision, 0)
+                               act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 0, flags)
+        if self.precision == 1 and w_sb == 0:
+            wk = self._wk.get(w.data_ptr())
+            if wk is not None and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
+                p.precision, w = 1, wk
         timed = self._prof is not None and tag in self._prof_tags
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -264,24 +282,25 @@ class AeroEngine:
         return self._gemm(out, w, a1=a, B=1, F_out=1, T=npix, N=N, C1=K, **kw)
 
     def _norm_act(self, x, stats, gamma, beta, y, *, B, F_in, T, C_, groups, scope, op, F_out=None, f_off=0,
-                  snake_a=None, scale=None, residual=None):
-        p = cabi.NormActParams(B, F_in, F_in if F_out is None else F_out, f_off, T, C_, groups, scope, op, 1e-5)
+                  snake_a=None, scale=None, residual=None, rnd=False):
+        p = cabi.NormActParams(B, F_in, F_in if F_out is None else F_out, f_off, T, C_, groups, scope, op, 1e-5,
+                               1 if (rnd and self.precision == 1) else 0)
         rc = self.lib.aero_norm_act_fwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(snake_a), _ptr(scale),
                                         _ptr(residual), _ptr(y), C.byref(p), self._stream())
         cabi.check(rc, self.lib)
         return y
 
     def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed):
-        p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed)
+        p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed, 1 if self.precision == 1 else 0)
         cabi.check(self.lib.aero_lstm_rec_fwd(_ptr(gin), _ptr(bias_pad), _ptr(whh), _ptr(hout), C.byref(p),
                                               self._stream()), self.lib)
 
     def _attn(self, qkvd, out, *, rows, T, H, heads, ndecay, ld):
-        p = cabi.AttnParams(rows, T, H, heads, ndecay, ld)
+        p = cabi.AttnParams(rows, T, H, heads, ndecay, ld, 1 if self.precision == 1 else 0)
         cabi.check(self.lib.aero_local_attn_fwd(_ptr(qkvd), _ptr(out), C.byref(p), self._stream()), self.lib)
 
     def _sample_norm(self, x, stats, y, affine, B, per_sample):
-        cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample,
+        cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample, 0,
                                                  self._stream()), self.lib)
 
     def stft_into(self, x, z, stats, *, n_fft, hop, win, channels, bins_out, strides):
@@ -334,17 +353,17 @@ class AeroEngine:
         r = 5
         R = self._buf(tag + ".R", B, T, Fq * r)
         self._gemm(R, W[p + ".ftb1.w"], a1=x, B=B, F_out=Fq, T=T, N=r, C1=Cc, bias=W[p + ".ftb1.b"], act=ACT_RELU,
-                   o_s=(T * Fq * r, r, Fq * r))
+                   o_s=(T * Fq * r, r, Fq * r), rnd=True)
         G = self._buf(tag + ".G", B, T, Cc)
         self._gemm(G, W[p + ".ftb1d.w"], a1=R, B=B, F_out=1, T=T, N=Cc, C1=Fq * r, kt=9, pad_t=4,
                    bias=W[p + ".ftb1d.b"], act=ACT_RELU, a1_s=(T * Fq * r, 0, Fq * r), o_s=(T * Cc, 0, Cc))
         Y = self._buf(tag + ".Y", B, Fq, T, Cc)
         # frequency mixing as a GEMM whose "weights" are the activations: out[f'] = sum_f Wfc[f',f] x[f], times the gate
         self._gemm(Y, x, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq, a1_s=(0, 0, Fq),
-                   w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0))
+                   w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True)
         out = self._buf(tag + ".out", B, Fq, T, Cc)
         self._gemm(out, W[p + ".ftb2.w"], a1=Y, a2=x, B=1, F_out=1, T=B * Fq * T, N=Cc, C1=Cc, C2=Cc,
-                   bias=W[p + ".ftb2.b"], act=ACT_RELU)
+                   bias=W[p + ".ftb2.b"], act=ACT_RELU, rnd=True)
         return out
 
     def _blstm(self, h, W, o, rows, T, H, tag):
@@ -365,7 +384,7 @@ class AeroEngine:
         h2 = self._buf(tag + ".h2", rows * T, 2 * H)
         self._lstm_rec(gin2, W[o + ".lstm1.b"], W[o + ".lstm1.whh"], h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
                        stride=stride, in_windowed=1, out_windowed=0)
-        self._gemm_flat(h, h2, W[o + ".lin.w"], rows * T, 2 * H, H, bias=W[o + ".lin.b"], residual=h)
+        self._gemm_flat(h, h2, W[o + ".lin.w"], rows * T, 2 * H, H, bias=W[o + ".lin.b"], residual=h, rnd=True)
         return h
 
     def _local_attn(self, h, W, o, rows, T, H, tag):
@@ -375,7 +394,7 @@ class AeroEngine:
         self._gemm_flat(qkvd, h, W[o + ".qkvd.w"], rows * T, H, ld, bias=W[o + ".qkvd.b"])
         r = self._buf(tag + ".attn", rows * T, H)
         self._attn(qkvd, r, rows=rows, T=T, H=H, heads=_ATTN_HEADS, ndecay=_ATTN_NDECAY, ld=ld)
-        self._gemm_flat(h, r, W[o + ".proj.w"], rows * T, H, H, bias=W[o + ".proj.b"], residual=h)
+        self._gemm_flat(h, r, W[o + ".proj.w"], rows * T, H, H, bias=W[o + ".proj.b"], residual=h, rnd=True)
         return h
 
     def _dconv(self, y, W, g, B, T, tag):
@@ -392,7 +411,7 @@ class AeroEngine:
             self._gemm(h, W[o + ".c1.w"], a1=y, B=B, F_out=Fq, T=T, N=hid, C1=Cc, kt=3, dil_t=dil, pad_t=dil,
                        bias=W[o + ".c1.b"], stats=st1, stats_mode=2)
             self._norm_act(h, st1, W[o + ".n1.g"], W[o + ".n1.b"], h, B=B, F_in=Fq, T=T, C_=hid, groups=1, scope=2,
-                           op=NA_SNAKE, snake_a=W[o + ".a"])
+                           op=NA_SNAKE, snake_a=W[o + ".a"], rnd=True)
             if g.lstm:
                 self._blstm(h, W, o, rows, T, hid, f"{tag}.lstm")
             if g.attn:
@@ -402,7 +421,7 @@ class AeroEngine:
             self._gemm(u, W[o + ".c2.w"], a1=h, B=B, F_out=Fq, T=T, N=2 * Cc, C1=hid, bias=W[o + ".c2.b"],
                        stats=st2, stats_mode=2)
             self._norm_act(u, st2, W[o + ".n2.g"], W[o + ".n2.b"], y, B=B, F_in=Fq, T=T, C_=2 * Cc, groups=1, scope=2,
-                           op=NA_GLU_SCALE_RES, scale=W[o + ".ls"], residual=y)
+                           op=NA_GLU_SCALE_RES, scale=W[o + ".ls"], residual=y, rnd=True)
         return y
 
     def _encode(self, x, W, g, B, T):
@@ -414,7 +433,7 @@ class AeroEngine:
         cin = g.enc_cin
         if g.index == 0:
             pre = self._buf(tag + ".pre", B, Fi, T, Cc)
-            self._gemm_flat(pre, x, W[p + ".pre.w"], B * Fi * T, cin, Cc, bias=W[p + ".pre.b"])
+            self._gemm_flat(pre, x, W[p + ".pre.w"], B * Fi * T, cin, Cc, bias=W[p + ".pre.b"], rnd=True)
             x, cin = pre, Cc
         if g.ftb:
             x = self._ftb(x, W, p, B, Fi, T, cin, tag + ".ftb")
@@ -425,10 +444,10 @@ class AeroEngine:
                        stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], stats=st, stats_mode=1,
                        groups=kw["norm_groups"])
             self._norm_act(y, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fo, T=T, C_=Cc,
-                           groups=kw["norm_groups"], scope=1, op=NA_GELU)
+                           groups=kw["norm_groups"], scope=1, op=NA_GELU, rnd=True)
         else:
             self._gemm(y, W[p + ".conv.w"], a1=x, B=B, F_out=Fo, F_in=Fi, T=T, N=Cc, C1=cin, kf=g.kernel,
-                       stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], act=ACT_GELU)
+                       stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], act=ACT_GELU, rnd=True)
         if g.dconv:
             y = self._dconv(y, W, g, B, T, tag + ".dc")
         out = self._buf(tag + ".out", B, Fo, T, Cc)
@@ -438,10 +457,10 @@ class AeroEngine:
             self._gemm(raw, W[p + ".rw.w"], a1=y, B=B, F_out=Fo, T=T, N=2 * Cc, C1=Cc, bias=W[p + ".rw.b"],
                        stats=st, stats_mode=1, groups=kw["norm_groups"])
             self._norm_act(raw, st, W[p + ".norm2.g"], W[p + ".norm2.b"], out, B=B, F_in=Fo, T=T, C_=2 * Cc,
-                           groups=kw["norm_groups"], scope=1, op=NA_GLU)
+                           groups=kw["norm_groups"], scope=1, op=NA_GLU, rnd=True)
         else:
             self._gemm(out, W[p + ".rw.w"], a1=y, B=B, F_out=Fo, T=T, N=2 * Cc, C1=Cc, bias=W[p + ".rw.b"], glu=1,
-                       addend=W.get("emb") if g.index == 0 else None)
+                       addend=W.get("emb") if g.index == 0 else None, rnd=True)
         return out
 
     def _decode(self, x, skip, W, g, j, B, T, last, samp_affine):
@@ -459,9 +478,9 @@ class AeroEngine:
             raw = self._buf(tag + ".rw", B, Fq, T, 4 * Cc)
             self._gemm(raw, W[p + ".rw.w"], stats=st, stats_mode=1, groups=kw["norm_groups"], **common)
             self._norm_act(raw, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fq, T=T, C_=4 * Cc,
-                           groups=kw["norm_groups"], scope=1, op=NA_GLU)
+                           groups=kw["norm_groups"], scope=1, op=NA_GLU, rnd=True)
         else:
-            self._gemm(y, W[p + ".rw.w"], glu=1, **common)
+            self._gemm(y, W[p + ".rw.w"], glu=1, rnd=True, **common)
         cout = g.dec_cout
         f_full = (Fq - 1) * g.stride + g.kernel
         f_keep = f_full - 2 * g.pad
@@ -474,13 +493,13 @@ class AeroEngine:
                        groups=kw["norm_groups"])
             self._norm_act(raw, st, W[p + ".norm2.g"], W[p + ".norm2.b"], z, B=B, F_in=f_full, F_out=f_keep,
                            f_off=g.pad, T=T, C_=cout, groups=kw["norm_groups"], scope=1,
-                           op=cabi.NA_NONE if last else NA_GELU)
+                           op=cabi.NA_NONE if last else NA_GELU, rnd=not last)
             if last and samp_affine is not None:
                 raise NotImplementedError("GroupNorm on the last decoder layer (norm_starts=0) is not supported")
         else:
             self._gemm(z, W[p + ".ct.w"], a1=y, B=B, F_out=f_keep, F_in=Fq, T=T, N=cout, C1=2 * Cc, mode=TAPS_CONVT,
                        kf=g.kernel, stride_f=g.stride, f_off=g.pad, bias=W[p + ".ct.b"],
-                       act=ACT_NONE if last else ACT_GELU, samp_affine=samp_affine if last else None)
+                       act=ACT_NONE if last else ACT_GELU, samp_affine=samp_affine if last else None, rnd=not last)
         return z
 
     # ------------------------------------------------------------------ forward

@@ -120,13 +120,17 @@ typedef struct {
     int64_t o_sb, o_sf, o_st;
     int64_t r_sb, r_sf, r_st;         /* residual strides */
     int64_t cs_sb, cs_st;             /* colscale strides */
-    int32_t precision;                /* 0: fp32 SIMT, 1: TF32 tcgen05 (falls back to 0 when the shape is not eligible) */
-    int32_t reserved;
+    int32_t precision;                /* 0: fp32 SIMT tiles, weights N-contiguous  W[slab][K][pad4(N)];
+                                         1: TF32 tcgen05 tiles, weights K-contiguous W[slab][pad4(N)][K] rounded to TF32;
+                                            AERO_ERR_UNSUPPORTED unless aero_tapgemm_tc_eligible() */
+    int32_t flags;                    /* bit 0: round stored outputs to TF32 (round-to-nearest) for a tensor-core consumer */
 } aero_tapgemm_params;
 int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w, const float* bias,
                      const float* addend_fn, const float* colscale, const float* residual,
                      const float* samp_affine, float* out, double* stats,
                      const aero_tapgemm_params* p, aero_stream_t stream);
+/* 1 when the shape can run on the tcgen05 path (precision 1), else 0 */
+int aero_tapgemm_tc_eligible(const aero_tapgemm_params* p);
 
 /* ------------------------------------------------------------------------------------------
  * Normalisation / activation passes (HBM-bound elementwise kernels)
@@ -137,7 +141,7 @@ int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w, const flo
  *   de-normalisation (aero.py:497-498).
  */
 int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* samp_affine,
-                         int32_t B, int64_t per_sample, aero_stream_t stream);
+                         int32_t B, int64_t per_sample, int32_t round_tf32, aero_stream_t stream);
 
 /* aero_norm_act_fwd: y = op(GroupNorm(x))   (replaces nn.GroupNorm + F.gelu / F.glu / Snake /
  *   LayerScale + residual: aero.py:127,133,198,206-214; modules.py:189,210,232-244; snake.py:67)
@@ -153,6 +157,7 @@ typedef struct {
     int32_t B, F_in, F_out, f_off, T, C;
     int32_t groups, scope, op;
     float eps;
+    int32_t round_tf32;               /* round stored outputs to TF32 for a tensor-core consumer */
 } aero_norm_act_params;
 int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
                       const float* snake_a, const float* scale, const float* residual, float* y,
@@ -177,6 +182,7 @@ typedef struct {
     int32_t rows, T, H;
     int32_t n_win, steps, win_stride;
     int32_t in_windowed, out_windowed;
+    int32_t round_tf32;
 } aero_lstm_params;
 int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout,
                       const aero_lstm_params* p, aero_stream_t stream);
@@ -190,6 +196,7 @@ int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh,
  */
 typedef struct {
     int32_t rows, T, H, heads, ndecay, ld;
+    int32_t round_tf32;
 } aero_attn_params;
 int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream);
 

@@ -31,6 +31,7 @@ class EmuEngine(AeroEngine):
         self._stats = None
         self.precision = 0
         self._prof, self._prof_tags = None, set()
+        self._wk = {}
         self.calls = []
 
     def _require(self, x):
@@ -43,7 +44,7 @@ class EmuEngine(AeroEngine):
     def _gemm(self, out, w, *, B, F_out, T, N, C1, a1=None, a2=None, C2=0, F_in=None, T_in=None,
               a1_s=None, a2_s=None, o_s=None, mode=cabi.TAPS_CONV, kf=1, kt=1, stride_f=1, pad_f=0, dil_t=1, pad_t=0,
               f_off=0, bias=None, act=cabi.ACT_NONE, glu=0, stats=None, stats_mode=0, groups=1, addend=None,
-              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0, tag=None):
+              colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0, tag=None, rnd=False):
         self.calls.append(("tapgemm", N, C1 + C2))
         F_in = F_out if F_in is None else F_in
         T_in = T if T_in is None else T_in
@@ -115,7 +116,7 @@ class EmuEngine(AeroEngine):
 
     # ---- aero_norm_act_fwd
     def _norm_act(self, x, stats, gamma, beta, y, *, B, F_in, T, C_, groups, scope, op, F_out=None, f_off=0,
-                  snake_a=None, scale=None, residual=None):
+                  snake_a=None, scale=None, residual=None, rnd=False):
         self.calls.append(("norm_act", op))
         F_out = F_in if F_out is None else F_out
         xv = x.reshape(B, F_in, T, C_).double()

@@ -47,9 +47,9 @@ def test_struct_sizes_match_header(lib):
     assert ctypes.sizeof(cabi.StftParams) == 8 * 4 + 4 * 8
     assert ctypes.sizeof(cabi.IstftParams) == 8 * 4 + 4 * 8
     assert ctypes.sizeof(cabi.TapGemmParams) == 20 * 4 + 15 * 8 + 8
-    assert ctypes.sizeof(cabi.NormActParams) == 10 * 4
-    assert ctypes.sizeof(cabi.LstmParams) == 8 * 4
-    assert ctypes.sizeof(cabi.AttnParams) == 6 * 4
+    assert ctypes.sizeof(cabi.NormActParams) == 11 * 4
+    assert ctypes.sizeof(cabi.LstmParams) == 9 * 4
+    assert ctypes.sizeof(cabi.AttnParams) == 7 * 4
 
 
 def test_oracle_is_not_imported_by_the_product():

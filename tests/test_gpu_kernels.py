@@ -205,3 +205,75 @@ def test_stft_istft_golden_and_roundtrip(golden_dir):
             assert rel_l2(y[..., :n], x[..., :n]) < 1e-5, (i, "roundtrip")
         i += 1
     assert i >= 6
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 path: same contract, TF32 operands.  Inputs are pre-rounded to TF32 so every product is exact
+# in fp32 and the comparison is tight (it checks descriptors / swizzle / tap geometry, not TF32 noise).
+TC_CASES = [c for c in GEMM_CASES if c[0] not in ("k2_thin_in", "thin_out_relu", "convt_s4_crop_affine")] + [
+    ("big_n_tiles", dict(B=1, F_out=2, T=300, N=768, C1=96, kf=3, kt=3, pad_f=1, pad_t=1, stats_mode=1, groups=4)),
+    ("k_tail_48", dict(B=2, F_out=3, T=129, N=96, C1=48, C2=48, glu=1)),
+    ("n_304", dict(B=1, F_out=1, T=1000, N=304, C1=96)),
+    ("hidden12", dict(B=2, F_out=4, T=200, N=12, C1=48, kt=3, dil_t=1, pad_t=1, stats_mode=2)),
+    ("deep_k", dict(B=1, F_out=1, T=256, N=48, C1=1280, kt=9, pad_t=4, act=cabi.ACT_RELU)),
+]
+
+
+@pytest.mark.parametrize("name,cfg", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tapgemm_tcgen05(engines, name, cfg):
+    from aero_b200.engine import tf32_round
+    gpu, emu = engines
+    cfg = dict(cfg)
+    B, F_out, T, N, C1 = cfg["B"], cfg["F_out"], cfg["T"], cfg["N"], cfg["C1"]
+    C2, F_in = cfg.get("C2", 0), cfg.get("F_in", F_out)
+    mode = cfg.get("mode", cabi.TAPS_CONV)
+    nslab = cfg.get("kf", 1) * cfg.get("kt", 1)
+    K = C1 + C2
+    w = tf32_round(pack_taps(rnd(N, K, nslab, seed=1) / math.sqrt(K * (nslab if mode == cabi.TAPS_CONV else 2))))
+    a1 = tf32_round(rnd(B, F_in, T, C1, seed=2)) if C1 else None
+    a2 = tf32_round(rnd(B, F_in, T, C2, seed=3)) if C2 else None
+    bias = rnd(N, seed=4)
+    glu = cfg.get("glu", 0)
+    n_out = N // 2 if glu else N
+    extra = {}
+    if cfg.pop("residual", False):
+        extra["residual"] = rnd(B, F_out, T, n_out, seed=5)
+    if cfg.pop("addend", False):
+        extra["addend"] = rnd(F_out, n_out, seed=6)
+    sm = cfg.get("stats_mode", 0)
+    nslots = {0: 0, 1: B * cfg.get("groups", 1), 2: B * F_out}[sm]
+    for k in ("B", "F_out", "T", "N", "C1"):
+        cfg.pop(k)
+    res = {}
+    for tag, eng, dev in (("cpu", emu, "cpu"), ("gpu", gpu, "cuda")):
+        def mv(t):
+            return None if t is None else t.to(dev)
+        out = torch.full((B, F_out, T, n_out), float("nan"), device=dev)
+        stats = torch.zeros(max(nslots, 1), 2, dtype=torch.float64, device=dev)
+        wd = mv(w)
+        if tag == "gpu":
+            eng.precision = 1
+            eng._wk[wd.data_ptr()] = tf32_round(wd.permute(0, 2, 1).contiguous())
+            before = eng.lib.aero_launch_count()
+        try:
+            eng._gemm(out, wd, a1=mv(a1), a2=mv(a2), B=B, F_out=F_out, T=T, N=N, C1=C1, bias=mv(bias),
+                      stats=stats if sm else None, **{k: mv(v) for k, v in extra.items()}, **cfg)
+            if tag == "gpu":
+                torch.cuda.synchronize()
+        finally:
+            if tag == "gpu":
+                eng.precision = 0
+                eng._wk.clear()
+        res[tag] = (out.cpu(), stats.cpu())
+    assert torch.isfinite(res["gpu"][0]).all()
+    assert rel_l2(res["gpu"][0], res["cpu"][0]) < 3e-6
+    if sm:
+        assert torch.allclose(res["gpu"][1], res["cpu"][1], rtol=1e-4, atol=1e-2)
+
+
+def test_tcgen05_is_selected_for_the_big_convs(engines):
+    gpu, _ = engines
+    p = cabi.TapGemmParams(32, 4, 501, 1536, 4, 501, 0, 384, 0, 3, 3, 1, 1, 1, 1, 0, 0, 0, 1, 4,
+                           0, 0, 0, 4 * 501 * 384, 501 * 384, 384, 0, 4 * 501 * 1536, 501 * 1536, 1536, 0, 0, 0, 0, 0, 0, 0)
+    import ctypes
+    assert gpu.lib.aero_tapgemm_tc_eligible(ctypes.byref(p)) == 1

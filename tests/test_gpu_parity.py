@@ -71,3 +71,19 @@ def test_repeatable_and_buffer_reuse():
     m(b)
     o2 = m(a)
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("case", ["c1_4-16_hop64_b2", "c3_12-48_hop128", "c4_11-44_stereo", "c6_4-16_hop64_short"])
+def test_forward_tf32_tensor_core_path_within_tolerance(golden_dir, case):
+    """precision=1: TF32 tcgen05 tap-GEMMs (fp32 accumulate).  north_star bar: 1e-3 relative."""
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    m = build(str(g["exp"])).cuda()
+    m._engine().precision = 1
+    mix = white_noise((int(g["B"]), m.in_channels, int(g["L"]))).cuda()
+    out, zc = m(mix, return_spec=True)
+    torch.cuda.synchronize()
+    err = rel_l2(out.cpu(), g["out"])
+    zc_r = torch.view_as_real(zc.contiguous()).cpu().reshape(-1)[torch.from_numpy(g["spec_idx"].astype(np.int64))]
+    print(f"{case} [tf32]: rel_l2 wave {err:.3e} spec {rel_l2(zc_r, g['spec_val']):.3e}")
+    assert torch.isfinite(out).all()
+    assert err < TOL
