@@ -47,7 +47,7 @@ class NormActParams(C.Structure):
 
 class LstmParams(C.Structure):
     _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("n_win", i32), ("steps", i32), ("win_stride", i32),
-                ("in_windowed", i32), ("out_windowed", i32), ("round_tf32", i32)]
+                ("in_windowed", i32), ("out_windowed", i32), ("round_tf32", i32), ("precision", i32)]
 
 
 class AttnParams(C.Structure):

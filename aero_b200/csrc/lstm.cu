@@ -132,6 +132,8 @@ static int launch_lstm(const float* gin, const float* bias_pad, const float* whh
     return check_launch("aero_lstm_rec_fwd");
 }
 
+int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, float* hout, const aero_lstm_params& p,
+                   cudaStream_t st);
 }  // namespace aero
 
 extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout,
@@ -143,6 +145,10 @@ extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const 
     AERO_REQUIRE(p->n_win == 1 || (p->win_stride >= 2 && p->win_stride % 2 == 0), "aero_lstm_rec_fwd: win_stride");
     AERO_REQUIRE(p->n_win > 1 || p->steps == p->T || p->in_windowed, "aero_lstm_rec_fwd: single window must span T");
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->precision == 1) {
+        AERO_REQUIRE(bias_pad, "aero_lstm_rec_fwd: bias_pad required");
+        return lstm_tc_launch(gin, bias_pad, whh, hout, *p, st);
+    }
     switch (p->H) {
         case 12: return launch_lstm<12, 16>(gin, bias_pad, whh, hout, *p, st);
         case 24: return launch_lstm<24, 16>(gin, bias_pad, whh, hout, *p, st);

@@ -20,88 +20,18 @@
 #include <cstring>
 
 #include "tapgemm.cuh"
+#include "tc_common.cuh"
 
 namespace aero {
 
 constexpr int kBM = 128;
 constexpr int kBKc = 32;                 // fp32 elements per 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kATileBytes = kBM * 128;   // 16 KB
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 24)) {
-            printf("aero tapgemm_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
-// LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) (8 rows x 128 B = 1024), version 1 [46,48),
-// layout type SWIZZLE_128B = 2 [61,64).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
 struct TcShared {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t acc_full;
     uint32_t tmem_base;
     float stats[8][2];
@@ -126,10 +56,10 @@ __device__ __forceinline__ bool tap_geometry(const aero_tapgemm_params& p, int t
     return it.fi >= 0 && it.fi < p.F_in;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                   const __grid_constant__ CUtensorMap mapW, const TapGemmArgs g, const int BN, const uint32_t idesc,
-                  const uint32_t tmem_cols) {
+                  const uint32_t tmem_cols, const int kStages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = kATileBytes + BN * 128;
@@ -372,8 +302,8 @@ struct MapKeyHash {
     }
 };
 
-static int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key;
@@ -469,10 +399,20 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
     // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    const size_t smem = (size_t)kStages * (kATileBytes + BN * 128) + sizeof(TcShared) + 1024;
+    // pipeline depth: deep for long K loops; shallow for short ones so that several CTAs share an SM and
+    // hide each other's prologue / epilogue (these layers are latency- and HBM-bound, not tensor-bound)
+    const int nch = (p.C1 + kBKc - 1) / kBKc + (p.C2 + kBKc - 1) / kBKc;
+    const int max_iters = nch * ((p.mode == AERO_TAPS_CONV) ? p.kf * p.kt : p.kf / p.stride_f);
+    const int stage_bytes = kATileBytes + BN * 128;
+    int kStages = max_iters < 4 ? max_iters : 4;
+    if (max_iters <= 12 && kStages * stage_bytes > 56 * 1024) kStages = (56 * 1024) / stage_bytes > 2 ? (56 * 1024) / stage_bytes : 2;
+    if (kStages > max_iters) kStages = max_iters;
+    if (max_iters >= 48 && 5 * stage_bytes + 2048 <= 227 * 1024) kStages = 5;
+    if (max_iters >= 48 && 6 * stage_bytes + 2048 <= 227 * 1024) kStages = 6;
+    const size_t smem = (size_t)kStages * stage_bytes + sizeof(TcShared) + 1024;
     cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     dim3 grid((unsigned)tiles, cdiv(p.N, BN));
-    tapgemm_tc_kernel<<<grid, 192, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols);
+    tapgemm_tc_kernel<<<grid, 192, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols, kStages);
     return check_launch("aero_tapgemm_fwd(tcgen05)");
 }
 

@@ -45,6 +45,16 @@ def tf32_round(t):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def lstm_gate_reorder(H):
+    """Row order of the tcgen05 LSTM recurrence: row m*128 + 4*c + gate <-> (cell 32m + c, gate), padded to
+    ceil(H/32) tiles of 128.  Returns (source row in PyTorch's [i|f|g|o] x H order, validity mask)."""
+    nM = (H + 31) // 32
+    idx = torch.arange(nM * 128)
+    cell = 32 * (idx // 128) + (idx % 128) // 4
+    src = ((idx % 4) * H + cell).clamp_max(4 * H - 1)
+    return src, cell < H
+
+
 def glu_perm(n, device):
     """Column order that puts GLU partners (j, j + n/2) next to each other."""
     half = n // 2
@@ -187,12 +197,26 @@ class AeroEngine:
                     if g.lstm:
                         for l in range(2):
                             wih = torch.cat([sd[f"{q}.lstm.lstm.weight_ih_l{l}"], sd[f"{q}.lstm.lstm.weight_ih_l{l}_reverse"]], 0)
-                            W[f"{o}.lstm{l}.wih"] = pack_taps(wih[:, :, None])
+                            W[f"{o}.lstm{l}.ih.w"] = pack_taps(wih[:, :, None])
                             W[f"{o}.lstm{l}.b"] = torch.cat([
                                 sd[f"{q}.lstm.lstm.bias_ih_l{l}"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}"],
                                 sd[f"{q}.lstm.lstm.bias_ih_l{l}_reverse"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}_reverse"]]).contiguous()
                             W[f"{o}.lstm{l}.whh"] = torch.stack([sd[f"{q}.lstm.lstm.weight_hh_l{l}"],
                                                                   sd[f"{q}.lstm.lstm.weight_hh_l{l}_reverse"]]).contiguous()
+                        # tcgen05 recurrence: gate rows re-ordered / padded (include/aero_b200.h, aero_lstm_params.precision)
+                        H_ = sd[f"{q}.lstm.lstm.weight_hh_l0"].shape[1]
+                        src, ok = lstm_gate_reorder(H_)
+                        for l in range(2):
+                            def reord(t):
+                                return torch.where(ok.view(-1, *([1] * (t.dim() - 1))), t[src], torch.zeros_like(t[src]))
+                            wih, whh, bb = [], [], []
+                            for sfx in ("", "_reverse"):
+                                wih.append(reord(sd[f"{q}.lstm.lstm.weight_ih_l{l}{sfx}"]))
+                                whh.append(reord(sd[f"{q}.lstm.lstm.weight_hh_l{l}{sfx}"]))
+                                bb.append(reord(sd[f"{q}.lstm.lstm.bias_ih_l{l}{sfx}"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}{sfx}"]))
+                            W[f"{o}.lstm{l}r.ih.w"] = pack_taps(torch.cat(wih, 0)[:, :, None])
+                            W[f"{o}.lstm{l}r.b"] = torch.cat(bb).contiguous()
+                            W[f"{o}.lstm{l}r.whh"] = tf32_round(torch.cat(whh, 0).contiguous())
                         W[o + ".lin.w"] = pack_taps(sd[q + ".lstm.linear.weight"][:, :, None])
                         W[o + ".lin.b"] = sd[q + ".lstm.linear.bias"].contiguous()
                     if g.attn:
@@ -290,8 +314,10 @@ class AeroEngine:
         cabi.check(rc, self.lib)
         return y
 
-    def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed):
-        p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed, 1 if self.precision == 1 else 0)
+    def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed,
+                  tc=False):
+        p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed,
+                            1 if self.precision == 1 else 0, 1 if tc else 0)
         cabi.check(self.lib.aero_lstm_rec_fwd(_ptr(gin), _ptr(bias_pad), _ptr(whh), _ptr(hout), C.byref(p),
                                               self._stream()), self.lib)
 
@@ -374,16 +400,18 @@ class AeroEngine:
         else:
             steps, stride, n_win = T, 0, 1
         n_seq = rows * n_win
-        gin1 = self._buf(tag + ".gin1", rows * T, 8 * H)
-        self._gemm_flat(gin1, h, W[o + ".lstm0.wih"], rows * T, H, 8 * H, bias=W[o + ".lstm0.b"])
+        tc = self.precision == 1 and H % 4 == 0 and H <= 96
+        L0, L1, G = ("lstm0r", "lstm1r", 2 * ((H + 31) // 32) * 128) if tc else ("lstm0", "lstm1", 8 * H)
+        gin1 = self._buf(tag + ".gin1", rows * T, G)
+        self._gemm_flat(gin1, h, W[f"{o}.{L0}.ih.w"], rows * T, H, G, bias=W[f"{o}.{L0}.b"])
         h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H)
-        self._lstm_rec(gin1, W[o + ".lstm0.b"], W[o + ".lstm0.whh"], h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
-                       stride=stride, in_windowed=0, out_windowed=1)
-        gin2 = self._buf(tag + ".gin2", n_seq * steps, 8 * H)
-        self._gemm_flat(gin2, h1, W[o + ".lstm1.wih"], n_seq * steps, 2 * H, 8 * H, bias=W[o + ".lstm1.b"])
+        self._lstm_rec(gin1, W[f"{o}.{L0}.b"], W[f"{o}.{L0}.whh"], h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+                       stride=stride, in_windowed=0, out_windowed=1, tc=tc)
+        gin2 = self._buf(tag + ".gin2", n_seq * steps, G)
+        self._gemm_flat(gin2, h1, W[f"{o}.{L1}.ih.w"], n_seq * steps, 2 * H, G, bias=W[f"{o}.{L1}.b"])
         h2 = self._buf(tag + ".h2", rows * T, 2 * H)
-        self._lstm_rec(gin2, W[o + ".lstm1.b"], W[o + ".lstm1.whh"], h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
-                       stride=stride, in_windowed=1, out_windowed=0)
+        self._lstm_rec(gin2, W[f"{o}.{L1}.b"], W[f"{o}.{L1}.whh"], h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+                       stride=stride, in_windowed=1, out_windowed=0, tc=tc)
         self._gemm_flat(h, h2, W[o + ".lin.w"], rows * T, 2 * H, H, bias=W[o + ".lin.b"], residual=h, rnd=True)
         return h
 

@@ -147,7 +147,8 @@ class EmuEngine(AeroEngine):
         return y
 
     # ---- aero_lstm_rec_fwd
-    def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed):
+    def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed,
+                  tc=False):
         self.calls.append(("lstm", H))
         G = 4 * H
         n_seq = rows * n_win

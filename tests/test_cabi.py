@@ -48,7 +48,7 @@ def test_struct_sizes_match_header(lib):
     assert ctypes.sizeof(cabi.IstftParams) == 8 * 4 + 4 * 8
     assert ctypes.sizeof(cabi.TapGemmParams) == 20 * 4 + 15 * 8 + 8
     assert ctypes.sizeof(cabi.NormActParams) == 11 * 4
-    assert ctypes.sizeof(cabi.LstmParams) == 9 * 4
+    assert ctypes.sizeof(cabi.LstmParams) == 10 * 4
     assert ctypes.sizeof(cabi.AttnParams) == 7 * 4
 
 

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Run one hot-path kernel shape in isolation (for ncu captures and CUDA-event timing).
+
+    python tools/kprof.py dec0_rw [--precision 1] [--iters 5] [--batch 32]
+
+Shapes are the aero_4-16_512_64, T=501 geometry."""
+import argparse
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from aero_b200 import Aero, aero_kwargs, cabi  # noqa: E402
+from aero_b200.engine import AeroEngine, pack_taps, tf32_round  # noqa: E402
+
+T = 501
+SHAPES = {
+    # name: (kwargs of AeroEngine._gemm without B, note)
+    "dec0_rw": dict(F_out=4, N=1536, C1=0, C2=384, kf=3, kt=3, pad_f=1, pad_t=1, stats_mode=1, groups=4),
+    "dec1_rw": dict(F_out=8, N=768, C1=192, C2=192, kf=3, kt=3, pad_f=1, pad_t=1, stats_mode=1, groups=4),
+    "dec2_rw": dict(F_out=16, N=384, C1=96, C2=96, kf=3, kt=3, pad_f=1, pad_t=1, glu=1),
+    "dec3_rw": dict(F_out=64, N=192, C1=48, C2=48, kf=3, kt=3, pad_f=1, pad_t=1, glu=1),
+    "dec0_ct": dict(F_out=14, F_in=4, N=192, C1=768, mode=cabi.TAPS_CONVT, kf=8, stride_f=2, stats_mode=1, groups=4),
+    "enc3_conv": dict(F_out=4, F_in=8, N=384, C1=192, kf=8, stride_f=2, pad_f=3, stats_mode=1, groups=4),
+    "enc0_ftb2": dict(F_out=256, N=48, C1=48, C2=48, act=cabi.ACT_RELU),
+    "enc0_conv": dict(F_out=64, F_in=256, N=48, C1=48, kf=8, stride_f=4, pad_f=2, act=cabi.ACT_GELU),
+    "enc0_dc_c2": dict(F_out=64, N=96, C1=12, stats_mode=2),
+    "enc3_gin2": dict(F_out=1, N=768, C1=192, T=768 * 200 // 32),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("shape", choices=sorted(SHAPES))
+    ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=32)
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
+    eng = AeroEngine(m)
+    eng.precision = args.precision
+    cfg = dict(SHAPES[args.shape])
+    B = args.batch
+    Tt = cfg.pop("T", T)
+    F_out, N, C1 = cfg.pop("F_out"), cfg.pop("N"), cfg.pop("C1")
+    C2, F_in = cfg.get("C2", 0), cfg.get("F_in", F_out)
+    mode = cfg.get("mode", cabi.TAPS_CONV)
+    nslab = cfg.get("kf", 1) * cfg.get("kt", 1)
+    K = C1 + C2
+    w = tf32_round(pack_taps(torch.randn(N, K, nslab) / math.sqrt(K * nslab))).cuda()
+    eng._wk[w.data_ptr()] = tf32_round(w.permute(0, 2, 1).contiguous())
+    a1 = tf32_round(torch.randn(B, F_in, Tt, C1)).cuda() if C1 else None
+    a2 = tf32_round(torch.randn(B, F_in, Tt, C2)).cuda() if C2 else None
+    bias = torch.randn(N).cuda()
+    n_out = N // 2 if cfg.get("glu") else N
+    out = torch.empty(B, F_out, Tt, n_out, device="cuda")
+    sm = cfg.get("stats_mode", 0)
+    stats = torch.zeros(max(1, {0: 0, 1: B * cfg.get("groups", 1), 2: B * F_out}[sm]), 2, dtype=torch.float64, device="cuda")
+    ntaps = nslab if mode == cabi.TAPS_CONV else cfg["kf"] // cfg["stride_f"]
+    flops = 2.0 * B * F_out * Tt * N * K * ntaps
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.iters + 1)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ms = []
+    for i in range(args.iters + 2):
+        flush.zero_()                       # evict L2 between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng._gemm(out, w, a1=a1, a2=a2, B=B, F_out=F_out, T=Tt, N=N, C1=C1, bias=bias, stats=stats if sm else None, **cfg)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    best = min(ms)
+    print(f"{args.shape}: precision {args.precision} B={B} {flops/1e9:.1f} GFLOP  best {best*1e3:.1f} us  median {sorted(ms)[len(ms)//2]*1e3:.1f} us"
+          f"  -> {flops/best/1e9:.1f} TFLOP/s (best)")
+
+
+if __name__ == "__main__":
+    main()
