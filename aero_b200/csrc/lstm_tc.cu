@@ -2,21 +2,26 @@
 // precision = 1).
 //
 // Per step the recurrent term is the small GEMM  D[gate rows x sequences] = W_hh[gate rows x H] * h^T[H x sequences]:
-//   A = W_hh, loaded ONCE by TMA into shared memory (K-major, SWIZZLE_128B) and resident for all steps;
-//       rows are re-ordered so that TMEM lane r of M-tile m holds (cell 32m + r/4, gate r%4): the four gates
-//       of a cell sit in four adjacent lanes of one warp and are combined with quad shuffles;
+//   A = W_hh, loaded ONCE by TMA into shared memory (K-major, SWIZZLE_128B) and resident for all steps.
+//       Gate rows are re-ordered into 128-row M tiles so that a thread finds the gates it needs in its
+//       own TMEM lane (or one xor-16 shuffle away):
+//         GPT = 1 (64 < H <= 128): tile g holds gate g, lane = cell             -> 4 tiles, no exchange
+//         GPT = 2 (32 < H <=  64): tile t holds gates (2t, 2t+1); in every warp lanes 0-15 carry gate 2t
+//                                  and lanes 16-31 gate 2t+1 of the same 16 cells -> 2 tiles, one shfl.xor 16
 //   B = h of the previous step, written by the cell-update threads straight into the swizzled
 //       shared-memory operand layout (TF32-rounded), 16 sequences per CTA;
-//   D = nM x 16 fp32 columns of TMEM, read back with tcgen05.ld by the same threads.
-// The gate pre-activations of the input projection (computed by the tap-GEMM in the same re-ordered
-// column order, so a warp reads 128 contiguous bytes per sequence) are prefetched while the MMA runs.
-// One elected thread issues the MMAs; a pair of mbarriers ping-pongs between "h ready" and
-// "accumulators ready".  c stays in registers for the whole sequence.
+//   D = (4/GPT) x 16 fp32 columns of TMEM, read back with tcgen05.ld by the same threads.
+// The input-projection gate pre-activations (computed by the tap-GEMM in the same re-ordered column
+// order, so a warp reads 128 contiguous bytes per sequence) are prefetched while the MMA runs.
+// One elected thread issues the MMAs; two mbarriers ping-pong between "h ready" and "accumulators
+// ready".  c stays in registers for the whole sequence.  8 cell-update warps: two per TMEM lane
+// quarter, each owning 8 of the 16 sequences.
 #include "tc_common.cuh"
 
 namespace aero {
 
 constexpr int kNT = 16;          // sequences per CTA (UMMA N)
+constexpr int kNS = 8;           // sequences per cell-update warp
 
 struct LstmTcShared {
     uint64_t w_full;
@@ -26,12 +31,23 @@ struct LstmTcShared {
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 2.0f * fast_sigmoid(2.0f * x) - 1.0f; }
+__device__ __forceinline__ float fast_tanh(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
-template <int NM>   // number of 128-row M tiles = ceil(H / 32)
-__global__ void __launch_bounds__(192, (NM == 3 ? 1 : 2))
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int GPT>   // gates per 128-row tile
+__global__ void __launch_bounds__(320, (GPT == 1 ? 1 : 2))
 lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ gin, const float* __restrict__ bias_pad,
                float* __restrict__ hout, const aero_lstm_params p, const int nK) {
+    constexpr int NM = 4 / GPT;                          // M tiles
+    constexpr int CPW = 32 / GPT;                        // cells per warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                  // [NM][nK] tiles of 128 rows x 128 B
@@ -48,7 +64,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
     if (threadIdx.x == 0) {
         mbar_init(&sh->w_full, 1);
         mbar_init(&sh->acc_ready, 1);
-        mbar_init(&sh->h_ready, 128);
+        mbar_init(&sh->h_ready, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < nK * 2048 / 4; i += blockDim.x) reinterpret_cast<float*>(sB)[i] = 0.f;
@@ -74,14 +90,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         if (lane == 0) {
             // UMMA instruction descriptor: D=F32, A=B=TF32, K-major, N=16, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             mbar_wait(&sh->w_full, 0);
             for (int s = 1; s < p.steps; ++s) {
                 mbar_wait(&sh->h_ready, (uint32_t)((s - 1) & 1));
                 tcgen05_fence_after();
+#pragma unroll
                 for (int m = 0; m < NM; ++m) {
                     for (int kc = 0; kc < nK; ++kc) {
-                        const uint64_t da = make_desc_sw128(smem_u32(sA + (m * nK + kc) * 16384));
-                        const uint64_t db = make_desc_sw128(smem_u32(sB + kc * 2048));
+                        const uint64_t da = make_desc_sw128(a0 + (uint32_t)((m * nK + kc) * 16384));
+                        const uint64_t db = make_desc_sw128(b0 + (uint32_t)(kc * 2048));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_tf32(tmem_base + (uint32_t)(m * kNT), da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
@@ -91,90 +109,106 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             }
         }
     } else {
-        // ===================================================== cell update (warps 2..5, 128 threads)
-        const int q = warp & 3;
-        const int r = q * 32 + lane;                     // TMEM lane inside an M tile
-        const int gate = lane & 3;
-        const int c_local = r >> 2;
+        // ===================================================== cell update (warps 2..9, 256 threads)
+        const int ew = warp - 2;
+        const int q = warp & 3;                          // TMEM lane quarter
+        const int wp = ew >> 2;                          // which half of the 16 sequences
+        const int sub = lane / CPW;                      // gate slot inside the tile (0 for GPT=1)
+        const int cell = q * CPW + (lane % CPW);
+        const bool cell_ok = cell < H;
+        const int r = q * 32 + lane;                     // TMEM lane == gin column inside a tile
         const int half = p.win_stride / 2;
+        const int dpos = dir ? -1 : 1;
+        const int pos0 = dir ? p.steps - 1 : 0;
 
-        // per-sequence addressing (identical for all lanes)
-        int seq_row[kNT], seq_k[kNT];
+        // Per-sequence state (32-bit element offsets; the host checks they fit).  For GPT=2 lane<16 updates even
+        // local sequences, lane>=16 odd ones.
+        int goff[kNS], ooff[kNS], frame0[kNS];
+        uint32_t flags = 0;          // per i: bit i = sequence exists, bit 8+i = first window, bit 16+i = last window
 #pragma unroll
-        for (int n = 0; n < kNT; ++n) {
-            const int s = min(seq0 + n, n_seq - 1);
-            seq_row[n] = s / p.n_win;
-            seq_k[n] = s - seq_row[n] * p.n_win;
+        for (int i = 0; i < kNS; ++i) {
+            const int n = wp * kNS + i;
+            const int sq = min(seq0 + n, n_seq - 1);
+            const int row = sq / p.n_win, k = sq - row * p.n_win;
+            if (seq0 + n < n_seq) flags |= 1u << i;
+            if (k == 0) flags |= 1u << (8 + i);
+            if (k == p.n_win - 1) flags |= 1u << (16 + i);
+            frame0[i] = k * p.win_stride + pos0;
+            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + frame0[i])) * ldg + dir * (NM * 128) + r;
+            ooff[i] = (p.out_windowed ? (sq * p.steps + pos0) : (row * p.T + frame0[i])) * 2 * H + dir * H + cell;
         }
-        float c_state[NM][kNT];
+        const float* bptr = bias_pad + dir * (NM * 128) + r;
+        const int gstep = dpos * ldg, ostep = dpos * 2 * H;
+        // swizzled B-operand address of (sequence n = wp*8+i, k = cell): tile kc = cell/32, row n, chunk (j/4)^(n%8)
+        const int jq = (cell & 31) >> 2;
+        uint8_t* bbase = sB + (cell >> 5) * 2048 + wp * 1024 + ((cell & 3) << 2);
+
+        float c_state[kNS];
 #pragma unroll
-        for (int m = 0; m < NM; ++m)
-#pragma unroll
-            for (int n = 0; n < kNT; ++n) c_state[m][n] = 0.f;
+        for (int i = 0; i < kNS; ++i) c_state[i] = 0.f;
 
         for (int s = 0; s < p.steps; ++s) {
-            const int pos = dir ? p.steps - 1 - s : s;
+            const int pos = pos0 + dpos * s;
             // ---- prefetch the input-projection gate pre-activations (coalesced: lane r is contiguous)
-            float gi[NM][kNT];
+            float gi[NM][kNS];
 #pragma unroll
-            for (int n = 0; n < kNT; ++n) {
-                const float* src;
-                if (p.in_windowed) {
-                    src = gin + ((int64_t)min(seq0 + n, n_seq - 1) * p.steps + pos) * ldg;
-                } else {
-                    const int frame = seq_k[n] * p.win_stride + pos;
-                    src = frame < p.T ? gin + ((int64_t)seq_row[n] * p.T + frame) * ldg : bias_pad;
-                }
+            for (int i = 0; i < kNS; ++i) {
+                const float* src = gin + goff[i];
+                if (!p.in_windowed && frame0[i] + dpos * s >= p.T) src = bptr;   // zero-padded frames: bias only
 #pragma unroll
-                for (int m = 0; m < NM; ++m) gi[m][n] = src[(dir * NM + m) * 128 + r];
+                for (int m = 0; m < NM; ++m) gi[m][i] = src[m * 128];
+                goff[i] += gstep;
             }
             if (s > 0) {
                 mbar_wait(&sh->acc_ready, (uint32_t)((s - 1) & 1));
                 tcgen05_fence_after();
             }
+            float a[NM][kNS];
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                uint32_t acc[16];
+                uint32_t acc[8];
                 if (s > 0) {
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * kNT), acc);
+                    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * kNT + wp * kNS), acc);
                 } else {
 #pragma unroll
-                    for (int n = 0; n < kNT; ++n) acc[n] = 0u;
+                    for (int i = 0; i < kNS; ++i) acc[i] = 0u;
                 }
-                const int cell = m * 32 + c_local;
-                const bool cell_ok = cell < H;
+                const int gate = m * GPT + sub;           // PyTorch order: 0 i, 1 f, 2 g, 3 o
 #pragma unroll
-                for (int n = 0; n < kNT; ++n) {
-                    const float x = __uint_as_float(acc[n]) + gi[m][n];
-                    const float sg = fast_sigmoid(gate == 2 ? 2.0f * x : x);
-                    const float a = gate == 2 ? 2.0f * sg - 1.0f : sg;
-                    const int base = lane & ~3;
-                    const float fg = __shfl_sync(0xffffffffu, a, base + 1);
-                    const float gg = __shfl_sync(0xffffffffu, a, base + 2);
-                    const float og = __shfl_sync(0xffffffffu, a, base + 3);
-                    if (gate == 0) {
-                        const float c = fg * c_state[m][n] + a * gg;
-                        c_state[m][n] = c;
-                        const float h = round_tf32_rna(og * fast_tanh(c));
-                        if (cell_ok) {
-                            // B operand tile kc = cell/32: row n (sequence), 16-byte chunks XOR-swizzled by (row % 8)
-                            const int kc = cell >> 5, j = cell & 31;
-                            const uint32_t off = (uint32_t)(kc * 2048 + (n >> 3) * 1024 + (n & 7) * 128 + ((((j >> 2) ^ (n & 7)) << 4) | ((j & 3) << 2)));
-                            *reinterpret_cast<float*>(sB + off) = h;
-                            if (seq0 + n < n_seq) {
-                                if (p.out_windowed) {
-                                    hout[((int64_t)(seq0 + n) * p.steps + pos) * 2 * H + dir * H + cell] = h;
-                                } else {
-                                    const int frame = seq_k[n] * p.win_stride + pos;
-                                    const int lo = (seq_k[n] == 0) ? 0 : half;
-                                    const int hi = (seq_k[n] == p.n_win - 1) ? p.steps : p.steps - half;
-                                    if (pos >= lo && pos < hi && frame < p.T)
-                                        hout[((int64_t)seq_row[n] * p.T + frame) * 2 * H + dir * H + cell] = h;
-                                }
-                            }
+                for (int i = 0; i < kNS; ++i) {
+                    const float x = __uint_as_float(acc[i]) + gi[m][i];
+                    a[m][i] = (gate == 2) ? fast_tanh(x) : fast_sigmoid(x);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kNS; ++i) {
+                float ig, fg, gg, og;
+                bool mine = true;
+                if (GPT == 1) {
+                    ig = a[0][i]; fg = a[1 % NM][i]; gg = a[2 % NM][i]; og = a[3 % NM][i];
+                } else {
+                    const float p0 = __shfl_xor_sync(0xffffffffu, a[0][i], 16);
+                    const float p1 = __shfl_xor_sync(0xffffffffu, a[1 % NM][i], 16);
+                    if (sub == 0) { ig = a[0][i]; gg = a[1 % NM][i]; fg = p0; og = p1; }
+                    else          { fg = a[0][i]; og = a[1 % NM][i]; ig = p0; gg = p1; }
+                    mine = (i & 1) == sub;
+                }
+                if (mine) {
+                    const float c = fg * c_state[i] + ig * gg;
+                    c_state[i] = c;
+                    const float h = round_tf32_rna(og * fast_tanh(c));
+                    if (cell_ok) {
+                        *reinterpret_cast<float*>(bbase + i * 128 + ((jq ^ i) << 4)) = h;
+                        bool wr = (flags >> i) & 1u;
+                        if (!p.out_windowed) {
+                            const int lo = ((flags >> (8 + i)) & 1u) ? 0 : half;
+                            const int hi = ((flags >> (16 + i)) & 1u) ? p.steps : p.steps - half;
+                            wr = wr && pos >= lo && pos < hi && frame0[i] + dpos * s < p.T;
                         }
+                        if (wr) hout[ooff[i]] = h;
                     }
                 }
+                ooff[i] += ostep;
             }
             if (s + 1 < p.steps) {
                 fence_proxy_async_smem();                // generic-proxy stores of h -> visible to the tensor core
@@ -193,11 +227,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
 int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, float* hout, const aero_lstm_params& p,
                    cudaStream_t st) {
     const int H = p.H;
-    const int nM = (H + 31) / 32, nK = (H + 31) / 32;
-    if (H % 4 || nM > 3) {
-        set_error("aero_lstm_rec_fwd(tcgen05): hidden size %d unsupported (multiple of 4, <= 96)", H);
+    if (H % 4 || H <= 32 || H > 128) {
+        set_error("aero_lstm_rec_fwd(tcgen05): hidden size %d unsupported (multiple of 4 in (32, 128])", H);
         return AERO_ERR_UNSUPPORTED;
     }
+    const int gpt = H <= 64 ? 2 : 1;
+    const int nM = 4 / gpt, nK = (H + 31) / 32;
     CUtensorMap mW;
     uint64_t dims[2] = {(uint64_t)H, (uint64_t)(2 * nM * 128)};
     uint64_t strides[1] = {(uint64_t)H * 4};
@@ -205,21 +240,23 @@ int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, 
     int rc = encode_map(&mW, whh_r, 2, dims, strides, box);
     if (rc != AERO_OK) return rc;
     const size_t smem = (size_t)nM * nK * 16384 + (size_t)nK * 2048 + sizeof(LstmTcShared) + 1024;
+    if (smem > 227 * 1024) {
+        set_error("aero_lstm_rec_fwd(tcgen05): hidden size %d needs %zu bytes of shared memory", H, smem);
+        return AERO_ERR_UNSUPPORTED;
+    }
     const int n_seq = p.rows * p.n_win;
+    const int64_t max_rows = (int64_t)n_seq * p.steps > (int64_t)p.rows * p.T ? (int64_t)n_seq * p.steps : (int64_t)p.rows * p.T;
+    if ((max_rows + p.steps) * (2 * nM * 128) >= (1ll << 31)) {
+        set_error("aero_lstm_rec_fwd(tcgen05): problem too large for 32-bit offsets (%lld rows)", (long long)max_rows);
+        return AERO_ERR_UNSUPPORTED;
+    }
     dim3 grid(cdiv(n_seq, kNT), 2);
-    switch (nM) {
-        case 1:
-            cudaFuncSetAttribute(lstm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            lstm_tc_kernel<1><<<grid, 192, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
-            break;
-        case 2:
-            cudaFuncSetAttribute(lstm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            lstm_tc_kernel<2><<<grid, 192, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
-            break;
-        default:
-            cudaFuncSetAttribute(lstm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            lstm_tc_kernel<3><<<grid, 192, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
-            break;
+    if (gpt == 1) {
+        cudaFuncSetAttribute(lstm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_tc_kernel<1><<<grid, 320, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
+    } else {
+        cudaFuncSetAttribute(lstm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_tc_kernel<2><<<grid, 320, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
     }
     return check_launch("aero_lstm_rec_fwd(tcgen05)");
 }

@@ -46,12 +46,20 @@ def tf32_round(t):
 
 
 def lstm_gate_reorder(H):
-    """Row order of the tcgen05 LSTM recurrence: row m*128 + 4*c + gate <-> (cell 32m + c, gate), padded to
-    ceil(H/32) tiles of 128.  Returns (source row in PyTorch's [i|f|g|o] x H order, validity mask)."""
-    nM = (H + 31) // 32
-    idx = torch.arange(nM * 128)
-    cell = 32 * (idx // 128) + (idx % 128) // 4
-    src = ((idx % 4) * H + cell).clamp_max(4 * H - 1)
+    """Row order of the tcgen05 LSTM recurrence (csrc/lstm_tc.cu): 4/GPT tiles of 128 rows per direction.
+    GPT=1 (H > 64): tile g = gate g, lane = cell.  GPT=2 (H <= 64): tile t = gates (2t, 2t+1); in each 32-lane
+    group lanes 0-15 carry gate 2t and lanes 16-31 gate 2t+1 of the same 16 cells.
+    Returns (source row in PyTorch's [i|f|g|o] x H order, validity mask)."""
+    gpt = 2 if H <= 64 else 1
+    n_tiles = 4 // gpt
+    idx = torch.arange(n_tiles * 128)
+    m, r = idx // 128, idx % 128
+    if gpt == 1:
+        gate, cell = m, r
+    else:
+        q, lane = r // 32, r % 32
+        gate, cell = 2 * m + lane // 16, 16 * q + lane % 16
+    src = (gate * H + cell).clamp_max(4 * H - 1)
     return src, cell < H
 
 
@@ -90,9 +98,10 @@ class AeroEngine:
         self._bufs = {}
         self._windows = {}
         self._stats = None
-        self.precision = 0          # 0: fp32 SIMT tap-GEMM; 1: TF32 tcgen05 where eligible
+        self.precision = 1          # 1: TF32 tcgen05 tensor-core path where eligible (default); 0: all-fp32 SIMT path
+        self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
         self._prof, self._prof_tags = None, set()
-        self._wk = {}
+        self._wk, self._wname = {}, {}
 
     # ------------------------------------------------------------------ plumbing
     def invalidate(self):
@@ -205,7 +214,7 @@ class AeroEngine:
                                                                   sd[f"{q}.lstm.lstm.weight_hh_l{l}_reverse"]]).contiguous()
                         # tcgen05 recurrence: gate rows re-ordered / padded (include/aero_b200.h, aero_lstm_params.precision)
                         H_ = sd[f"{q}.lstm.lstm.weight_hh_l0"].shape[1]
-                        src, ok = lstm_gate_reorder(H_)
+                        src, ok = (t_.to(dev) for t_ in lstm_gate_reorder(H_))
                         for l in range(2):
                             def reord(t):
                                 return torch.where(ok.view(-1, *([1] * (t.dim() - 1))), t[src], torch.zeros_like(t[src]))
@@ -244,10 +253,11 @@ class AeroEngine:
             W[p + ".ct.b"] = sd[p + ".conv_tr.bias"].contiguous()
         out = {k: v.to(device=dev, dtype=torch.float32) for k, v in W.items()}
         # K-major TF32 twins of every tap-GEMM weight for the tcgen05 path: [taps, K, pad4(N)] -> [taps, pad4(N), K]
-        self._wk = {}
+        self._wk, self._wname = {}, {}
         for k in [k for k in out if k.endswith(".w") and out[k].dim() == 3]:
             out[k + "@k"] = tf32_round(out[k].permute(0, 2, 1).contiguous())
             self._wk[out[k].data_ptr()] = out[k + "@k"]
+            self._wname[out[k].data_ptr()] = k[:-2]
         return out
 
     # ------------------------------------------------------------------ kernel wrappers
@@ -265,10 +275,11 @@ class AeroEngine:
         a2_s = a2_s or (cl(F_in, C2) if a2 is not None else (0, 0, 0))
         o_s = o_s or (F_out * T * n_out, T * n_out, n_out)
         r_s = r_s or (o_s if residual is not None else (0, 0, 0))
+        tag = tag or self._wname.get(w.data_ptr())
         flags = 1 if (rnd and self.precision == 1) else 0
         p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
                                act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 0, flags)
-        if self.precision == 1 and w_sb == 0:
+        if self.precision == 1 and w_sb == 0 and not (tag and self.fp32_tags and tag.startswith(self.fp32_tags)):
             wk = self._wk.get(w.data_ptr())
             if wk is not None and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
                 p.precision, w = 1, wk
@@ -400,8 +411,8 @@ class AeroEngine:
         else:
             steps, stride, n_win = T, 0, 1
         n_seq = rows * n_win
-        tc = self.precision == 1 and H % 4 == 0 and H <= 96
-        L0, L1, G = ("lstm0r", "lstm1r", 2 * ((H + 31) // 32) * 128) if tc else ("lstm0", "lstm1", 8 * H)
+        tc = self.precision == 1 and H % 4 == 0 and 32 < H <= 96
+        L0, L1, G = ("lstm0r", "lstm1r", 2 * (2 if H <= 64 else 4) * 128) if tc else ("lstm0", "lstm1", 8 * H)
         gin1 = self._buf(tag + ".gin1", rows * T, G)
         self._gemm_flat(gin1, h, W[f"{o}.{L0}.ih.w"], rows * T, H, G, bias=W[f"{o}.{L0}.b"])
         h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H)
@@ -500,7 +511,7 @@ class AeroEngine:
         c1 = 0 if x is None else Cc
         y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc)
         common = dict(a1=x, a2=skip, B=B, F_out=Fq, T=T, N=4 * Cc, C1=c1, C2=Cc, kf=3, kt=3, pad_f=1, pad_t=1,
-                      bias=W[p + ".rw.b"], tag=p + ".rw")
+                      bias=W[p + ".rw.b"])
         if g.norm:
             st = self._stats.take(B * kw["norm_groups"])
             raw = self._buf(tag + ".rw", B, Fq, T, 4 * Cc)

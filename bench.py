@@ -216,7 +216,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    eng.start_profile(("decoder.0.rw", "decoder.1.rw", "decoder.2.rw", "decoder.3.rw"))
+    eng.start_profile(("decoder.0.rw", "decoder.1.rw", "decoder.2.rw", "decoder.3.rw"))   # tags = packed-weight names
     launches0 = lib.aero_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -31,7 +31,8 @@ class EmuEngine(AeroEngine):
         self._stats = None
         self.precision = 0
         self._prof, self._prof_tags = None, set()
-        self._wk = {}
+        self._wk, self._wname = {}, {}
+        self.fp32_tags = ()
         self.calls = []
 
     def _require(self, x):

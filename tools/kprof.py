@@ -32,14 +32,48 @@ SHAPES = {
 }
 
 
+def run_lstm(args):
+    """enc3-like BiLSTM layer-2 recurrence: H=96 (or 48), 768 (1536) windows of 200 steps."""
+    from aero_b200.engine import lstm_gate_reorder
+    H = 96 if args.shape == "lstm96" else 48
+    rows = (4 if H == 96 else 8) * args.batch
+    T, n_win, steps, stride = 501, 6, 200, 100
+    m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
+    eng = AeroEngine(m)
+    eng.precision = args.precision
+    tc = args.precision == 1
+    G = 2 * (2 if H <= 64 else 4) * 128 if tc else 8 * H
+    gin = torch.randn(rows * n_win * steps, G, device="cuda")
+    bias = torch.randn(G, device="cuda")
+    whh = torch.randn(2, 4 * H, H) / math.sqrt(H)
+    if tc:
+        src, ok = lstm_gate_reorder(H)
+        whh = tf32_round(torch.cat([torch.where(ok[:, None], whh[d][src], torch.zeros(())) for d in range(2)], 0).contiguous())
+    whh = whh.cuda()
+    hout = torch.zeros(rows * T, 2 * H, device="cuda")
+    ms = []
+    for i in range(args.iters + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng._lstm_rec(gin, bias, whh, hout, rows=rows, T=T, H=H, n_win=n_win, steps=steps, stride=stride, in_windowed=1,
+                      out_windowed=0, tc=tc)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    print(f"{args.shape}: precision {args.precision} rows {rows} best {min(ms)*1e3:.1f} us -> {min(ms)*1e3/steps:.2f} us/step")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("shape", choices=sorted(SHAPES))
+    ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48"])
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
     args = ap.parse_args()
     torch.manual_seed(0)
+    if args.shape.startswith("lstm"):
+        return run_lstm(args)
     m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
     eng = AeroEngine(m)
     eng.precision = args.precision
