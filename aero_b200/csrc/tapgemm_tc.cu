@@ -34,7 +34,7 @@ struct TcShared {
     uint64_t empty[kMaxStages];
     uint64_t acc_full;
     uint32_t tmem_base;
-    float stats[8][2];
+    float stats[4][8][2];      // [epilogue warp][group slot][sum, sumsq]: fixed-order reduction, run-to-run deterministic
 };
 
 // number of (tap, source, channel-chunk) iterations and their enumeration, shared by all roles
@@ -86,7 +86,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
         for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
         mbar_init(&sh->acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 8; ++i) { sh->stats[i][0] = 0.f; sh->stats[i][1] = 0.f; }
+        for (int w = 0; w < 4; ++w)
+            for (int i = 0; i < 8; ++i) { sh->stats[w][i][0] = 0.f; sh->stats[w][i][1] = 0.f; }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(tmem_cols) : "memory");
@@ -210,7 +211,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     if (gi != cur_g) {
                         if (cur_g >= 0) {
                             const float a = warp_sum(ssum), c = warp_sum(ssq);
-                            if (lane == 0) { atomicAdd(&sh->stats[cur_g - g_lo][0], a); atomicAdd(&sh->stats[cur_g - g_lo][1], c); }
+                            if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
                         }
                         cur_g = gi; ssum = 0.f; ssq = 0.f;
                     }
@@ -246,12 +247,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
         if (p.stats_mode != 0) {
             if (cur_g >= 0) {
                 const float a = warp_sum(ssum), c = warp_sum(ssq);
-                if (lane == 0) { atomicAdd(&sh->stats[cur_g - g_lo][0], a); atomicAdd(&sh->stats[cur_g - g_lo][1], c); }
+                if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int e = threadIdx.x - 64;
             if (e < 8) {
-                const float a = sh->stats[e][0], c = sh->stats[e][1];
+                const float a = (sh->stats[0][e][0] + sh->stats[1][e][0]) + (sh->stats[2][e][0] + sh->stats[3][e][0]);
+                const float c = (sh->stats[0][e][1] + sh->stats[1][e][1]) + (sh->stats[2][e][1] + sh->stats[3][e][1]);
                 const int gi = g_lo + e;
                 const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
                 if (gi < ngroups && (a != 0.f || c != 0.f)) {
