@@ -54,7 +54,7 @@ class AttnParams(C.Structure):
     _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32), ("round_tf32", i32)]
 
 
-TAPS_CONV, TAPS_CONVT = 0, 1
+TAPS_CONV, TAPS_CONVT, TAPS_MIX = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES = 0, 1, 2, 3, 4
 

@@ -19,6 +19,9 @@ extern "C" int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w
     } else if (p.mode == AERO_TAPS_CONVT) {
         AERO_REQUIRE(p.kt == 1 && p.kf % p.stride_f == 0, "aero_tapgemm_fwd: transposed conv needs kt=1 and kf %% stride == 0");
         ntaps = p.kf / p.stride_f;
+    } else if (p.mode == AERO_TAPS_MIX) {
+        AERO_REQUIRE(p.precision == 1, "aero_tapgemm_fwd: AERO_TAPS_MIX exists on the tcgen05 path only (precision 1)");
+        ntaps = 1;
     } else {
         set_error("aero_tapgemm_fwd: mode=%d", p.mode);
         return AERO_ERR_INVALID;

@@ -76,10 +76,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
     const int n0 = blockIdx.y * BN;
     const int nch1 = (p.C1 + kBKc - 1) / kBKc, nch2 = (p.C2 + kBKc - 1) / kBKc;
 
+    const bool mix = p.mode == AERO_TAPS_MIX;
     int n_iters = 0;
-    for (int tap = 0; tap < g.ntaps; ++tap) {
-        TapIter it;
-        if (tap_geometry(p, tap, fo, it)) n_iters += nch1 + nch2;
+    if (mix) {
+        n_iters = nch1;
+    } else {
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+            TapIter it;
+            if (tap_geometry(p, tap, fo, it)) n_iters += nch1 + nch2;
+        }
     }
 
     if (threadIdx.x == 0) {
@@ -106,7 +111,20 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (uint32_t)stage_bytes;
-            for (int tap = 0; tap < g.ntaps; ++tap) {
+            if (mix) {
+                // A = activations [K rows][M contiguous]: four 32(m) x 32(k) boxes form one MN-major 128 x 32 operand tile
+                for (int kc = 0; kc < nch1; ++kc) {
+                    mbar_wait(&sh->empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    mbar_expect_tx(&sh->full[stage], tx);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_3d(sa + j * 4096, &mapA1, &sh->full[stage], t0 + 32 * j, kc * kBKc, b);
+                    tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kc * kBKc, n0, 0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            for (int tap = 0; tap < (mix ? 0 : g.ntaps); ++tap) {
                 TapIter it;
                 if (!tap_geometry(p, tap, fo, it)) continue;
                 for (int src = 0; src < 2; ++src) {
@@ -133,10 +151,21 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 mbar_wait(&sh->full[stage], phase);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kATileBytes);
+                const uint64_t db = make_desc_sw128(sa + kATileBytes);
+                if (mix) {
+                    // MN-major A (cute::UMMA canonical ((4,8,m),(8,k)):((1,4,LBO),(32,SBO))): 32-element atoms along M are
+                    // LBO = 4096 B apart, 8-row atoms along K are SBO = 1024 B apart; one UMMA (K = 8) consumes one K atom.
+                    const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                                        ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 #pragma unroll
-                for (int k = 0; k < kBKc / 8; ++k)      // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
-                    umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < kBKc / 8; ++k)
+                        umma_tf32(tmem_base, da + (uint64_t)(k * (1024 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                } else {
+                    const uint64_t da = make_desc_sw128(sa);
+#pragma unroll
+                    for (int k = 0; k < kBKc / 8; ++k)      // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
+                        umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&sh->empty[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -165,7 +194,27 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
         float ssum = 0.f, ssq = 0.f;
         const int g_lo = (p.glu ? n0 >> 1 : n0) / gw;
 
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (mix) {
+            // transposed store: lane = pixel m (contiguous in memory), column = output row n
+            const float gate = (row_ok && g.colscale) ? g.colscale[(int64_t)b * p.cs_sb + t] : 1.f;
+            float* ob = g.out + (int64_t)b * p.o_sb + t;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < p.N) {
+                            float x = __uint_as_float(r[j]) * gate;
+                            if (rnd) x = round_tf32_rna(x);
+                            ob[(int64_t)n * p.o_st] = x;
+                        }
+                    }
+                }
+            }
+        }
+        for (int c0 = 0; c0 < (mix ? 0 : BN); c0 += 16) {
             uint32_t r[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -348,6 +397,9 @@ static int pick_bn(int N) {
 }
 
 bool tapgemm_tc_eligible(const aero_tapgemm_params& p) {
+    if (p.mode == AERO_TAPS_MIX)
+        return p.w_sb == 0 && p.C1 % 4 == 0 && p.C2 == 0 && p.T % 4 == 0 && p.a1_st % 4 == 0 && p.a1_sb % 4 == 0 && p.N >= 8 &&
+               p.stats_mode == 0 && !p.glu && p.F_out == 1 && p.F_in == 1;
     if (p.w_sb != 0) return false;                                   // activations-as-weights (FTB frequency mix)
     if (p.N < 8) return false;                                       // thin outputs stay on the SIMT path
     const int K = p.C1 + p.C2;
@@ -380,10 +432,17 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     const aero_tapgemm_params& p = g.p;
     const int K = p.C1 + p.C2;
     const int BN = pick_bn(p.N);
-    const int nslab = (p.mode == AERO_TAPS_CONV) ? p.kf * p.kt : p.kf;
+    const int nslab = (p.mode == AERO_TAPS_CONVT) ? p.kf : p.kf * p.kt;
     CUtensorMap mA1, mA2, mW;
     int rc;
-    if (p.C1) { if ((rc = make_a_map(&mA1, g.a1, p.C1, p, p.a1_sb, p.a1_sf, p.a1_st)) != AERO_OK) return rc; }
+    const bool mix = p.mode == AERO_TAPS_MIX;
+    if (mix) {
+        // activations as [K = C1 rows][M = T contiguous] per batch item
+        uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.C1, (uint64_t)p.B};
+        uint64_t strides[2] = {(uint64_t)p.a1_st * 4, (uint64_t)(p.a1_sb > 0 ? p.a1_sb : (int64_t)p.a1_st * p.C1) * 4};
+        uint32_t box[3] = {32, 32, 1};
+        if ((rc = encode_map(&mA1, g.a1, 3, dims, strides, box)) != AERO_OK) return rc;
+    } else if (p.C1) { if ((rc = make_a_map(&mA1, g.a1, p.C1, p, p.a1_sb, p.a1_sf, p.a1_st)) != AERO_OK) return rc; }
     if (p.C2) { if ((rc = make_a_map(&mA2, g.a2, p.C2, p, p.a2_sb, p.a2_sf, p.a2_st)) != AERO_OK) return rc; }
     if (!p.C1) mA1 = mA2;
     if (!p.C2) mA2 = mA1;
@@ -400,11 +459,12 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
     // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24) |
+                           (mix ? (1u << 15) : 0u);                 // bit 15: A is MN-major
     // pipeline depth: deep for long K loops; shallow for short ones so that several CTAs share an SM and
     // hide each other's prologue / epilogue (these layers are latency- and HBM-bound, not tensor-bound)
     const int nch = (p.C1 + kBKc - 1) / kBKc + (p.C2 + kBKc - 1) / kBKc;
-    const int max_iters = nch * ((p.mode == AERO_TAPS_CONV) ? p.kf * p.kt : p.kf / p.stride_f);
+    const int max_iters = nch * ((p.mode == AERO_TAPS_CONVT) ? p.kf / p.stride_f : p.kf * p.kt);
     const int stage_bytes = kATileBytes + BN * 128;
     int kStages = max_iters < 4 ? max_iters : 4;
     if (max_iters <= 12 && kStages * stage_bytes > 56 * 1024) kStages = (56 * 1024) / stage_bytes > 2 ? (56 * 1024) / stage_bytes : 2;

@@ -254,6 +254,8 @@ class AeroEngine:
         out = {k: v.to(device=dev, dtype=torch.float32) for k, v in W.items()}
         # K-major TF32 twins of every tap-GEMM weight for the tcgen05 path: [taps, K, pad4(N)] -> [taps, pad4(N), K]
         self._wk, self._wname = {}, {}
+        for k in [k for k in out if k.endswith("ftbfc.w")]:
+            out[k + "@k"] = tf32_round(out[k])          # [F', F] is already K-contiguous
         for k in [k for k in out if k.endswith(".w") and out[k].dim() == 3]:
             out[k + "@k"] = tf32_round(out[k].permute(0, 2, 1).contiguous())
             self._wk[out[k].data_ptr()] = out[k + "@k"]
@@ -279,7 +281,9 @@ class AeroEngine:
         flags = 1 if (rnd and self.precision == 1) else 0
         p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
                                act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 0, flags)
-        if self.precision == 1 and w_sb == 0 and not (tag and self.fp32_tags and tag.startswith(self.fp32_tags)):
+        if mode == cabi.TAPS_MIX:
+            p.precision = 1                      # tcgen05-only mode; `w` is already K-major / TF32
+        elif self.precision == 1 and w_sb == 0 and not (tag and self.fp32_tags and tag.startswith(self.fp32_tags)):
             wk = self._wk.get(w.data_ptr())
             if wk is not None and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
                 p.precision, w = 1, wk
@@ -395,9 +399,16 @@ class AeroEngine:
         self._gemm(G, W[p + ".ftb1d.w"], a1=R, B=B, F_out=1, T=T, N=Cc, C1=Fq * r, kt=9, pad_t=4,
                    bias=W[p + ".ftb1d.b"], act=ACT_RELU, a1_s=(T * Fq * r, 0, Fq * r), o_s=(T * Cc, 0, Cc))
         Y = self._buf(tag + ".Y", B, Fq, T, Cc)
-        # frequency mixing as a GEMM whose "weights" are the activations: out[f'] = sum_f Wfc[f',f] x[f], times the gate
-        self._gemm(Y, x, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq, a1_s=(0, 0, Fq),
-                   w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True)
+        if self.precision == 1 and Fq % 4 == 0 and Fq >= 8 and not (self.fp32_tags and (p + ".ftbfc").startswith(self.fp32_tags)):
+            # frequency mixing on the tensor cores: contraction over the row axis, activations as the MN-major operand
+            self._gemm(Y, W[p + ".ftbfc.w@k"], a1=x, mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc, N=Fq, C1=Fq,
+                       a1_s=(Fq * T * Cc, 0, T * Cc), o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True,
+                       tag=p + ".ftbfc")
+        else:
+            # fp32 path: a GEMM whose "weights" are the activations: out[f'] = sum_f Wfc[f',f] x[f], times the gate
+            self._gemm(Y, x, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq, a1_s=(0, 0, Fq),
+                       w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True,
+                       tag=p + ".ftbfc")
         out = self._buf(tag + ".out", B, Fq, T, Cc)
         self._gemm(out, W[p + ".ftb2.w"], a1=Y, a2=x, B=1, F_out=1, T=B * Fq * T, N=Cc, C1=Cc, C2=Cc,
                    bias=W[p + ".ftb2.b"], act=ACT_RELU, rnd=True)

@@ -93,6 +93,10 @@ int aero_istft_fwd(const float* z, const float* window, float* y,
  *   mode AERO_TAPS_CONVT : fo' = fo + f_out_offset (row in the uncropped output),
  *                          jf in [0, kf/stride_f): kf_idx = fo' % stride_f + jf*stride_f,
  *                          fi = fo' / stride_f - jf,  slab = kf_idx  (nn.ConvTranspose2d [k,1]/[s,1])
+ *   mode AERO_TAPS_MIX   : (precision 1 only) contraction over the ROW axis of a channels-last tensor, FTB's
+ *                          `freq_fc` (modules.py:296,317-320):  out[b][n][m] = colscale[b][m] * sum_{k<C1} a1[b][k][m] * W[n][k],
+ *                          m < T pixels (contiguous), a1 element (b,k,m) at a1 + b*a1_sb + k*a1_st + m, out element
+ *                          at out + b*o_sb + n*o_st + m, colscale at colscale + b*cs_sb + m.  F_out = F_in = 1.
  * Replaces nn.Conv2d/ConvTranspose2d (aero.py:89,95,101,172,179), nn.Conv1d (modules.py:80-92,
  * 206,209,292), nn.Linear (modules.py:29,296) and their cuDNN/cuBLAS kernels.
  *
@@ -106,7 +110,7 @@ int aero_istft_fwd(const float* z, const float* window, float* y,
  * Generic strides (in floats) let one kernel serve NCHW-free layouts: element (b,f,t,c) of a
  * source is at  src + b*sb + f*sf + t*st + c.
  */
-enum { AERO_TAPS_CONV = 0, AERO_TAPS_CONVT = 1 };
+enum { AERO_TAPS_CONV = 0, AERO_TAPS_CONVT = 1, AERO_TAPS_MIX = 2 };
 enum { AERO_ACT_NONE = 0, AERO_ACT_GELU = 1, AERO_ACT_RELU = 2 };
 typedef struct {
     int32_t B, F_out, T, N;

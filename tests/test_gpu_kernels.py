@@ -320,3 +320,18 @@ def test_lstm_layer_pair_tcgen05(engines, H, T, rows):
     e1, e2 = rel_l2(h1.cpu(), h1c), rel_l2(h2.cpu(), h2c)
     print(f"lstm tcgen05 H={H} T={T}: rel_l2 {e1:.2e} {e2:.2e}")
     assert e1 < 2e-3 and e2 < 2e-3
+
+
+@pytest.mark.parametrize("B,Fq,T,Cc", [(2, 256, 37, 48), (1, 64, 131, 48), (3, 16, 50, 96), (2, 8, 77, 192)])
+def test_freq_mix_tcgen05_mn_major(engines, B, Fq, T, Cc):
+    """AERO_TAPS_MIX: contraction over the frequency rows with the activations as the MN-major UMMA operand."""
+    from aero_b200.engine import tf32_round
+    gpu, _ = engines
+    x, wfc, gate = tf32_round(rnd(B, Fq, T, Cc, seed=1)), tf32_round(rnd(Fq, Fq, seed=2) / math.sqrt(Fq)), rnd(B, T, Cc, seed=3)
+    y = torch.full((B, Fq, T, Cc), float("nan"), device="cuda")
+    gpu._gemm(y, wfc.cuda(), a1=x.cuda(), mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc, N=Fq, C1=Fq,
+              a1_s=(Fq * T * Cc, 0, T * Cc), o_s=(Fq * T * Cc, 0, T * Cc), colscale=gate.cuda(), cs_s=(T * Cc, 0))
+    torch.cuda.synchronize()
+    ref = torch.einsum("gf,bftc->bgtc", wfc.double(), x.double()) * gate[:, None].double()
+    assert torch.isfinite(y).all()
+    assert rel_l2(y.cpu(), ref) < 5e-6
