@@ -153,10 +153,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                 const uint64_t db = make_desc_sw128(sa + kATileBytes);
                 if (mix) {
-                    // MN-major A (cute::UMMA canonical ((4,8,m),(8,k)):((1,4,LBO),(32,SBO))): 32-element atoms along M are
-                    // LBO = 4096 B apart, 8-row atoms along K are SBO = 1024 B apart; one UMMA (K = 8) consumes one K atom.
-                    const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-                                        ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                    // MN-major tf32 A: the only legal layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom: 32 elements
+                    // along M x 4 rows along K = 512 B atoms, 32-byte chunks XOR-swizzled by row%4; TMA SWIZZLE_128B_ATOM_32B writes
+                    // exactly that).  A 32(m) x 32(k) TMA box is 8 K-atoms stacked (SBO = 512 B); the four boxes of a stage are the
+                    // M atoms (LBO = 4096 B).  One UMMA (K = 8) consumes two K atoms = 1024 B.
+                    const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+                                        ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 #pragma unroll
                     for (int k = 0; k < kBKc / 8; ++k)
                         umma_tf32(tmem_base, da + (uint64_t)(k * (1024 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
@@ -341,7 +343,7 @@ static EncodeTiledFn get_encode() {
 struct MapKey {
     const void* base;
     uint64_t d[4], s[3];
-    uint32_t box[4], rank;
+    uint32_t box[4], rank, swz, pad_;
     bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -354,13 +356,14 @@ struct MapKeyHash {
 };
 
 int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, bool swizzle_32b_atom) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key;
     std::memset(&key, 0, sizeof(key));
     key.base = base;
     key.rank = rank;
+    key.swz = swizzle_32b_atom ? 1u : 0u;
     for (uint32_t i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.box[i] = box[i]; }
     for (uint32_t i = 0; i + 1 < rank; ++i) key.s[i] = strides_bytes[i];
     {
@@ -376,7 +379,8 @@ int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t
     for (uint32_t i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (uint32_t i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %u dims %llu %llu %llu %llu", (int)r, rank,
@@ -441,7 +445,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
         uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.C1, (uint64_t)p.B};
         uint64_t strides[2] = {(uint64_t)p.a1_st * 4, (uint64_t)(p.a1_sb > 0 ? p.a1_sb : (int64_t)p.a1_st * p.C1) * 4};
         uint32_t box[3] = {32, 32, 1};
-        if ((rc = encode_map(&mA1, g.a1, 3, dims, strides, box)) != AERO_OK) return rc;
+        if ((rc = encode_map(&mA1, g.a1, 3, dims, strides, box, true)) != AERO_OK) return rc;
     } else if (p.C1) { if ((rc = make_a_map(&mA1, g.a1, p.C1, p, p.a1_sb, p.a1_sf, p.a1_st)) != AERO_OK) return rc; }
     if (p.C2) { if ((rc = make_a_map(&mA2, g.a2, p.C2, p, p.a2_sb, p.a2_sf, p.a2_st)) != AERO_OK) return rc; }
     if (!p.C1) mA1 = mA2;
