@@ -50,7 +50,9 @@ extern "C" int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w
     g.vec_a = (p.C1 % 4 == 0) && (p.C2 % 4 == 0) &&
               (p.C1 == 0 || (al16(a1) && p.a1_sb % 4 == 0 && p.a1_sf % 4 == 0 && p.a1_st % 4 == 0)) &&
               (p.C2 == 0 || (al16(a2) && p.a2_sb % 4 == 0 && p.a2_sf % 4 == 0 && p.a2_st % 4 == 0));
-    g.vec_o = al16(out) && p.o_sb % 4 == 0 && p.o_sf % 4 == 0 && p.o_st % 4 == 0 && Nout % 4 == 0;
+    g.vec_o = al16(out) && p.o_sb % 4 == 0 && p.o_sf % 4 == 0 && p.o_st % 4 == 0 && Nout % 4 == 0 &&
+              (!residual || (al16(residual) && p.r_sb % 4 == 0 && p.r_sf % 4 == 0 && p.r_st % 4 == 0)) &&
+              (!addend_fn || al16(addend_fn));
     AERO_REQUIRE(al16(w) && p.w_sb % 4 == 0, "aero_tapgemm_fwd: weights must be 16-byte aligned");
     if (p.precision == 1) {
         if (!tapgemm_tc_eligible(p)) {

@@ -35,6 +35,8 @@ struct TcShared {
     uint64_t acc_full;
     uint32_t tmem_base;
     float stats[4][8][2];      // [epilogue warp][group slot][sum, sumsq]: fixed-order reduction, run-to-run deterministic
+    float part[4][8][2];       // per-warp scratch for the fixed-order flush of the coalesced epilogue
+    float stage[4][32][36];    // per-warp transpose buffer: row-per-lane accumulators -> row-contiguous stores
 };
 
 // number of (tap, source, channel-chunk) iterations and their enumeration, shared by all roles
@@ -216,7 +218,99 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 }
             }
         }
-        for (int c0 = 0; c0 < (mix ? 0 : BN); c0 += 16) {
+        const bool fast = !mix && g.vec_o && !g.colscale && (p.stats_mode == 0 || gw % 4 == 0);
+        if (fast) {
+            // Coalesced epilogue.  Stage A: lane = row, 32 accumulator columns -> bias / activation / GLU -> per-warp smem tile.
+            // Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
+            // (residual loads and stores are full 128-byte segments), adds the row-wise terms and accumulates statistics.
+            float (*stg)[36] = sh->stage[q];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int ncol = min(32, BN - c0);                       // 32 or 16 (BN is a multiple of 16)
+                const int nb = n0 + c0;
+                if (nb >= p.N) break;
+                uint32_t r[32];
+                if (n_iters > 0) {
+                    if (ncol == 32) {
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                    } else {
+                        uint32_t r16[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r16);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0u; }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                const int cnt = p.glu ? ncol / 2 : ncol;                 // staged columns per row
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int n = nb + j + u;
+                        float x = __uint_as_float(r[j + u]);
+                        if (n < p.N) {
+                            if (g.bias) x += g.bias[n];
+                            if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                            else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                        }
+                        v[u] = x;
+                    }
+                    if (p.glu) {
+                        const float o0 = v[0] * sigmoid_f(v[1]), o1 = v[2] * sigmoid_f(v[3]);
+                        if (j < ncol) { stg[lane][j / 2] = o0; stg[lane][j / 2 + 1] = o1; }
+                    } else if (j < ncol) {
+                        *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+                __syncwarp();
+                const int lpr = cnt >> 2;                                // lanes per row (float4 each): 8, 4 or 2
+                const int cq = lane % lpr, ro = lane / lpr, rpi = 32 / lpr;
+                const int no0 = p.glu ? nb >> 1 : nb;
+                const int nn = no0 + 4 * cq;
+                const bool col_ok = nn < Nout;                           // Nout % 4 == 0 (vec_o)
+                float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (adp && col_ok) ad = *reinterpret_cast<const float4*>(adp + nn);
+                float ls = 0.f, lq = 0.f;
+                for (int r0 = 0; r0 < 32; r0 += rpi) {
+                    const int rr = r0 + ro;
+                    const int tr = t0 + q * 32 + rr;
+                    if (tr < p.T && col_ok) {
+                        float4 x = *reinterpret_cast<const float4*>(&stg[rr][4 * cq]);
+                        x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+                        const int64_t ro_off = (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)tr * p.o_st + nn;
+                        if (g.residual) {
+                            const float4 rs = *reinterpret_cast<const float4*>(g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)tr * p.r_st + nn);
+                            x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
+                        }
+                        x.x = x.x * sa + sb; x.y = x.y * sa + sb; x.z = x.z * sa + sb; x.w = x.w * sa + sb;
+                        if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
+                        ls += (x.x + x.y) + (x.z + x.w);
+                        lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+                        *reinterpret_cast<float4*>(g.out + ro_off) = x;
+                    }
+                }
+                if (p.stats_mode != 0) {
+                    // lanes with the same column quad (same group) first, then a fixed-order pass over the quads by lane 0
+                    for (int o = lpr; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+                    if (lane < lpr) { sh->part[q][lane][0] = ls; sh->part[q][lane][1] = lq; }
+                    __syncwarp();
+                    if (lane == 0) {
+                        for (int u = 0; u < lpr; ++u) {
+                            const int nq = no0 + 4 * u;
+                            if (nq < Nout) {
+                                const int gi = nq / gw - g_lo;
+                                sh->stats[q][gi][0] += sh->part[q][u][0];
+                                sh->stats[q][gi][1] += sh->part[q][u][1];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int c0 = 0; c0 < ((mix || fast) ? 0 : BN); c0 += 16) {
             uint32_t r[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -296,7 +390,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             }
         }
         if (p.stats_mode != 0) {
-            if (cur_g >= 0) {
+            if (cur_g >= 0 && !fast) {
                 const float a = warp_sum(ssum), c = warp_sum(ssq);
                 if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
             }
@@ -473,8 +567,9 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     int kStages = max_iters < 4 ? max_iters : 4;
     if (max_iters <= 12 && kStages * stage_bytes > 56 * 1024) kStages = (56 * 1024) / stage_bytes > 2 ? (56 * 1024) / stage_bytes : 2;
     if (kStages > max_iters) kStages = max_iters;
-    if (max_iters >= 48 && 5 * stage_bytes + 2048 <= 227 * 1024) kStages = 5;
-    if (max_iters >= 48 && 6 * stage_bytes + 2048 <= 227 * 1024) kStages = 6;
+    const int fixed = (int)sizeof(TcShared) + 1024;
+    if (max_iters >= 48 && 5 * stage_bytes + fixed <= 227 * 1024) kStages = 5;
+    if (max_iters >= 48 && 6 * stage_bytes + fixed <= 227 * 1024) kStages = 6;
     const size_t smem = (size_t)kStages * stage_bytes + sizeof(TcShared) + 1024;
     cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     dim3 grid((unsigned)tiles, cdiv(p.N, BN));
