@@ -36,7 +36,7 @@ struct TcShared {
     uint32_t tmem_base;
     float stats[4][8][2];      // [epilogue warp][group slot][sum, sumsq]: fixed-order reduction, run-to-run deterministic
     float part[4][8][2];       // per-warp scratch for the fixed-order flush of the coalesced epilogue
-    float stage[4][32][36];    // per-warp transpose buffer: row-per-lane accumulators -> row-contiguous stores
+    alignas(16) float stage[4][32][36];    // per-warp transpose buffer: row-per-lane accumulators -> row-contiguous stores
 };
 
 // number of (tap, source, channel-chunk) iterations and their enumeration, shared by all roles
