@@ -37,6 +37,10 @@ CLIP_SECONDS = 2.0
 SEED = 2036
 GFLOP_PER_CLIP = 124.16          # reference-equivalent; 102.9 with decoder-0's structural zeros skipped
 GFLOP_PER_CLIP_REQUIRED = 102.9
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the family (decoder.0 rewrite, B=32) from the
+# `ncu --set full` capture summarised in profiles/ (algorithmic bytes of that launch: 514 MB); None until captured
+TRAFFIC_NCU = {"kernel": "tapgemm_tc_kernel decoder.0.rw B=32", "bytes_per_launch": 966.3e6, "algorithmic_bytes": 514.0e6,
+               "source": "profiles/r1_dec0rw_tc_ncu.md"}
 
 
 def peaks():
@@ -168,7 +172,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", type=int, default=None, help="override engine precision (0 fp32 SIMT, 1 TF32 tcgen05)")
+    ap.add_argument("--precision", type=int, default=None,
+                    help="engine precision: 1 (default) TF32 tcgen05 tensor-core path, 0 every kernel in exact fp32")
     ap.add_argument("--_cpu_probe", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args._cpu_probe:
@@ -243,10 +248,8 @@ def main():
     ms_e2e = ev2.elapsed_time(ev3) / args.steps
     sampler.stop_flag = True
 
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    from aero_b200.parallel import reduce_max
+    ms_dev, ms_e2e = reduce_max(ms_dev, dev), reduce_max(ms_e2e, dev)
 
     if rank == 0:
         pk = peaks()
@@ -258,14 +261,16 @@ def main():
         ms_k = sum(v["ms"] for v in prof.values())
         n_l = sum(v["launches"] for v in prof.values())
         tf32 = eng.precision == 1
-        peak = pk["bf16_tflops"] / 2 if tf32 else pk["bf16_tflops"] / 2
+        peak = pk["bf16_tflops"] / 2
         ach = flops / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "tap-GEMM, decoder 3x3 rewrite convs (4 launches/step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": pk["source"] + "; TF32 dense peak taken as half the measured bf16 cuBLAS throughput",
                 "precision": "tf32 tcgen05" if tf32 else "fp32 SIMT (no tensor pipe)",
                 "ms_per_step_in_kernel": ms_k / args.steps, "share_of_step": (ms_k / args.steps) / ms_dev,
-                "launches_timed": n_l, "traffic": None}
+                "launches_timed": n_l,
+                "per_layer_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0) for k, v in sorted(prof.items())},
+                "traffic": TRAFFIC_NCU}
         line = {"metric": "audio-seconds/sec forward", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)" if tf32 else "f32", "data": "synthetic",
