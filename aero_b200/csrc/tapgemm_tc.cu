@@ -32,7 +32,8 @@ constexpr int kATileBytes = kBM * 128;   // 16 KB
 struct TcShared {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t acc_full;
+    uint64_t acc_full[2];      // MMA -> epilogue, one per TMEM accumulator buffer
+    uint64_t acc_empty[2];     // epilogue -> MMA
     uint32_t tmem_base;
     float stats[4][8][2];      // [epilogue warp][group slot][sum, sumsq]: fixed-order reduction, run-to-run deterministic
     float part[4][8][2];       // per-warp scratch for the fixed-order flush of the coalesced epilogue
@@ -58,10 +59,37 @@ __device__ __forceinline__ bool tap_geometry(const aero_tapgemm_params& p, int t
     return it.fi >= 0 && it.fi < p.F_in;
 }
 
+struct TileCoord {
+    int b, fo, t0, n0, n_iters;
+};
+// tile order: the n-tiles of one pixel tile are adjacent, so CTAs working at the same time share the A operand in L2
+__device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, int n_tiles, int BN, int nch1, int nch2) {
+    const aero_tapgemm_params& p = g.p;
+    TileCoord c;
+    const int nt = tile % n_tiles, mt = tile / n_tiles;
+    const int tt = mt % g.tiles_t, row = mt / g.tiles_t;
+    c.fo = row % p.F_out;
+    c.b = row / p.F_out;
+    c.t0 = tt * kBM;
+    c.n0 = nt * BN;
+    if (p.mode == AERO_TAPS_MIX) {
+        c.n_iters = nch1;
+    } else {
+        c.n_iters = 0;
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+            TapIter it;
+            if (tap_geometry(p, tap, c.fo, it)) c.n_iters += nch1 + nch2;
+        }
+    }
+    return c;
+}
+
+// Persistent: CTA c processes tiles c, c + gridDim.x, ...  The TMA producer runs ahead across tile boundaries; the
+// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 __global__ void __launch_bounds__(192)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                   const __grid_constant__ CUtensorMap mapW, const TapGemmArgs g, const int BN, const uint32_t idesc,
-                  const uint32_t tmem_cols, const int kStages) {
+                  const uint32_t tmem_cols, const int kStages, const int n_tiles, const int tiles_total) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = kATileBytes + BN * 128;
@@ -69,29 +97,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
 
     const aero_tapgemm_params& p = g.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int tt = tile % g.tiles_t;
-    const int row = tile / g.tiles_t;
-    const int fo = row % p.F_out;
-    const int b = row / p.F_out;
-    const int t0 = tt * kBM;
-    const int n0 = blockIdx.y * BN;
     const int nch1 = (p.C1 + kBKc - 1) / kBKc, nch2 = (p.C2 + kBKc - 1) / kBKc;
-
     const bool mix = p.mode == AERO_TAPS_MIX;
-    int n_iters = 0;
-    if (mix) {
-        n_iters = nch1;
-    } else {
-        for (int tap = 0; tap < g.ntaps; ++tap) {
-            TapIter it;
-            if (tap_geometry(p, tap, fo, it)) n_iters += nch1 + nch2;
-        }
-    }
+    const uint32_t acc_cols = tmem_cols >> 1;          // columns per accumulator buffer
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-        mbar_init(&sh->acc_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1); mbar_init(&sh->acc_empty[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int w = 0; w < 4; ++w)
             for (int i = 0; i < 8; ++i) { sh->stats[w][i][0] = 0.f; sh->stats[w][i][1] = 0.f; }
@@ -113,299 +125,316 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (uint32_t)stage_bytes;
-            if (mix) {
-                // A = activations [K rows][M contiguous]: four 32(m) x 32(k) boxes form one MN-major 128 x 32 operand tile
-                for (int kc = 0; kc < nch1; ++kc) {
-                    mbar_wait(&sh->empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * stage_bytes;
-                    mbar_expect_tx(&sh->full[stage], tx);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        tma_load_3d(sa + j * 4096, &mapA1, &sh->full[stage], t0 + 32 * j, kc * kBKc, b);
-                    tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kc * kBKc, n0, 0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-            }
-            for (int tap = 0; tap < (mix ? 0 : g.ntaps); ++tap) {
-                TapIter it;
-                if (!tap_geometry(p, tap, fo, it)) continue;
-                for (int src = 0; src < 2; ++src) {
-                    const int nch = src ? nch2 : nch1;
-                    const CUtensorMap* mA = src ? &mapA2 : &mapA1;
-                    const int kw0 = src ? p.C1 : 0;
-                    for (int kc = 0; kc < nch; ++kc) {
+            for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+                const TileCoord c = tile_coord(g, tile, n_tiles, BN, nch1, nch2);
+                if (mix) {
+                    // A = activations [K rows][M contiguous]: four 32(m) x 32(k) boxes form one MN-major 128 x 32 operand tile
+                    for (int kc = 0; kc < nch1; ++kc) {
                         mbar_wait(&sh->empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * stage_bytes;
                         mbar_expect_tx(&sh->full[stage], tx);
-                        tma_load_4d(sa, mA, &sh->full[stage], kc * kBKc, t0 + it.dt, it.fi, b);
-                        tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kw0 + kc * kBKc, n0, it.slab);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tma_load_3d(sa + j * 4096, &mapA1, &sh->full[stage], c.t0 + 32 * j, kc * kBKc, c.b);
+                        tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kc * kBKc, c.n0, 0);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
+                for (int tap = 0; tap < g.ntaps; ++tap) {
+                    TapIter it;
+                    if (!tap_geometry(p, tap, c.fo, it)) continue;
+                    for (int src = 0; src < 2; ++src) {
+                        const int nch = src ? nch2 : nch1;
+                        const CUtensorMap* mA = src ? &mapA2 : &mapA1;
+                        const int kw0 = src ? p.C1 : 0;
+                        for (int kc = 0; kc < nch; ++kc) {
+                            mbar_wait(&sh->empty[stage], phase ^ 1);
+                            uint8_t* sa = smem + stage * stage_bytes;
+                            mbar_expect_tx(&sh->full[stage], tx);
+                            tma_load_4d(sa, mA, &sh->full[stage], kc * kBKc, c.t0 + it.dt, it.fi, c.b);
+                            tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kw0 + kc * kBKc, c.n0, it.slab);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0 && n_iters > 0) {
+        if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < n_iters; ++i) {
-                mbar_wait(&sh->full[stage], phase);
+            int local = 0;
+            for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
+                const TileCoord c = tile_coord(g, tile, n_tiles, BN, nch1, nch2);
+                const int buf = local & 1;
+                mbar_wait(&sh->acc_empty[buf], (uint32_t)(((local >> 1) & 1) ^ 1));     // epilogue has drained this buffer
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                const uint64_t db = make_desc_sw128(sa + kATileBytes);
-                if (mix) {
-                    // MN-major tf32 A: the only legal layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom: 32 elements
-                    // along M x 4 rows along K = 512 B atoms, 32-byte chunks XOR-swizzled by row%4; TMA SWIZZLE_128B_ATOM_32B writes
-                    // exactly that).  A 32(m) x 32(k) TMA box is 8 K-atoms stacked (SBO = 512 B); the four boxes of a stage are the
-                    // M atoms (LBO = 4096 B).  One UMMA (K = 8) consumes two K atoms = 1024 B.
-                    const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-                                        ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+                const uint32_t tacc = tmem_base + (uint32_t)buf * acc_cols;
+                for (int i = 0; i < c.n_iters; ++i) {
+                    mbar_wait(&sh->full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint64_t db = make_desc_sw128(sa + kATileBytes);
+                    if (mix) {
+                        // MN-major tf32 A: the only legal layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom: 32 elements
+                        // along M x 4 rows along K = 512 B atoms, 32-byte chunks XOR-swizzled by row%4; TMA SWIZZLE_128B_ATOM_32B
+                        // writes exactly that).  A 32(m) x 32(k) TMA box is 8 K-atoms stacked (SBO = 512 B); the four boxes of a
+                        // stage are the M atoms (LBO = 4096 B).  One UMMA (K = 8) consumes two K atoms = 1024 B.
+                        const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+                                            ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 #pragma unroll
-                    for (int k = 0; k < kBKc / 8; ++k)
-                        umma_tf32(tmem_base, da + (uint64_t)(k * (1024 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                } else {
-                    const uint64_t da = make_desc_sw128(sa);
+                        for (int k = 0; k < kBKc / 8; ++k)
+                            umma_tf32(tacc, da + (uint64_t)(k * (1024 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    } else {
+                        const uint64_t da = make_desc_sw128(sa);
 #pragma unroll
-                    for (int k = 0; k < kBKc / 8; ++k)      // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
-                        umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBKc / 8; ++k)      // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
+                            umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&sh->empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&sh->empty[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                umma_commit(&sh->acc_full[buf]);
             }
-            umma_commit(&sh->acc_full);
         }
     } else {
         // ===================================================== epilogue (warps 2..5)
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const int t = t0 + m;
-        const bool row_ok = t < p.T;
-        if (n_iters > 0) {
-            mbar_wait(&sh->acc_full, 0);
-            tcgen05_fence_after();
-        }
         const int Nout = p.glu ? p.N / 2 : p.N;
         const int gw = (p.stats_mode == 1) ? Nout / p.groups : Nout;
-        float sa = 1.f, sb = 0.f;
-        if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
         const bool rnd = p.flags & 1;
-        float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
-        const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
-        const float* csp = g.colscale ? g.colscale + (int64_t)b * p.cs_sb + (int64_t)t * p.cs_st : nullptr;
-        const float* adp = g.addend_fn ? g.addend_fn + (int64_t)fo * Nout : nullptr;
-        int cur_g = -1;
-        float ssum = 0.f, ssq = 0.f;
-        const int g_lo = (p.glu ? n0 >> 1 : n0) / gw;
-
-        if (mix) {
-            // transposed store: lane = pixel m (contiguous in memory), column = output row n
-            const float gate = (row_ok && g.colscale) ? g.colscale[(int64_t)b * p.cs_sb + t] : 1.f;
-            float* ob = g.out + (int64_t)b * p.o_sb + t;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c0 + j;
-                        if (n < p.N) {
-                            float x = __uint_as_float(r[j]) * gate;
-                            if (rnd) x = round_tf32_rna(x);
-                            ob[(int64_t)n * p.o_st] = x;
-                        }
-                    }
-                }
-            }
-        }
         const bool fast = !mix && g.vec_o && !g.colscale && (p.stats_mode == 0 || gw % 4 == 0);
-        if (fast) {
-            // Coalesced epilogue.  Stage A: lane = row, 32 accumulator columns -> bias / activation / GLU -> per-warp smem tile.
-            // Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
-            // (residual loads and stores are full 128-byte segments), adds the row-wise terms and accumulates statistics.
-            float (*stg)[36] = sh->stage[q];
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int ncol = min(32, BN - c0);                       // 32 or 16 (BN is a multiple of 16)
-                const int nb = n0 + c0;
-                if (nb >= p.N) break;
-                uint32_t r[32];
-                if (n_iters > 0) {
-                    if (ncol == 32) {
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                    } else {
-                        uint32_t r16[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r16);
+        int local = 0;
+        for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
+            const TileCoord tc = tile_coord(g, tile, n_tiles, BN, nch1, nch2);
+            const int b = tc.b, fo = tc.fo, t0 = tc.t0, n0 = tc.n0, n_iters = tc.n_iters;
+            const int buf = local & 1;
+            const uint32_t tacc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16);
+            const int t = t0 + m;
+            const bool row_ok = t < p.T;
+            mbar_wait(&sh->acc_full[buf], (uint32_t)((local >> 1) & 1));
+            tcgen05_fence_after();
+            float sa = 1.f, sb = 0.f;
+            if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
+            float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+            const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+            const float* csp = g.colscale ? g.colscale + (int64_t)b * p.cs_sb + (int64_t)t * p.cs_st : nullptr;
+            const float* adp = g.addend_fn ? g.addend_fn + (int64_t)fo * Nout : nullptr;
+            int cur_g = -1;
+            float ssum = 0.f, ssq = 0.f;
+            const int g_lo = (p.glu ? n0 >> 1 : n0) / gw;
+
+            if (mix) {
+                // transposed store: lane = pixel m (contiguous in memory), column = output row n
+                const float gate = (row_ok && g.colscale) ? g.colscale[(int64_t)b * p.cs_sb + t] : 1.f;
+                float* ob = g.out + (int64_t)b * p.o_sb + t;
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tacc + (uint32_t)c0, r);
+                    if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0u; }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0u;
-                }
-                const int cnt = p.glu ? ncol / 2 : ncol;                 // staged columns per row
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int n = nb + j + u;
-                        float x = __uint_as_float(r[j + u]);
-                        if (n < p.N) {
-                            if (g.bias) x += g.bias[n];
-                            if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
-                            else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
-                        }
-                        v[u] = x;
-                    }
-                    if (p.glu) {
-                        const float o0 = v[0] * sigmoid_f(v[1]), o1 = v[2] * sigmoid_f(v[3]);
-                        if (j < ncol) { stg[lane][j / 2] = o0; stg[lane][j / 2 + 1] = o1; }
-                    } else if (j < ncol) {
-                        *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
-                    }
-                }
-                __syncwarp();
-                const int lpr = cnt >> 2;                                // lanes per row (float4 each): 8, 4 or 2
-                const int cq = lane % lpr, ro = lane / lpr, rpi = 32 / lpr;
-                const int no0 = p.glu ? nb >> 1 : nb;
-                const int nn = no0 + 4 * cq;
-                const bool col_ok = nn < Nout;                           // Nout % 4 == 0 (vec_o)
-                float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (adp && col_ok) ad = *reinterpret_cast<const float4*>(adp + nn);
-                float ls = 0.f, lq = 0.f;
-                for (int r0 = 0; r0 < 32; r0 += rpi) {
-                    const int rr = r0 + ro;
-                    const int tr = t0 + q * 32 + rr;
-                    if (tr < p.T && col_ok) {
-                        float4 x = *reinterpret_cast<const float4*>(&stg[rr][4 * cq]);
-                        x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
-                        const int64_t ro_off = (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)tr * p.o_st + nn;
-                        if (g.residual) {
-                            const float4 rs = *reinterpret_cast<const float4*>(g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)tr * p.r_st + nn);
-                            x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
-                        }
-                        x.x = x.x * sa + sb; x.y = x.y * sa + sb; x.z = x.z * sa + sb; x.w = x.w * sa + sb;
-                        if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
-                        ls += (x.x + x.y) + (x.z + x.w);
-                        lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-                        *reinterpret_cast<float4*>(g.out + ro_off) = x;
-                    }
-                }
-                if (p.stats_mode != 0) {
-                    // lanes with the same column quad (same group) first, then a fixed-order pass over the quads by lane 0
-                    for (int o = lpr; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
-                    if (lane < lpr) { sh->part[q][lane][0] = ls; sh->part[q][lane][1] = lq; }
-                    __syncwarp();
-                    if (lane == 0) {
-                        for (int u = 0; u < lpr; ++u) {
-                            const int nq = no0 + 4 * u;
-                            if (nq < Nout) {
-                                const int gi = nq / gw - g_lo;
-                                sh->stats[q][gi][0] += sh->part[q][u][0];
-                                sh->stats[q][gi][1] += sh->part[q][u][1];
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c0 + j;
+                            if (n < p.N) {
+                                float x = __uint_as_float(r[j]) * gate;
+                                if (rnd) x = round_tf32_rna(x);
+                                ob[(int64_t)n * p.o_st] = x;
                             }
                         }
                     }
                 }
-                __syncwarp();
-            }
-        }
-        for (int c0 = 0; c0 < ((mix || fast) ? 0 : BN); c0 += 16) {
-            uint32_t r[16];
-            if (n_iters > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            } else {
+            } else if (fast) {
+                // Coalesced epilogue.  Stage A: lane = row, 32 accumulator columns -> bias / activation / GLU -> per-warp smem
+                // tile.  Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
+                // (residual loads and stores are full 128-byte segments), adds the row-wise terms and accumulates statistics.
+                float (*stg)[36] = sh->stage[q];
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int ncol = min(32, BN - c0);                       // 32 or 16 (BN is a multiple of 16)
+                    const int nb = n0 + c0;
+                    if (nb >= p.N) break;
+                    uint32_t r[32];
+                    if (n_iters > 0) {
+                        if (ncol == 32) {
+                            tmem_ld32(tacc + (uint32_t)c0, r);
+                        } else {
+                            uint32_t r16[16];
+                            tmem_ld16(tacc + (uint32_t)c0, r16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = 0u;
-            }
-            const int nb = n0 + c0;
-            if (nb >= p.N) continue;                   // uniform: padded columns of the last tile
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = nb + j;
-                float x = __uint_as_float(r[j]);
-                if (row_ok && n < p.N) {
-                    if (g.bias) x += g.bias[n];
-                    if (csp) x *= csp[n];
-                    if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
-                    else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
-                }
-                v[j] = x;
-            }
-            float o[16];
-            int no0, cnt;
-            if (p.glu) {
-                no0 = nb >> 1;
-                cnt = 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
-            } else {
-                no0 = nb;
-                cnt = 16;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = v[j];
-            }
-            // statistics bookkeeping is warp-uniform: groups depend on columns only
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-                if (sub * 8 >= cnt) break;
-                const int ns = no0 + sub * 8;
-                if (p.stats_mode != 0 && ns < Nout) {
-                    const int gi = ns / gw;
-                    if (gi != cur_g) {
-                        if (cur_g >= 0) {
-                            const float a = warp_sum(ssum), c = warp_sum(ssq);
-                            if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
+                            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0u; }
                         }
-                        cur_g = gi; ssum = 0.f; ssq = 0.f;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    const int cnt = p.glu ? ncol / 2 : ncol;                 // staged columns per row
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int n = nb + j + u;
+                            float x = __uint_as_float(r[j + u]);
+                            if (n < p.N) {
+                                if (g.bias) x += g.bias[n];
+                                if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                                else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                            }
+                            v[u] = x;
+                        }
+                        if (p.glu) {
+                            const float o0 = v[0] * sigmoid_f(v[1]), o1 = v[2] * sigmoid_f(v[3]);
+                            if (j < ncol) { stg[lane][j / 2] = o0; stg[lane][j / 2 + 1] = o1; }
+                        } else if (j < ncol) {
+                            *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                    __syncwarp();
+                    const int lpr = cnt >> 2;                                // lanes per row (float4 each): 8, 4 or 2
+                    const int cq = lane % lpr, ro = lane / lpr, rpi = 32 / lpr;
+                    const int no0 = p.glu ? nb >> 1 : nb;
+                    const int nn = no0 + 4 * cq;
+                    const bool col_ok = nn < Nout;                           // Nout % 4 == 0 (vec_o)
+                    float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (adp && col_ok) ad = *reinterpret_cast<const float4*>(adp + nn);
+                    float ls = 0.f, lq = 0.f;
+                    for (int r0 = 0; r0 < 32; r0 += rpi) {
+                        const int rr = r0 + ro;
+                        const int tr = t0 + q * 32 + rr;
+                        if (tr < p.T && col_ok) {
+                            float4 x = *reinterpret_cast<const float4*>(&stg[rr][4 * cq]);
+                            x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+                            const int64_t ro_off = (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)tr * p.o_st + nn;
+                            if (g.residual) {
+                                const float4 rs = *reinterpret_cast<const float4*>(g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)tr * p.r_st + nn);
+                                x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
+                            }
+                            x.x = x.x * sa + sb; x.y = x.y * sa + sb; x.z = x.z * sa + sb; x.w = x.w * sa + sb;
+                            if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
+                            ls += (x.x + x.y) + (x.z + x.w);
+                            lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+                            *reinterpret_cast<float4*>(g.out + ro_off) = x;
+                        }
+                    }
+                    if (p.stats_mode != 0) {
+                        // lanes with the same column quad (same group) first, then a fixed-order pass over the quads by lane 0
+                        for (int o = lpr; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+                        if (lane < lpr) { sh->part[q][lane][0] = ls; sh->part[q][lane][1] = lq; }
+                        __syncwarp();
+                        if (lane == 0) {
+                            for (int u = 0; u < lpr; ++u) {
+                                const int nq = no0 + 4 * u;
+                                if (nq < Nout) {
+                                    const int gi = nq / gw - g_lo;
+                                    sh->stats[q][gi][0] += sh->part[q][u][0];
+                                    sh->stats[q][gi][1] += sh->part[q][u][1];
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // generic (unaligned outputs / colscale) epilogue: lane = row, scattered stores
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    if (n_iters > 0) {
+                        tmem_ld16(tacc + (uint32_t)c0, r);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = 0u;
+                    }
+                    const int nb = n0 + c0;
+                    if (nb >= p.N) continue;                   // uniform: padded columns of the last tile
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = nb + j;
+                        float x = __uint_as_float(r[j]);
+                        if (row_ok && n < p.N) {
+                            if (g.bias) x += g.bias[n];
+                            if (csp) x *= csp[n];
+                            if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                            else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                        }
+                        v[j] = x;
+                    }
+                    float o[16];
+                    int no0, cnt;
+                    if (p.glu) {
+                        no0 = nb >> 1;
+                        cnt = 8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
+                    } else {
+                        no0 = nb;
+                        cnt = 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = v[j];
+                    }
+                    // statistics bookkeeping is warp-uniform: groups depend on columns only
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        if (sub * 8 >= cnt) break;
+                        const int ns = no0 + sub * 8;
+                        if (p.stats_mode != 0 && ns < Nout) {
+                            const int gi = ns / gw;
+                            if (gi != cur_g) {
+                                if (cur_g >= 0) {
+                                    const float a = warp_sum(ssum), c = warp_sum(ssq);
+                                    if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
+                                }
+                                cur_g = gi; ssum = 0.f; ssq = 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int jj = sub * 8 + j;
+                            const int nn = no0 + jj;
+                            if (row_ok && nn < Nout) {
+                                float x = o[jj];
+                                if (adp) x += adp[nn];
+                                if (rp) x += rp[nn];
+                                x = x * sa + sb;
+                                if (rnd) x = round_tf32_rna(x);
+                                o[jj] = x;
+                                ssum += x;
+                                ssq += x * x;
+                            }
+                        }
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < cnt && no0 + j < Nout) op[no0 + j] = o[j];
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int jj = sub * 8 + j;
-                    const int nn = no0 + jj;
-                    if (row_ok && nn < Nout) {
-                        float x = o[jj];
-                        if (adp) x += adp[nn];
-                        if (rp) x += rp[nn];
-                        x = x * sa + sb;
-                        if (rnd) x = round_tf32_rna(x);
-                        o[jj] = x;
-                        ssum += x;
-                        ssq += x * x;
+                if (p.stats_mode != 0 && cur_g >= 0) {
+                    const float a = warp_sum(ssum), c = warp_sum(ssq);
+                    if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
+                }
+            }
+            // accumulator buffer drained: hand it back to the MMA warp before the (cheap) statistics flush
+            tcgen05_fence_before();
+            mbar_arrive(&sh->acc_empty[buf]);
+            if (p.stats_mode != 0) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int e = threadIdx.x - 64;
+                if (e < 8) {
+                    const float a = (sh->stats[0][e][0] + sh->stats[1][e][0]) + (sh->stats[2][e][0] + sh->stats[3][e][0]);
+                    const float c = (sh->stats[0][e][1] + sh->stats[1][e][1]) + (sh->stats[2][e][1] + sh->stats[3][e][1]);
+                    const int gi = g_lo + e;
+                    const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
+                    if (gi < ngroups && (a != 0.f || c != 0.f)) {
+                        const int64_t slot = (p.stats_mode == 1) ? ((int64_t)b * p.groups + gi) : ((int64_t)b * p.F_out + fo);
+                        atomicAdd(&g.stats[2 * slot], (double)a);
+                        atomicAdd(&g.stats[2 * slot + 1], (double)c);
                     }
+                    for (int w = 0; w < 4; ++w) { sh->stats[w][e][0] = 0.f; sh->stats[w][e][1] = 0.f; }
                 }
-            }
-            if (row_ok) {
-                if (g.vec_o && no0 + cnt <= Nout) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        if (j < cnt) *reinterpret_cast<float4*>(op + no0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < cnt && no0 + j < Nout) op[no0 + j] = o[j];
-                }
-            }
-        }
-        if (p.stats_mode != 0) {
-            if (cur_g >= 0 && !fast) {
-                const float a = warp_sum(ssum), c = warp_sum(ssq);
-                if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int e = threadIdx.x - 64;
-            if (e < 8) {
-                const float a = (sh->stats[0][e][0] + sh->stats[1][e][0]) + (sh->stats[2][e][0] + sh->stats[3][e][0]);
-                const float c = (sh->stats[0][e][1] + sh->stats[1][e][1]) + (sh->stats[2][e][1] + sh->stats[3][e][1]);
-                const int gi = g_lo + e;
-                const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
-                if (gi < ngroups && (a != 0.f || c != 0.f)) {
-                    const int64_t slot = (p.stats_mode == 1) ? ((int64_t)b * p.groups + gi) : ((int64_t)b * p.F_out + fo);
-                    atomicAdd(&g.stats[2 * slot], (double)a);
-                    atomicAdd(&g.stats[2 * slot + 1], (double)c);
-                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
     }
@@ -554,8 +583,9 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     g.tiles_t = cdiv(p.T, kBM);
     const int64_t tiles = (int64_t)p.B * p.F_out * g.tiles_t;
     if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
-    uint32_t tmem_cols = 32;
+    uint32_t tmem_cols = 32;                       // two accumulator buffers (double-buffered epilogue)
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    tmem_cols <<= 1;
     // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24) |
                            (mix ? (1u << 15) : 0u);                 // bit 15: A is MN-major
@@ -564,16 +594,36 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     const int nch = (p.C1 + kBKc - 1) / kBKc + (p.C2 + kBKc - 1) / kBKc;
     const int max_iters = nch * ((p.mode == AERO_TAPS_CONVT) ? p.kf / p.stride_f : p.kf * p.kt);
     const int stage_bytes = kATileBytes + BN * 128;
-    int kStages = max_iters < 4 ? max_iters : 4;
-    if (max_iters <= 12 && kStages * stage_bytes > 56 * 1024) kStages = (56 * 1024) / stage_bytes > 2 ? (56 * 1024) / stage_bytes : 2;
-    if (kStages > max_iters) kStages = max_iters;
+    // pipeline depth: the producer runs ahead across tiles, so depth is set by bytes in flight, not by the K length.
+    // Long K loops get as many stages as fit; short, HBM-bound layers keep ~64 KB in flight and leave room for 2-3 CTAs/SM.
     const int fixed = (int)sizeof(TcShared) + 1024;
-    if (max_iters >= 48 && 5 * stage_bytes + fixed <= 227 * 1024) kStages = 5;
-    if (max_iters >= 48 && 6 * stage_bytes + fixed <= 227 * 1024) kStages = 6;
+    int kStages;
+    if (max_iters >= 24) {
+        kStages = (227 * 1024 - fixed) / stage_bytes;
+    } else {
+        kStages = (72 * 1024) / stage_bytes;
+    }
+    if (kStages > kMaxStages) kStages = kMaxStages;
+    if (kStages < 2) kStages = 2;
     const size_t smem = (size_t)kStages * stage_bytes + sizeof(TcShared) + 1024;
     cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    dim3 grid((unsigned)tiles, cdiv(p.N, BN));
-    tapgemm_tc_kernel<<<grid, 192, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols, kStages);
+    // persistent grid: as many CTAs as can be co-resident (shared memory and TMEM columns), never more than tiles
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_tiles = cdiv(p.N, BN);
+    const int64_t tiles_total = tiles * n_tiles;
+    if (tiles_total > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > (int)(512 / tmem_cols)) per_sm = (int)(512 / tmem_cols);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (int64_t)num_sms * per_sm;
+    dim3 grid((unsigned)(tiles_total < want ? tiles_total : want));
+    tapgemm_tc_kernel<<<grid, 192, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols, kStages, n_tiles, (int)tiles_total);
     return check_launch("aero_tapgemm_fwd(tcgen05)");
 }
 
