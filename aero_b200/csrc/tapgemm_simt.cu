@@ -216,9 +216,131 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Thin shapes are HBM-bound, not FLOP-bound; the tiled kernel above wastes most of its tile on them.
+//
+// thin-N (N <= 8: FTB's C->5 squeeze, the final 96->2 transposed conv): one thread per output pixel computes all N
+// columns over all taps; the weights live in shared memory ([tap][c][8]) and are read as broadcasts.
+constexpr int kThinN = 8;
+
+__global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g) {
+    extern __shared__ __align__(16) float wsm[];          // [nslab][K][8]
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1 + p.C2;
+    const int nslab = (p.mode == AERO_TAPS_CONVT) ? p.kf : p.kf * p.kt;
+    for (int i = threadIdx.x; i < nslab * K * kThinN; i += blockDim.x) {
+        const int n = i % kThinN, rk = i / kThinN;
+        wsm[i] = n < p.N ? g.w[(int64_t)rk * g.ldw + n] : 0.f;
+    }
+    __syncthreads();
+    const int64_t npix = (int64_t)p.B * p.F_out * p.T;
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(pix % p.T);
+        const int64_t rowi = pix / p.T;
+        const int fo = (int)(rowi % p.F_out), b = (int)(rowi / p.F_out);
+        float acc[kThinN];
+#pragma unroll
+        for (int n = 0; n < kThinN; ++n) acc[n] = 0.f;
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+            int fi, dt, slab;
+            if (p.mode == AERO_TAPS_CONV) {
+                const int jf = tap / p.kt, jt = tap - jf * p.kt;
+                fi = fo * p.stride_f + jf - p.pad_f; dt = jt * p.dil_t - p.pad_t; slab = tap;
+            } else {
+                const int fof = fo + p.f_out_offset;
+                fi = fof / p.stride_f - tap; dt = 0; slab = fof % p.stride_f + tap * p.stride_f;
+            }
+            const int ti = t + dt;
+            if (fi < 0 || fi >= p.F_in || ti < 0 || ti >= p.T_in) continue;
+            const float* wt = wsm + (int64_t)slab * K * kThinN;
+            for (int src = 0; src < 2; ++src) {
+                const int Cs = src ? p.C2 : p.C1;
+                if (Cs == 0) continue;
+                const float* a = src ? g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (int64_t)ti * p.a2_st
+                                     : g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)ti * p.a1_st;
+                const float* wc = wt + (src ? p.C1 : 0) * kThinN;
+                for (int c = 0; c < Cs; c += 4) {
+                    const float4 av = *reinterpret_cast<const float4*>(a + c);       // vec_a holds (host check)
+                    const float avs[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wc + (c + u) * kThinN);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wc + (c + u) * kThinN + 4);
+                        acc[0] = fmaf(avs[u], w0.x, acc[0]); acc[1] = fmaf(avs[u], w0.y, acc[1]);
+                        acc[2] = fmaf(avs[u], w0.z, acc[2]); acc[3] = fmaf(avs[u], w0.w, acc[3]);
+                        acc[4] = fmaf(avs[u], w1.x, acc[4]); acc[5] = fmaf(avs[u], w1.y, acc[5]);
+                        acc[6] = fmaf(avs[u], w1.z, acc[6]); acc[7] = fmaf(avs[u], w1.w, acc[7]);
+                    }
+                }
+            }
+        }
+        float sa = 1.f, sb = 0.f;
+        if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
+        float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+        const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+#pragma unroll
+        for (int n = 0; n < kThinN; ++n) {
+            if (n < p.N) {
+                float x = acc[n] + (g.bias ? g.bias[n] : 0.f);
+                if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                if (rp) x += rp[n];
+                x = x * sa + sb;
+                if (p.flags & 1) x = round_tf32_rna(x);
+                op[n] = x;
+            }
+        }
+    }
+}
+
+// thin-K (K <= 4, single tap: pre_conv 2->48): one thread per (pixel, 4 output columns), 16-byte stores.
+__global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g) {
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1;
+    const int n4 = p.N >> 2;
+    const int64_t total = (int64_t)p.B * p.F_out * p.T * n4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % n4) * 4;
+        const int64_t pix = i / n4;
+        const int t = (int)(pix % p.T);
+        const int64_t rowi = pix / p.T;
+        const int fo = (int)(rowi % p.F_out), b = (int)(rowi / p.F_out);
+        const float* a = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fo * p.a1_sf + (int64_t)t * p.a1_st;
+        float4 acc = g.bias ? *reinterpret_cast<const float4*>(g.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < K; ++k) {
+            const float av = a[k];
+            const float4 w = *reinterpret_cast<const float4*>(g.w + (int64_t)k * g.ldw + n);
+            acc.x = fmaf(av, w.x, acc.x); acc.y = fmaf(av, w.y, acc.y); acc.z = fmaf(av, w.z, acc.z); acc.w = fmaf(av, w.w, acc.w);
+        }
+        if (p.act == AERO_ACT_GELU) { acc.x = gelu_exact(acc.x); acc.y = gelu_exact(acc.y); acc.z = gelu_exact(acc.z); acc.w = gelu_exact(acc.w); }
+        else if (p.act == AERO_ACT_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        if (p.flags & 1) { acc.x = round_tf32_rna(acc.x); acc.y = round_tf32_rna(acc.y); acc.z = round_tf32_rna(acc.z); acc.w = round_tf32_rna(acc.w); }
+        *reinterpret_cast<float4*>(g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n) = acc;
+    }
+}
+
 int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
     const aero_tapgemm_params& p = g.p;
     TapGemmArgs a = g;
+    const bool plain = !p.glu && p.stats_mode == 0 && !g.addend_fn && !g.colscale && p.w_sb == 0;
+    const int nslab = (p.mode == AERO_TAPS_CONVT) ? p.kf : p.kf * p.kt;
+    if (plain && p.N <= kThinN && g.vec_a && (size_t)nslab * (p.C1 + p.C2) * kThinN * 4 <= 96 * 1024) {
+        const size_t smem = (size_t)nslab * (p.C1 + p.C2) * kThinN * 4;
+        cudaFuncSetAttribute(tapgemm_thin_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int64_t npix = (int64_t)p.B * p.F_out * p.T;
+        int blocks = (int)((npix + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        tapgemm_thin_n_kernel<<<blocks, 256, smem, st>>>(a);
+        return check_launch("aero_tapgemm_fwd(thin-n)");
+    }
+    if (plain && p.mode == AERO_TAPS_CONV && p.kf == 1 && p.kt == 1 && p.stride_f == 1 && p.pad_f == 0 && p.C2 == 0 && p.C1 <= 4 &&
+        p.N % 4 == 0 && g.vec_o && !g.residual && !g.samp_affine && p.F_in == p.F_out) {
+        const int64_t total = (int64_t)p.B * p.F_out * p.T * (p.N / 4);
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        tapgemm_thin_k_kernel<<<blocks, 256, 0, st>>>(a);
+        return check_launch("aero_tapgemm_fwd(thin-k)");
+    }
     const bool thin = p.N <= 16;
     const int BM = 128;
     a.tiles_t = cdiv(p.T, BM);

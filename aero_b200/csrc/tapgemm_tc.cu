@@ -84,6 +84,41 @@ __device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, 
     return c;
 }
 
+// Stage A of the coalesced epilogue, specialised on activation / GLU so the inner loop is branch-free: this thread's 32
+// accumulator columns -> bias -> activation -> (GLU) -> row `lane` of the per-warp staging tile.
+template <int ACT, bool GLU>
+__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[32], float (*stg)[36], int lane, const float* __restrict__ bias,
+                                                 int nb, int N, int ncol) {
+    const bool full = (nb + 32 <= N) && ncol == 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+        if (full) {
+            if (bias) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias + nb + j);
+                v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (bias && nb + j + u < N) v[u] += bias[nb + j + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ACT == AERO_ACT_GELU) v[u] = gelu_exact(v[u]);
+            else if (ACT == AERO_ACT_RELU) v[u] = fmaxf(v[u], 0.f);
+        }
+        if (GLU) {
+            if (j < ncol) {
+                stg[lane][j / 2] = v[0] * sigmoid_f(v[1]);
+                stg[lane][j / 2 + 1] = v[2] * sigmoid_f(v[3]);
+            }
+        } else if (j < ncol) {
+            *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 // Persistent: CTA c processes tiles c, c + gridDim.x, ...  The TMA producer runs ahead across tile boundaries; the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 __global__ void __launch_bounds__(192)
@@ -270,26 +305,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         for (int j = 0; j < 32; ++j) r[j] = 0u;
                     }
                     const int cnt = p.glu ? ncol / 2 : ncol;                 // staged columns per row
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float v[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int n = nb + j + u;
-                            float x = __uint_as_float(r[j + u]);
-                            if (n < p.N) {
-                                if (g.bias) x += g.bias[n];
-                                if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
-                                else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
-                            }
-                            v[u] = x;
-                        }
-                        if (p.glu) {
-                            const float o0 = v[0] * sigmoid_f(v[1]), o1 = v[2] * sigmoid_f(v[3]);
-                            if (j < ncol) { stg[lane][j / 2] = o0; stg[lane][j / 2 + 1] = o1; }
-                        } else if (j < ncol) {
-                            *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
-                        }
+                    if (p.glu) {
+                        if (p.act == AERO_ACT_NONE) epilogue_stage_a<AERO_ACT_NONE, true>(r, stg, lane, g.bias, nb, p.N, ncol);
+                        else if (p.act == AERO_ACT_GELU) epilogue_stage_a<AERO_ACT_GELU, true>(r, stg, lane, g.bias, nb, p.N, ncol);
+                        else epilogue_stage_a<AERO_ACT_RELU, true>(r, stg, lane, g.bias, nb, p.N, ncol);
+                    } else {
+                        if (p.act == AERO_ACT_NONE) epilogue_stage_a<AERO_ACT_NONE, false>(r, stg, lane, g.bias, nb, p.N, ncol);
+                        else if (p.act == AERO_ACT_GELU) epilogue_stage_a<AERO_ACT_GELU, false>(r, stg, lane, g.bias, nb, p.N, ncol);
+                        else epilogue_stage_a<AERO_ACT_RELU, false>(r, stg, lane, g.bias, nb, p.N, ncol);
                     }
                     __syncwarp();
                     const int lpr = cnt >> 2;                                // lanes per row (float4 each): 8, 4 or 2
@@ -319,17 +342,24 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         }
                     }
                     if (p.stats_mode != 0) {
-                        // lanes with the same column quad (same group) first, then a fixed-order pass over the quads by lane 0
-                        for (int o = lpr; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
-                        if (lane < lpr) { sh->part[q][lane][0] = ls; sh->part[q][lane][1] = lq; }
-                        __syncwarp();
-                        if (lane == 0) {
-                            for (int u = 0; u < lpr; ++u) {
-                                const int nq = no0 + 4 * u;
-                                if (nq < Nout) {
-                                    const int gi = nq / gw - g_lo;
-                                    sh->stats[q][gi][0] += sh->part[q][u][0];
-                                    sh->stats[q][gi][1] += sh->part[q][u][1];
+                        const int g_first = no0 / gw, g_last = (min(no0 + cnt, Nout) - 1) / gw;
+                        if (g_first == g_last) {
+                            // the whole chunk is one group: plain warp reduction (fixed xor order -> deterministic)
+                            const float a = warp_sum(ls), c = warp_sum(lq);
+                            if (lane == 0) { sh->stats[q][g_first - g_lo][0] += a; sh->stats[q][g_first - g_lo][1] += c; }
+                        } else {
+                            // lanes with the same column quad first, then a fixed-order pass over the quads by lane 0
+                            for (int o = lpr; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+                            if (lane < lpr) { sh->part[q][lane][0] = ls; sh->part[q][lane][1] = lq; }
+                            __syncwarp();
+                            if (lane == 0) {
+                                for (int u = 0; u < lpr; ++u) {
+                                    const int nq = no0 + 4 * u;
+                                    if (nq < Nout) {
+                                        const int gi = nq / gw - g_lo;
+                                        sh->stats[q][gi][0] += sh->part[q][u][0];
+                                        sh->stats[q][gi][1] += sh->part[q][u][1];
+                                    }
                                 }
                             }
                         }
