@@ -27,6 +27,8 @@ namespace aero {
 constexpr int kBM = 128;
 constexpr int kBKc = 32;                 // fp32 elements per 128-byte swizzle row
 constexpr int kMaxStages = 6;
+constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, alternating 16-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kATileBytes = kBM * 128;   // 16 KB
 
 struct TcShared {
@@ -35,9 +37,9 @@ struct TcShared {
     uint64_t acc_full[2];      // MMA -> epilogue, one per TMEM accumulator buffer
     uint64_t acc_empty[2];     // epilogue -> MMA
     uint32_t tmem_base;
-    float stats[4][8][2];      // [epilogue warp][group slot][sum, sumsq]: fixed-order reduction, run-to-run deterministic
-    float part[4][8][2];       // per-warp scratch for the fixed-order flush of the coalesced epilogue
-    alignas(16) float stage[4][32][36];    // per-warp transpose buffer: row-per-lane accumulators -> row-contiguous stores
+    float stats[kEpiWarps][8][2];   // [epilogue warp][group slot][sum, sumsq]: fixed-order reduction, run-to-run deterministic
+    float part[kEpiWarps][4][2];    // per-warp scratch for the fixed-order flush of the coalesced epilogue
+    alignas(16) float stage[kEpiWarps][32][20];   // per-warp transpose buffer (16 columns): lane-per-row -> row-contiguous stores
 };
 
 // number of (tap, source, channel-chunk) iterations and their enumeration, shared by all roles
@@ -84,44 +86,129 @@ __device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, 
     return c;
 }
 
-// Stage A of the coalesced epilogue, specialised on activation / GLU so the inner loop is branch-free: this thread's 32
-// accumulator columns -> bias -> activation -> (GLU) -> row `lane` of the per-warp staging tile.
-template <int ACT, bool GLU>
-__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[32], float (*stg)[36], int lane, const float* __restrict__ bias,
-                                                 int nb, int N, int ncol) {
-    const bool full = (nb + 32 <= N) && ncol == 32;
+// Coalesced epilogue, specialised at compile time (AMODE: 0 none, 1 GELU, 2 ReLU, 3 GLU; RES: residual add; STATS).
+// Stage A: this thread's 16 accumulator columns of its row -> bias -> activation / GLU -> row `lane` of the per-warp
+// staging tile.  Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
+// (residual loads and stores are whole 32-byte sectors of one row), adds the row-wise terms, rounds, accumulates statistics.
+template <int AMODE>
+__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], float (*stg)[20], int lane, const float* __restrict__ bias,
+                                                 int nb, int N) {
+    const bool full = nb + 16 <= N;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < 16; j += 4) {
         float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-        if (full) {
-            if (bias) {
+        if (bias) {
+            if (full) {
                 const float4 bv = *reinterpret_cast<const float4*>(bias + nb + j);
                 v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (bias && nb + j + u < N) v[u] += bias[nb + j + u];
+                for (int u = 0; u < 4; ++u)
+                    if (nb + j + u < N) v[u] += bias[nb + j + u];
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (ACT == AERO_ACT_GELU) v[u] = gelu_exact(v[u]);
-            else if (ACT == AERO_ACT_RELU) v[u] = fmaxf(v[u], 0.f);
+            if (AMODE == 1) v[u] = gelu_exact(v[u]);
+            else if (AMODE == 2) v[u] = fmaxf(v[u], 0.f);
         }
-        if (GLU) {
-            if (j < ncol) {
-                stg[lane][j / 2] = v[0] * sigmoid_f(v[1]);
-                stg[lane][j / 2 + 1] = v[2] * sigmoid_f(v[3]);
-            }
-        } else if (j < ncol) {
+        if (AMODE == 3) {
+            stg[lane][j / 2] = v[0] * sigmoid_f(v[1]);
+            stg[lane][j / 2 + 1] = v[2] * sigmoid_f(v[3]);
+        } else {
             *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
 
+template <int AMODE, bool RES, bool STATS>
+__device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmArgs& g, const TileCoord& tc, uint32_t tacc, int BN, int q,
+                                                   int ew, int lane, int Nout, int gw) {
+    const aero_tapgemm_params& p = g.p;
+    constexpr int CNT = (AMODE == 3) ? 8 : 16;          // staged output columns per 16 accumulator columns
+    constexpr int LPR = CNT / 4;                         // lanes per row (one float4 each)
+    constexpr int RPI = 32 / LPR;                        // rows per pass
+    float (*stg)[20] = sh->stage[ew];
+    const bool rnd = p.flags & 1;
+    float sa = 1.f, sb = 0.f;
+    if (g.samp_affine) { sa = g.samp_affine[2 * tc.b]; sb = g.samp_affine[2 * tc.b + 1]; }
+    const int cq = lane % LPR, ro = lane / LPR;
+    const int row0 = tc.t0 + q * 32;                     // first output row (t) of this warp's lane quarter
+    const int rows = min(32, p.T - row0);                // valid rows (<= 0: nothing to store)
+    const int g_lo = ((AMODE == 3) ? tc.n0 >> 1 : tc.n0) / gw;
+    float* const obase = g.out + (int64_t)tc.b * p.o_sb + (int64_t)tc.fo * p.o_sf + (int64_t)row0 * p.o_st;
+    const float* const rbase = RES ? g.residual + (int64_t)tc.b * p.r_sb + (int64_t)tc.fo * p.r_sf + (int64_t)row0 * p.r_st : nullptr;
+    const float* const adp = g.addend_fn ? g.addend_fn + (int64_t)tc.fo * Nout : nullptr;
+    for (int c0 = (ew >> 2) * 16; c0 < BN; c0 += 32) {   // the two warps of a lane quarter alternate 16-column chunks
+        const int nb = tc.n0 + c0;
+        if (nb >= p.N) break;
+        uint32_t r[16];
+        if (tc.n_iters > 0) {
+            tmem_ld16(tacc + (uint32_t)c0, r);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        epilogue_stage_a<AMODE>(r, stg, lane, g.bias, nb, p.N);
+        __syncwarp();
+        const int no0 = (AMODE == 3) ? nb >> 1 : nb;
+        const int nn = no0 + 4 * cq;
+        float ls = 0.f, lq = 0.f;
+        if (nn < Nout) {                                 // Nout % 4 == 0 (vec_o)
+            float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (adp) ad = *reinterpret_cast<const float4*>(adp + nn);
+            float* op = obase + (int64_t)ro * p.o_st + nn;
+            const float* rp = RES ? rbase + (int64_t)ro * p.r_st + nn : nullptr;
+            const int64_t ostep = (int64_t)RPI * p.o_st, rstep = (int64_t)RPI * p.r_st;
+#pragma unroll 2
+            for (int rr = ro; rr < rows; rr += RPI) {
+                float4 x = *reinterpret_cast<const float4*>(&stg[rr][4 * cq]);
+                x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+                if (RES) {
+                    const float4 rs = *reinterpret_cast<const float4*>(rp);
+                    x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
+                    rp += rstep;
+                }
+                x.x = fmaf(x.x, sa, sb); x.y = fmaf(x.y, sa, sb); x.z = fmaf(x.z, sa, sb); x.w = fmaf(x.w, sa, sb);
+                if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
+                if (STATS) {
+                    ls += (x.x + x.y) + (x.z + x.w);
+                    lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+                }
+                *reinterpret_cast<float4*>(op) = x;
+                op += ostep;
+            }
+        }
+        if (STATS) {
+            const int g_first = no0 / gw, g_last = (min(no0 + CNT, Nout) - 1) / gw;
+            if (g_first == g_last) {
+                // the whole chunk is one group: plain warp reduction (fixed xor order -> deterministic)
+                const float a = warp_sum(ls), c = warp_sum(lq);
+                if (lane == 0) { sh->stats[ew][g_first - g_lo][0] += a; sh->stats[ew][g_first - g_lo][1] += c; }
+            } else {
+                // lanes with the same column quad first, then a fixed-order pass over the quads by lane 0
+                for (int o = LPR; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+                if (lane < LPR) { sh->part[ew][lane][0] = ls; sh->part[ew][lane][1] = lq; }
+                __syncwarp();
+                if (lane == 0) {
+                    for (int u = 0; u < LPR; ++u) {
+                        const int nq = no0 + 4 * u;
+                        if (nq < Nout) {
+                            sh->stats[ew][nq / gw - g_lo][0] += sh->part[ew][u][0];
+                            sh->stats[ew][nq / gw - g_lo][1] += sh->part[ew][u][1];
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Persistent: CTA c processes tiles c, c + gridDim.x, ...  The TMA producer runs ahead across tile boundaries; the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
-__global__ void __launch_bounds__(192)
+template <int AMODE, bool RES, bool STATS>
+__global__ void __launch_bounds__(kThreads)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                   const __grid_constant__ CUtensorMap mapW, const TapGemmArgs g, const int BN, const uint32_t idesc,
                   const uint32_t tmem_cols, const int kStages, const int n_tiles, const int tiles_total) {
@@ -138,9 +225,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1); mbar_init(&sh->acc_empty[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1); mbar_init(&sh->acc_empty[s], 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int w = 0; w < 4; ++w)
+        for (int w = 0; w < kEpiWarps; ++w)
             for (int i = 0; i < 8; ++i) { sh->stats[w][i][0] = 0.f; sh->stats[w][i][1] = 0.f; }
     }
     if (warp == 1) {
@@ -235,8 +322,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             }
         }
     } else {
-        // ===================================================== epilogue (warps 2..5)
+        // ===================================================== epilogue (warps 2..9)
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int ew = warp - 2;                       // epilogue warp index; ew >> 2 selects odd / even column chunks
         const int m = q * 32 + lane;
         const int Nout = p.glu ? p.N / 2 : p.N;
         const int gw = (p.stats_mode == 1) ? Nout / p.groups : Nout;
@@ -266,7 +354,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 // transposed store: lane = pixel m (contiguous in memory), column = output row n
                 const float gate = (row_ok && g.colscale) ? g.colscale[(int64_t)b * p.cs_sb + t] : 1.f;
                 float* ob = g.out + (int64_t)b * p.o_sb + t;
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                for (int c0 = (ew >> 2) * 16; c0 < BN; c0 += 32) {
                     uint32_t r[16];
                     tmem_ld16(tacc + (uint32_t)c0, r);
                     if (row_ok) {
@@ -282,93 +370,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     }
                 }
             } else if (fast) {
-                // Coalesced epilogue.  Stage A: lane = row, 32 accumulator columns -> bias / activation / GLU -> per-warp smem
-                // tile.  Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
-                // (residual loads and stores are full 128-byte segments), adds the row-wise terms and accumulates statistics.
-                float (*stg)[36] = sh->stage[q];
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    const int ncol = min(32, BN - c0);                       // 32 or 16 (BN is a multiple of 16)
-                    const int nb = n0 + c0;
-                    if (nb >= p.N) break;
-                    uint32_t r[32];
-                    if (n_iters > 0) {
-                        if (ncol == 32) {
-                            tmem_ld32(tacc + (uint32_t)c0, r);
-                        } else {
-                            uint32_t r16[16];
-                            tmem_ld16(tacc + (uint32_t)c0, r16);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0u; }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = 0u;
-                    }
-                    const int cnt = p.glu ? ncol / 2 : ncol;                 // staged columns per row
-                    if (p.glu) {
-                        if (p.act == AERO_ACT_NONE) epilogue_stage_a<AERO_ACT_NONE, true>(r, stg, lane, g.bias, nb, p.N, ncol);
-                        else if (p.act == AERO_ACT_GELU) epilogue_stage_a<AERO_ACT_GELU, true>(r, stg, lane, g.bias, nb, p.N, ncol);
-                        else epilogue_stage_a<AERO_ACT_RELU, true>(r, stg, lane, g.bias, nb, p.N, ncol);
-                    } else {
-                        if (p.act == AERO_ACT_NONE) epilogue_stage_a<AERO_ACT_NONE, false>(r, stg, lane, g.bias, nb, p.N, ncol);
-                        else if (p.act == AERO_ACT_GELU) epilogue_stage_a<AERO_ACT_GELU, false>(r, stg, lane, g.bias, nb, p.N, ncol);
-                        else epilogue_stage_a<AERO_ACT_RELU, false>(r, stg, lane, g.bias, nb, p.N, ncol);
-                    }
-                    __syncwarp();
-                    const int lpr = cnt >> 2;                                // lanes per row (float4 each): 8, 4 or 2
-                    const int cq = lane % lpr, ro = lane / lpr, rpi = 32 / lpr;
-                    const int no0 = p.glu ? nb >> 1 : nb;
-                    const int nn = no0 + 4 * cq;
-                    const bool col_ok = nn < Nout;                           // Nout % 4 == 0 (vec_o)
-                    float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (adp && col_ok) ad = *reinterpret_cast<const float4*>(adp + nn);
-                    float ls = 0.f, lq = 0.f;
-                    for (int r0 = 0; r0 < 32; r0 += rpi) {
-                        const int rr = r0 + ro;
-                        const int tr = t0 + q * 32 + rr;
-                        if (tr < p.T && col_ok) {
-                            float4 x = *reinterpret_cast<const float4*>(&stg[rr][4 * cq]);
-                            x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
-                            const int64_t ro_off = (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)tr * p.o_st + nn;
-                            if (g.residual) {
-                                const float4 rs = *reinterpret_cast<const float4*>(g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)tr * p.r_st + nn);
-                                x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
-                            }
-                            x.x = x.x * sa + sb; x.y = x.y * sa + sb; x.z = x.z * sa + sb; x.w = x.w * sa + sb;
-                            if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
-                            ls += (x.x + x.y) + (x.z + x.w);
-                            lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-                            *reinterpret_cast<float4*>(g.out + ro_off) = x;
-                        }
-                    }
-                    if (p.stats_mode != 0) {
-                        const int g_first = no0 / gw, g_last = (min(no0 + cnt, Nout) - 1) / gw;
-                        if (g_first == g_last) {
-                            // the whole chunk is one group: plain warp reduction (fixed xor order -> deterministic)
-                            const float a = warp_sum(ls), c = warp_sum(lq);
-                            if (lane == 0) { sh->stats[q][g_first - g_lo][0] += a; sh->stats[q][g_first - g_lo][1] += c; }
-                        } else {
-                            // lanes with the same column quad first, then a fixed-order pass over the quads by lane 0
-                            for (int o = lpr; o < 32; o <<= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
-                            if (lane < lpr) { sh->part[q][lane][0] = ls; sh->part[q][lane][1] = lq; }
-                            __syncwarp();
-                            if (lane == 0) {
-                                for (int u = 0; u < lpr; ++u) {
-                                    const int nq = no0 + 4 * u;
-                                    if (nq < Nout) {
-                                        const int gi = nq / gw - g_lo;
-                                        sh->stats[q][gi][0] += sh->part[q][u][0];
-                                        sh->stats[q][gi][1] += sh->part[q][u][1];
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+                epilogue_fast_tile<AMODE, RES, STATS>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw);
             } else {
-                // generic (unaligned outputs / colscale) epilogue: lane = row, scattered stores
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                // generic (unaligned outputs / colscale) epilogue: lane = row, scattered stores; one warp per lane quarter
+                for (int c0 = 0; c0 < (ew < 4 ? BN : 0); c0 += 16) {
                     uint32_t r[16];
                     if (n_iters > 0) {
                         tmem_ld16(tacc + (uint32_t)c0, r);
@@ -414,7 +419,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                             if (gi != cur_g) {
                                 if (cur_g >= 0) {
                                     const float a = warp_sum(ssum), c = warp_sum(ssq);
-                                    if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
+                                    if (lane == 0) { sh->stats[ew][cur_g - g_lo][0] = a; sh->stats[ew][cur_g - g_lo][1] = c; }
                                 }
                                 cur_g = gi; ssum = 0.f; ssq = 0.f;
                             }
@@ -443,18 +448,19 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 }
                 if (p.stats_mode != 0 && cur_g >= 0) {
                     const float a = warp_sum(ssum), c = warp_sum(ssq);
-                    if (lane == 0) { sh->stats[q][cur_g - g_lo][0] = a; sh->stats[q][cur_g - g_lo][1] = c; }
+                    if (lane == 0) { sh->stats[ew][cur_g - g_lo][0] = a; sh->stats[ew][cur_g - g_lo][1] = c; }
                 }
             }
             // accumulator buffer drained: hand it back to the MMA warp before the (cheap) statistics flush
             tcgen05_fence_before();
             mbar_arrive(&sh->acc_empty[buf]);
             if (p.stats_mode != 0) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int e = threadIdx.x - 64;
                 if (e < 8) {
-                    const float a = (sh->stats[0][e][0] + sh->stats[1][e][0]) + (sh->stats[2][e][0] + sh->stats[3][e][0]);
-                    const float c = (sh->stats[0][e][1] + sh->stats[1][e][1]) + (sh->stats[2][e][1] + sh->stats[3][e][1]);
+                    float a = 0.f, c = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kEpiWarps; ++w) { a += sh->stats[w][e][0]; c += sh->stats[w][e][1]; }
                     const int gi = g_lo + e;
                     const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
                     if (gi < ngroups && (a != 0.f || c != 0.f)) {
@@ -462,9 +468,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         atomicAdd(&g.stats[2 * slot], (double)a);
                         atomicAdd(&g.stats[2 * slot + 1], (double)c);
                     }
-                    for (int w = 0; w < 4; ++w) { sh->stats[w][e][0] = 0.f; sh->stats[w][e][1] = 0.f; }
+                    for (int w = 0; w < kEpiWarps; ++w) { sh->stats[w][e][0] = 0.f; sh->stats[w][e][1] = 0.f; }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
@@ -636,7 +642,16 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     if (kStages > kMaxStages) kStages = kMaxStages;
     if (kStages < 2) kStages = 2;
     const size_t smem = (size_t)kStages * stage_bytes + sizeof(TcShared) + 1024;
-    cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, TapGemmArgs, int, uint32_t, uint32_t, int, int, int);
+    static const KernelFn table[4][2][2] = {
+        {{tapgemm_tc_kernel<0, false, false>, tapgemm_tc_kernel<0, false, true>}, {tapgemm_tc_kernel<0, true, false>, tapgemm_tc_kernel<0, true, true>}},
+        {{tapgemm_tc_kernel<1, false, false>, tapgemm_tc_kernel<1, false, true>}, {tapgemm_tc_kernel<1, true, false>, tapgemm_tc_kernel<1, true, true>}},
+        {{tapgemm_tc_kernel<2, false, false>, tapgemm_tc_kernel<2, false, true>}, {tapgemm_tc_kernel<2, true, false>, tapgemm_tc_kernel<2, true, true>}},
+        {{tapgemm_tc_kernel<3, false, false>, tapgemm_tc_kernel<3, false, true>}, {tapgemm_tc_kernel<3, true, false>, tapgemm_tc_kernel<3, true, true>}}};
+    const int amode = p.glu ? 3 : p.act;                 // the engine never combines GLU with an activation
+    if (p.glu && p.act != AERO_ACT_NONE) { set_error("aero_tapgemm_fwd(tcgen05): GLU with an activation is not supported"); return AERO_ERR_UNSUPPORTED; }
+    const KernelFn kern = table[amode][g.residual ? 1 : 0][p.stats_mode ? 1 : 0];
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     // persistent grid: as many CTAs as can be co-resident (shared memory and TMEM columns), never more than tiles
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -649,11 +664,11 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     if (tiles_total > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > (int)(512 / tmem_cols)) per_sm = (int)(512 / tmem_cols);
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 2) per_sm = 2;                      // 320 threads x ~96 registers: two CTAs per SM
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)num_sms * per_sm;
     dim3 grid((unsigned)(tiles_total < want ? tiles_total : want));
-    tapgemm_tc_kernel<<<grid, 192, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols, kStages, n_tiles, (int)tiles_total);
+    kern<<<grid, kThreads, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols, kStages, n_tiles, (int)tiles_total);
     return check_launch("aero_tapgemm_fwd(tcgen05)");
 }
 
