@@ -9,19 +9,21 @@
 //         GPT = 2 (32 < H <=  64): tile t holds gates (2t, 2t+1); in every warp lanes 0-15 carry gate 2t
 //                                  and lanes 16-31 gate 2t+1 of the same 16 cells -> 2 tiles, one shfl.xor 16
 //   B = h of the previous step, written by the cell-update threads straight into the swizzled
-//       shared-memory operand layout (TF32-rounded), 16 sequences per CTA;
+//       shared-memory operand layout, 16 sequences per CTA;
+//   operands are FP16 (kind::f16, K = 16 per UMMA): h is in (-1, 1) and W_hh is O(1), so FP16's 10-bit mantissa gives
+//       the same rounding as TF32 at half the shared-memory traffic and half the instruction count; accumulation is fp32;
 //   D = (4/GPT) x 16 fp32 columns of TMEM, read back with tcgen05.ld by the same threads.
 // The input-projection gate pre-activations (computed by the tap-GEMM in the same re-ordered column
 // order, so a warp reads 128 contiguous bytes per sequence) are prefetched while the MMA runs.
 // One elected thread issues the MMAs; two mbarriers ping-pong between "h ready" and "accumulators
 // ready".  c stays in registers for the whole sequence.  8 cell-update warps: two per TMEM lane
 // quarter, each owning 8 of the 16 sequences.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace aero {
 
 constexpr int kNT = 16;          // sequences per CTA (UMMA N)
-constexpr int kNS = 8;           // sequences per cell-update warp
 
 struct LstmTcShared {
     uint64_t w_full;
@@ -42,15 +44,40 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
         : "memory");
 }
 
-template <int GPT>   // gates per 128-row tile
-__global__ void __launch_bounds__(320, (GPT == 1 ? 1 : 2))
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int NSQ>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NSQ]);
+template <>
+__device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<4>(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(taddr)
+        : "memory");
+}
+
+// GPT: gates per 128-row tile.  NEW: cell-update warps (NEW/4 per TMEM lane quarter, each owning 64/NEW sequences).
+template <int GPT, int NEW>
+__global__ void __launch_bounds__(64 + 32 * NEW, (GPT == 1 ? 1 : 2))
 lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ gin, const float* __restrict__ bias_pad,
                float* __restrict__ hout, const aero_lstm_params p, const int nK) {
     constexpr int NM = 4 / GPT;                          // M tiles
     constexpr int CPW = 32 / GPT;                        // cells per warp
+    constexpr int kNS = 64 / NEW;                        // sequences per cell-update warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                                  // [NM][nK] tiles of 128 rows x 128 B
+    uint8_t* sA = smem;                                  // [NM][nK] tiles of 128 rows x 128 B (64 fp16 of K)
     uint8_t* sB = smem + NM * nK * 16384;                // [nK] tiles of 16 rows x 128 B
     LstmTcShared* sh = reinterpret_cast<LstmTcShared*>(sB + nK * 2048);
 
@@ -64,7 +91,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
     if (threadIdx.x == 0) {
         mbar_init(&sh->w_full, 1);
         mbar_init(&sh->acc_ready, 1);
-        mbar_init(&sh->h_ready, 256);
+        mbar_init(&sh->h_ready, 32 * NEW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < nK * 2048 / 4; i += blockDim.x) reinterpret_cast<float*>(sB)[i] = 0.f;
@@ -84,12 +111,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             mbar_expect_tx(&sh->w_full, (uint32_t)(NM * nK * 16384));
             for (int m = 0; m < NM; ++m)
                 for (int kc = 0; kc < nK; ++kc)
-                    tma_load_2d(sA + (m * nK + kc) * 16384, &mapW, &sh->w_full, kc * 32, (dir * NM + m) * 128);
+                    tma_load_2d(sA + (m * nK + kc) * 16384, &mapW, &sh->w_full, kc * 64, (dir * NM + m) * 128);
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // UMMA instruction descriptor: D=F32, A=B=TF32, K-major, N=16, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // UMMA instruction descriptor: D=F32 (1<<4), A=B=F16 (format 0), K-major, N=16, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             mbar_wait(&sh->w_full, 0);
             for (int s = 1; s < p.steps; ++s) {
@@ -102,17 +129,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                         const uint64_t db = make_desc_sw128(b0 + (uint32_t)(kc * 2048));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_tf32(tmem_base + (uint32_t)(m * kNT), da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_f16(tmem_base + (uint32_t)(m * kNT), da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);   // K = 16 fp16 = 32 B
                     }
                 }
                 umma_commit(&sh->acc_ready);
             }
         }
     } else {
-        // ===================================================== cell update (warps 2..9, 256 threads)
+        // ===================================================== cell update (warps 2..2+NEW)
         const int ew = warp - 2;
         const int q = warp & 3;                          // TMEM lane quarter
-        const int wp = ew >> 2;                          // which half of the 16 sequences
+        const int wp = ew >> 2;                          // which slice of the 16 sequences
         const int sub = lane / CPW;                      // gate slot inside the tile (0 for GPT=1)
         const int cell = q * CPW + (lane % CPW);
         const bool cell_ok = cell < H;
@@ -139,9 +166,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         }
         const float* bptr = bias_pad + dir * (NM * 128) + r;
         const int gstep = dpos * ldg, ostep = dpos * 2 * H;
-        // swizzled B-operand address of (sequence n = wp*8+i, k = cell): tile kc = cell/32, row n, chunk (j/4)^(n%8)
-        const int jq = (cell & 31) >> 2;
-        uint8_t* bbase = sB + (cell >> 5) * 2048 + wp * 1024 + ((cell & 3) << 2);
+        // swizzled B-operand address of (sequence n = wp*kNS+i, k = cell), fp16: tile kc = cell/64, row n (128 B),
+        // 16-byte chunk (j/8) ^ (n%8), 2 bytes per element
+        const int jq = (cell & 63) >> 3;
+        uint8_t* bbase = sB + (cell >> 6) * 2048 + ((cell & 7) << 1);
 
         float c_state[kNS];
 #pragma unroll
@@ -166,9 +194,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             float a[NM][kNS];
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                uint32_t acc[8];
+                uint32_t acc[kNS];
                 if (s > 0) {
-                    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * kNT + wp * kNS), acc);
+                    tmem_ld_n<kNS>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * kNT + wp * kNS), acc);
                 } else {
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) acc[i] = 0u;
@@ -198,7 +226,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                     c_state[i] = c;
                     const float h = round_tf32_rna(og * fast_tanh(c));
                     if (cell_ok) {
-                        *reinterpret_cast<float*>(bbase + i * 128 + ((jq ^ i) << 4)) = h;
+                        const int n = wp * kNS + i;
+                        *reinterpret_cast<__half*>(bbase + (n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4)) = __float2half_rn(h);
                         bool wr = (flags >> i) & 1u;
                         if (!p.out_windowed) {
                             const int lo = ((flags >> (8 + i)) & 1u) ? 0 : half;
@@ -232,12 +261,13 @@ int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, 
         return AERO_ERR_UNSUPPORTED;
     }
     const int gpt = H <= 64 ? 2 : 1;
-    const int nM = 4 / gpt, nK = (H + 31) / 32;
+    const int nM = 4 / gpt, nK = (H + 63) / 64;
+    const int Kp = nK * 64;                              // the host pads W_hh rows to a multiple of 64 fp16 (128 bytes)
     CUtensorMap mW;
-    uint64_t dims[2] = {(uint64_t)H, (uint64_t)(2 * nM * 128)};
-    uint64_t strides[1] = {(uint64_t)H * 4};
-    uint32_t box[2] = {32, 128};
-    int rc = encode_map(&mW, whh_r, 2, dims, strides, box);
+    uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)(2 * nM * 128)};
+    uint64_t strides[1] = {(uint64_t)Kp * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = encode_map(&mW, whh_r, 2, dims, strides, box, false, 2);
     if (rc != AERO_OK) return rc;
     const size_t smem = (size_t)nM * nK * 16384 + (size_t)nK * 2048 + sizeof(LstmTcShared) + 1024;
     if (smem > 227 * 1024) {
@@ -252,11 +282,11 @@ int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, 
     }
     dim3 grid(cdiv(n_seq, kNT), 2);
     if (gpt == 1) {
-        cudaFuncSetAttribute(lstm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lstm_tc_kernel<1><<<grid, 320, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
+        cudaFuncSetAttribute(lstm_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_tc_kernel<1, 16><<<grid, 64 + 32 * 16, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
     } else {
-        cudaFuncSetAttribute(lstm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lstm_tc_kernel<2><<<grid, 320, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
+        cudaFuncSetAttribute(lstm_tc_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_tc_kernel<2, 8><<<grid, 64 + 32 * 8, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
     }
     return check_launch("aero_lstm_rec_fwd(tcgen05)");
 }

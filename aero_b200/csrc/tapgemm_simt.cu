@@ -319,11 +319,82 @@ __global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g
     }
 }
 
+// thin transposed conv (stride_f * N <= 8: the final 96 -> 2 layer, reference aero.py:179,209): the s output rows fed by one
+// input row pair are computed together.  With a = fo' / s the taps are fi = a - j, slab = r + j*s for output row
+// fo' = a*s + r: treat (r, n) as 8 "virtual columns" of a plain conv over j.  Every input row is then read k/s times
+// instead of k times, and each thread keeps all its accumulators.
+__global__ void __launch_bounds__(256) tapgemm_thin_convt_kernel(const TapGemmArgs g, const int a_lo, const int n_a) {
+    extern __shared__ __align__(16) float wsm[];          // [ntaps][K][8]: column v = r*N + n
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1, s = p.stride_f, ntaps = p.kf / s;
+    for (int i = threadIdx.x; i < ntaps * K * kThinN; i += blockDim.x) {
+        const int v = i % kThinN, c = (i / kThinN) % K, j = i / (kThinN * K);
+        const int r = v / p.N, n = v % p.N;
+        wsm[i] = (r < s) ? g.w[((int64_t)(r + j * s) * K + c) * g.ldw + n] : 0.f;
+    }
+    __syncthreads();
+    const int64_t npix = (int64_t)p.B * n_a * p.T;
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(pix % p.T);
+        const int64_t rowi = pix / p.T;
+        const int a = a_lo + (int)(rowi % n_a), b = (int)(rowi / n_a);
+        float acc[kThinN];
+#pragma unroll
+        for (int v = 0; v < kThinN; ++v) acc[v] = 0.f;
+        for (int j = 0; j < ntaps; ++j) {
+            const int fi = a - j;
+            if (fi < 0 || fi >= p.F_in) continue;
+            const float* src = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)t * p.a1_st;
+            const float* wt = wsm + (int64_t)j * K * kThinN;
+            for (int c = 0; c < K; c += 4) {
+                const float4 av = *reinterpret_cast<const float4*>(src + c);
+                const float avs[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wt + (c + u) * kThinN);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wt + (c + u) * kThinN + 4);
+                    acc[0] = fmaf(avs[u], w0.x, acc[0]); acc[1] = fmaf(avs[u], w0.y, acc[1]);
+                    acc[2] = fmaf(avs[u], w0.z, acc[2]); acc[3] = fmaf(avs[u], w0.w, acc[3]);
+                    acc[4] = fmaf(avs[u], w1.x, acc[4]); acc[5] = fmaf(avs[u], w1.y, acc[5]);
+                    acc[6] = fmaf(avs[u], w1.z, acc[6]); acc[7] = fmaf(avs[u], w1.w, acc[7]);
+                }
+            }
+        }
+        float sa = 1.f, sb = 0.f;
+        if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
+#pragma unroll
+        for (int v = 0; v < kThinN; ++v) {
+            const int r = v / p.N, n = v % p.N;
+            const int fo = a * s + r - p.f_out_offset;
+            if (r < s && fo >= 0 && fo < p.F_out) {
+                float x = acc[v] + (g.bias ? g.bias[n] : 0.f);
+                if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                x = x * sa + sb;
+                if (p.flags & 1) x = round_tf32_rna(x);
+                g.out[(int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n] = x;
+            }
+        }
+    }
+}
+
 int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
     const aero_tapgemm_params& p = g.p;
     TapGemmArgs a = g;
     const bool plain = !p.glu && p.stats_mode == 0 && !g.addend_fn && !g.colscale && p.w_sb == 0;
     const int nslab = (p.mode == AERO_TAPS_CONVT) ? p.kf : p.kf * p.kt;
+    if (plain && p.mode == AERO_TAPS_CONVT && p.stride_f * p.N <= kThinN && p.C2 == 0 && g.vec_a && !g.residual &&
+        (size_t)(p.kf / p.stride_f) * p.C1 * kThinN * 4 <= 96 * 1024) {
+        const size_t smem = (size_t)(p.kf / p.stride_f) * p.C1 * kThinN * 4;
+        cudaFuncSetAttribute(tapgemm_thin_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int a_lo = p.f_out_offset / p.stride_f, a_hi = (p.f_out_offset + p.F_out - 1) / p.stride_f;
+        const int n_a = a_hi - a_lo + 1;
+        const int64_t npix = (int64_t)p.B * n_a * p.T;
+        int blocks = (int)((npix + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        tapgemm_thin_convt_kernel<<<blocks, 256, smem, st>>>(a, a_lo, n_a);
+        return check_launch("aero_tapgemm_fwd(thin-convt)");
+    }
     if (plain && p.N <= kThinN && g.vec_a && (size_t)nslab * (p.C1 + p.C2) * kThinN * 4 <= 96 * 1024) {
         const size_t smem = (size_t)nslab * (p.C1 + p.C2) * kThinN * 4;
         cudaFuncSetAttribute(tapgemm_thin_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -515,14 +515,14 @@ struct MapKeyHash {
 };
 
 int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, bool swizzle_32b_atom) {
+               const uint32_t* box, bool swizzle_32b_atom, int elem_bytes) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key;
     std::memset(&key, 0, sizeof(key));
     key.base = base;
     key.rank = rank;
-    key.swz = swizzle_32b_atom ? 1u : 0u;
+    key.swz = (swizzle_32b_atom ? 1u : 0u) | ((uint32_t)elem_bytes << 8);
     for (uint32_t i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.box[i] = box[i]; }
     for (uint32_t i = 0; i + 1 < rank; ++i) key.s[i] = strides_bytes[i];
     {
@@ -537,7 +537,7 @@ int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t
     cuuint32_t bx[4], es[4];
     for (uint32_t i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (uint32_t i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gd, gs, bx, es,
+    CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gd, gs, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -63,6 +63,14 @@ def lstm_gate_reorder(H):
     return src, cell < H
 
 
+def lstm_whh_fp16(whh_rows):
+    """[rows, H] fp32 -> [rows, 64*ceil(H/64)] fp16 (zero padded): the A operand of the tcgen05 LSTM recurrence."""
+    rows, H = whh_rows.shape
+    out = torch.zeros(rows, 64 * ((H + 63) // 64), dtype=torch.float16, device=whh_rows.device)
+    out[:, :H] = whh_rows.to(torch.float16)
+    return out.contiguous()
+
+
 def glu_perm(n, device):
     """Column order that puts GLU partners (j, j + n/2) next to each other."""
     half = n // 2
@@ -225,7 +233,7 @@ class AeroEngine:
                                 bb.append(reord(sd[f"{q}.lstm.lstm.bias_ih_l{l}{sfx}"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}{sfx}"]))
                             W[f"{o}.lstm{l}r.ih.w"] = pack_taps(torch.cat(wih, 0)[:, :, None])
                             W[f"{o}.lstm{l}r.b"] = torch.cat(bb).contiguous()
-                            W[f"{o}.lstm{l}r.whh"] = tf32_round(torch.cat(whh, 0).contiguous())
+                            W[f"{o}.lstm{l}r.whh"] = lstm_whh_fp16(torch.cat(whh, 0))
                         W[o + ".lin.w"] = pack_taps(sd[q + ".lstm.linear.weight"][:, :, None])
                         W[o + ".lin.b"] = sd[q + ".lstm.linear.bias"].contiguous()
                     if g.attn:
@@ -251,7 +259,7 @@ class AeroEngine:
             W[p + ".rw.w"], W[p + ".rw.b"] = pack_taps(wr), br.contiguous()
             W[p + ".ct.w"] = pack_taps(sd[p + ".conv_tr.weight"][:, :, :, 0].permute(1, 0, 2))
             W[p + ".ct.b"] = sd[p + ".conv_tr.bias"].contiguous()
-        out = {k: v.to(device=dev, dtype=torch.float32) for k, v in W.items()}
+        out = {k: (v.to(dev) if v.dtype == torch.float16 else v.to(device=dev, dtype=torch.float32)) for k, v in W.items()}
         # K-major TF32 twins of every tap-GEMM weight for the tcgen05 path: [taps, K, pad4(N)] -> [taps, pad4(N), K]
         self._wk, self._wname = {}, {}
         for k in [k for k in out if k.endswith("ftbfc.w")]:

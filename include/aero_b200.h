@@ -188,11 +188,11 @@ typedef struct {
     int32_t in_windowed, out_windowed;
     int32_t round_tf32;
     int32_t precision;                /* 0: fp32 SIMT recurrence (layouts above);
-                                         1: TF32 tcgen05 recurrence.  Gate rows are re-ordered into 4/GPT tiles of 128 per
+                                         1: tcgen05 recurrence, FP16 operands (h in (-1,1), W_hh O(1): same 10-bit mantissa as TF32), fp32 accumulate.  Gate rows are re-ordered into 4/GPT tiles of 128 per
                                             direction (GPT = 2 if H <= 64 else 1): GPT=1: tile g = gate g, row = cell;
                                             GPT=2: tile t = gates (2t, 2t+1), in each group of 32 rows rows 0-15 carry gate 2t
-                                            and rows 16-31 gate 2t+1 of the same 16 cells.  `whh` is [2][(4/GPT)*128][H]
-                                            (TF32-rounded, zero rows beyond H) and `gin` / `bias_pad` rows have
+                                            and rows 16-31 gate 2t+1 of the same 16 cells.  `whh` is FP16 [2][(4/GPT)*128][Kp],
+                                            Kp = 64*ceil(H/64) (zero rows beyond H, zero columns beyond H) and `gin` / `bias_pad` rows have
                                             2*(4/GPT)*128 columns in the same order.  H % 4 == 0, 32 < H <= 96. */
 } aero_lstm_params;
 int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout,

@@ -285,7 +285,7 @@ def test_tcgen05_is_selected_for_the_big_convs(engines):
 @pytest.mark.parametrize("H,T,rows", [(48, 251, 5), (96, 123, 3), (96, 501, 2), (64, 40, 20), (36, 230, 3)])
 def test_lstm_layer_pair_tcgen05(engines, H, T, rows):
     """tcgen05 recurrence (TF32 h*W_hh, fp32 accumulate, fast sigmoid/tanh) against the fp32 cell recurrence."""
-    from aero_b200.engine import lstm_gate_reorder, tf32_round
+    from aero_b200.engine import lstm_gate_reorder, lstm_whh_fp16, tf32_round
     gpu, emu = engines
     steps, stride, n_win = (200, 100, math.ceil(T / 100)) if T > 200 else (T, 0, 1)
     n_seq = rows * n_win
@@ -304,7 +304,7 @@ def test_lstm_layer_pair_tcgen05(engines, H, T, rows):
         return torch.cat(parts, -1).contiguous()
 
     def rows_(w):     # [2, 4H, H] -> [2*nM*128, H]
-        return tf32_round(torch.cat([torch.where(ok[:, None], w[d][src], torch.zeros(())) for d in range(2)], 0).contiguous())
+        return lstm_whh_fp16(torch.cat([torch.where(ok[:, None], w[d][src], torch.zeros(())) for d in range(2)], 0))
 
     gpu.precision = 1
     try:

@@ -34,7 +34,7 @@ SHAPES = {
 
 def run_lstm(args):
     """enc3-like BiLSTM layer-2 recurrence: H=96 (or 48), 768 (1536) windows of 200 steps."""
-    from aero_b200.engine import lstm_gate_reorder
+    from aero_b200.engine import lstm_gate_reorder, lstm_whh_fp16
     H = 96 if args.shape == "lstm96" else 48
     rows = (4 if H == 96 else 8) * args.batch
     T, n_win, steps, stride = 501, 6, 200, 100
@@ -48,7 +48,7 @@ def run_lstm(args):
     whh = torch.randn(2, 4 * H, H) / math.sqrt(H)
     if tc:
         src, ok = lstm_gate_reorder(H)
-        whh = tf32_round(torch.cat([torch.where(ok[:, None], whh[d][src], torch.zeros(())) for d in range(2)], 0).contiguous())
+        whh = lstm_whh_fp16(torch.cat([torch.where(ok[:, None], whh[d][src], torch.zeros(())) for d in range(2)], 0))
     whh = whh.cuda()
     hout = torch.zeros(rows * T, 2 * H, device="cuda")
     ms = []
