@@ -32,8 +32,17 @@ struct LstmTcShared {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+// ex2.approx / rcp.approx: <= 2 ulp each, i.e. ~1e-7 relative on the gates (far below the operand rounding)
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
@@ -148,41 +157,54 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         const int dpos = dir ? -1 : 1;
         const int pos0 = dir ? p.steps - 1 : 0;
 
-        // Per-sequence state (32-bit element offsets; the host checks they fit).  For GPT=2 lane<16 updates even
-        // local sequences, lane>=16 odd ones.
-        int goff[kNS], ooff[kNS], frame0[kNS];
-        uint32_t flags = 0;          // per i: bit i = sequence exists, bit 8+i = first window, bit 16+i = last window
+        // Per-sequence state, all loop-invariant work hoisted (32-bit element offsets; the host checks they fit).
+        // A step s reads the input projection iff (unsigned)(s - g_lo) < g_len (else the frame is zero padding: bias only)
+        // and writes its output iff (unsigned)(s - w_lo) < w_len (window crop of modules.py:53-59 and the T limit).
+        // For GPT=2 lane<16 updates even local sequences, lane>=16 odd ones.
+        int goff[kNS], ooff[kNS];
+        int g_lo[kNS], g_len[kNS], w_lo[kNS], w_len[kNS];
+        uint32_t baddr[kNS];
+        const int jq = (cell & 63) >> 3;
+        const uint32_t bbase = smem_u32(sB) + (uint32_t)((cell >> 6) * 2048 + ((cell & 7) << 1));
 #pragma unroll
         for (int i = 0; i < kNS; ++i) {
             const int n = wp * kNS + i;
             const int sq = min(seq0 + n, n_seq - 1);
+            const bool exists = seq0 + n < n_seq;
             const int row = sq / p.n_win, k = sq - row * p.n_win;
-            if (seq0 + n < n_seq) flags |= 1u << i;
-            if (k == 0) flags |= 1u << (8 + i);
-            if (k == p.n_win - 1) flags |= 1u << (16 + i);
-            frame0[i] = k * p.win_stride + pos0;
-            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + frame0[i])) * ldg + dir * (NM * 128) + r;
-            ooff[i] = (p.out_windowed ? (sq * p.steps + pos0) : (row * p.T + frame0[i])) * 2 * H + dir * H + cell;
+            const int f0 = k * p.win_stride;                               // first frame of the window
+            const int frame_start = f0 + pos0;
+            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + frame_start)) * ldg + dir * (NM * 128) + r;
+            ooff[i] = (p.out_windowed ? (sq * p.steps + pos0) : (row * p.T + frame_start)) * 2 * H + dir * H + cell;
+            // valid positions of this window: input frames < T; kept output positions [lo, hi) intersected with frames < T
+            const int in_hi = p.in_windowed ? p.steps : max(0, min(p.steps, p.T - f0));
+            int lo = 0, hi = p.steps;
+            if (!p.out_windowed) {
+                lo = (k == 0) ? 0 : half;
+                hi = min((k == p.n_win - 1) ? p.steps : p.steps - half, p.T - f0);
+            }
+            if (!exists || !cell_ok) hi = lo;
+            // position -> step: dir 0: s = pos; dir 1: s = steps-1-pos
+            g_lo[i] = dir ? p.steps - in_hi : 0;
+            g_len[i] = in_hi;
+            w_lo[i] = dir ? p.steps - hi : lo;
+            w_len[i] = max(0, hi - lo);
+            // swizzled B-operand address of (sequence n, k = cell), fp16: tile kc = cell/64, row n (128 B), chunk (j/8)^(n%8)
+            baddr[i] = bbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4));
         }
         const float* bptr = bias_pad + dir * (NM * 128) + r;
         const int gstep = dpos * ldg, ostep = dpos * 2 * H;
-        // swizzled B-operand address of (sequence n = wp*kNS+i, k = cell), fp16: tile kc = cell/64, row n (128 B),
-        // 16-byte chunk (j/8) ^ (n%8), 2 bytes per element
-        const int jq = (cell & 63) >> 3;
-        uint8_t* bbase = sB + (cell >> 6) * 2048 + ((cell & 7) << 1);
 
         float c_state[kNS];
 #pragma unroll
         for (int i = 0; i < kNS; ++i) c_state[i] = 0.f;
 
         for (int s = 0; s < p.steps; ++s) {
-            const int pos = pos0 + dpos * s;
             // ---- prefetch the input-projection gate pre-activations (coalesced: lane r is contiguous)
             float gi[NM][kNS];
 #pragma unroll
             for (int i = 0; i < kNS; ++i) {
-                const float* src = gin + goff[i];
-                if (!p.in_windowed && frame0[i] + dpos * s >= p.T) src = bptr;   // zero-padded frames: bias only
+                const float* src = ((unsigned)(s - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
                 for (int m = 0; m < NM; ++m) gi[m][i] = src[m * 128];
                 goff[i] += gstep;
@@ -201,11 +223,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) acc[i] = 0u;
                 }
-                const int gate = m * GPT + sub;           // PyTorch order: 0 i, 1 f, 2 g, 3 o
+                // PyTorch gate order 0 i, 1 f, 2 g, 3 o; gate 2 is tanh = 2*sigmoid(2x) - 1: fold into scale / affine
+                const int gate = m * GPT + sub;
+                const float k_in = (gate == 2) ? -2.885390081777927f : -1.4426950408889634f;   // -(1|2) * log2(e)
+                const float k_mul = (gate == 2) ? 2.0f : 1.0f, k_add = (gate == 2) ? -1.0f : 0.0f;
 #pragma unroll
                 for (int i = 0; i < kNS; ++i) {
                     const float x = __uint_as_float(acc[i]) + gi[m][i];
-                    a[m][i] = (gate == 2) ? fast_tanh(x) : fast_sigmoid(x);
+                    a[m][i] = fmaf(k_mul, fast_rcp(1.0f + fast_ex2(k_in * x)), k_add);
                 }
             }
 #pragma unroll
@@ -222,20 +247,15 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                     mine = (i & 1) == sub;
                 }
                 if (mine) {
-                    const float c = fg * c_state[i] + ig * gg;
+                    const float c = fmaf(fg, c_state[i], ig * gg);
                     c_state[i] = c;
-                    const float h = round_tf32_rna(og * fast_tanh(c));
+                    const float th = fmaf(2.0f, fast_rcp(1.0f + fast_ex2(-2.885390081777927f * c)), -1.0f);
+                    const float h = round_tf32_rna(og * th);
                     if (cell_ok) {
-                        const int n = wp * kNS + i;
-                        *reinterpret_cast<__half*>(bbase + (n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4)) = __float2half_rn(h);
-                        bool wr = (flags >> i) & 1u;
-                        if (!p.out_windowed) {
-                            const int lo = ((flags >> (8 + i)) & 1u) ? 0 : half;
-                            const int hi = ((flags >> (16 + i)) & 1u) ? p.steps : p.steps - half;
-                            wr = wr && pos >= lo && pos < hi && frame0[i] + dpos * s < p.T;
-                        }
-                        if (wr) hout[ooff[i]] = h;
+                        const unsigned short hh = __half_as_ushort(__float2half_rn(h));
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(baddr[i]), "h"(hh) : "memory");
                     }
+                    if ((unsigned)(s - w_lo[i]) < (unsigned)w_len[i]) hout[ooff[i]] = h;
                 }
                 ooff[i] += ostep;
             }
