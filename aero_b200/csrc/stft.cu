@@ -259,6 +259,268 @@ static int launch_istft(const float* z, const float* window, float* y, const aer
     return check_launch("aero_istft_fwd");
 }
 
+// ---------------------------------------------------------------------------------- n_fft = 512 fast path
+// The model's size.  The 256-point complex FFT behind the 512-point real transform is done as a four-step 16 x 16
+// decomposition with both 16-point FFTs held entirely in registers (two radix-4 passes, constant twiddles):
+//   n = 16 n1 + n2, k = k1 + 16 k2:  Z[k] = sum_n2 W256^(n2 k1) [ sum_n1 z[16 n1 + n2] W16^(n1 k1) ] W16^(n2 k2)
+// One thread owns one (frame, n2) column in pass 1 and one (frame, k1) row in pass 2; 16 frames per CTA = 256 threads;
+// four block barriers in total (the radix-2 kernel above needs eleven), no bit reversal.
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+    const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+    // forward: y1 = d02 - i d13, y3 = d02 + i d13; inverse: swapped
+    const float2 jd = INV ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);      // (-/+ i) * d13
+    a0 = make_float2(s02.x + s13.x, s02.y + s13.y);
+    a2 = make_float2(s02.x - s13.x, s02.y - s13.y);
+    a1 = make_float2(d02.x + jd.x, d02.y + jd.y);
+    a3 = make_float2(d02.x - jd.x, d02.y - jd.y);
+}
+
+// in-register 16-point DFT; on return v[r + 4 s] holds A[r + 4 s] (natural order)
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    // n = 4 p + q, k = r + 4 s.  Step 1: 4-point DFT over p for each q: (v[q], v[4+q], v[8+q], v[12+q]) -> B[q][r] stored at v[4 r + q]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dft4<INV>(v[q], v[4 + q], v[8 + q], v[12 + q]);
+    // Step 2: twiddle B[q][r] *= W16^(q r)
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+    const float sg = INV ? 1.f : -1.f;                   // forward twiddles have negative imaginary part
+    // (q, r) pairs with q r in {1,2,3,4,6,9}
+    v[4 * 1 + 1] = cmul(v[4 * 1 + 1], make_float2(C1, sg * S1));      // q r = 1
+    v[4 * 1 + 2] = cmul(v[4 * 1 + 2], make_float2(C2, sg * C2));      // 2  (r=1,q=2)
+    v[4 * 2 + 1] = cmul(v[4 * 2 + 1], make_float2(C2, sg * C2));      // 2  (r=2,q=1)
+    v[4 * 1 + 3] = cmul(v[4 * 1 + 3], make_float2(S1, sg * C1));      // 3  (r=1,q=3)
+    v[4 * 3 + 1] = cmul(v[4 * 3 + 1], make_float2(S1, sg * C1));      // 3  (r=3,q=1)
+    v[4 * 2 + 2] = cmul(v[4 * 2 + 2], make_float2(0.f, sg * 1.f));     // 4  (r=2,q=2)
+    v[4 * 2 + 3] = cmul(v[4 * 2 + 3], make_float2(-C2, sg * C2));      // 6  (r=2,q=3)
+    v[4 * 3 + 2] = cmul(v[4 * 3 + 2], make_float2(-C2, sg * C2));      // 6  (r=3,q=2)
+    v[4 * 3 + 3] = cmul(v[4 * 3 + 3], make_float2(-C1, -sg * S1));     // 9  (r=3,q=3): cos(9pi/8) = -C1, sin = -S1
+    // Step 3: 4-point DFT over q for each r: (v[4r], v[4r+1], v[4r+2], v[4r+3]) -> A[r + 4 s] at v[4 r + s]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dft4<INV>(v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);
+    // reorder v[4 r + s] -> v[r + 4 s]  (4x4 transpose, register renaming only)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int sx = r + 1; sx < 4; ++sx) { const float2 t = v[4 * r + sx]; v[4 * r + sx] = v[4 * sx + r]; v[4 * sx + r] = t; }
+}
+
+constexpr int kF512 = 16;            // frames per CTA
+constexpr int kTPad = 17;            // padded row of the transpose buffer (float2)
+
+__global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ x, const float* __restrict__ window,
+                                                      float* __restrict__ z, double* __restrict__ stats,
+                                                      const aero_stft_params p) {
+    constexpr int N = 512, M = 256;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* work = reinterpret_cast<float2*>(smem_raw);                 // [16][256]  Z in natural order
+    float2* tbuf = work + kF512 * M;                                    // [16][16][17] pass-1 output; later the store stage [257][16]
+    float2* tw256 = tbuf + kF512 * 16 * kTPad;                          // [256] exp(-2 pi i m / 256)
+    float2* twp = tw256 + M;                                            // [129] exp(-2 pi i k / 512)
+    float* wpad = reinterpret_cast<float*>(twp + 132);                  // [512]
+    float* seg = wpad + N;                                              // [15*hop + 512]
+
+    const int sig = blockIdx.y;
+    const int t0 = blockIdx.x * kF512;
+    const int nfr = min(kF512, p.frames - t0);
+    const int L = p.length;
+    const int tid = threadIdx.x;
+    {
+        float sn, cs;
+        sincospif(2.0f * (float)tid / 256.0f, &sn, &cs);
+        tw256[tid] = make_float2(cs, -sn);
+        if (tid <= 128) { sincospif(2.0f * (float)tid / 512.0f, &sn, &cs); twp[tid] = make_float2(cs, -sn); }
+    }
+    const int wl = (N - p.win) / 2;
+    for (int n = tid; n < N; n += 256) { const int k = n - wl; wpad[n] = (k >= 0 && k < p.win) ? window[k] : 0.0f; }
+    const int seg_len = (nfr - 1) * p.hop + N;
+    const float* xs = x + (int64_t)sig * L;
+    const int q0 = t0 * p.hop - N / 2;
+    for (int i = tid; i < seg_len; i += 256) {
+        int src = q0 + i;
+        if (src < 0) src = -src;
+        if (src >= L) src = 2 * (L - 1) - src;
+        seg[i] = xs[src];
+    }
+    __syncthreads();
+
+    const int fr = tid >> 4, c = tid & 15;            // pass 1: c = n2; pass 2: c = k1
+    float2 v[16];
+    if (fr < nfr) {
+        // z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n = 16 n1 + n2
+        const float* sf = seg + fr * p.hop;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int n = 2 * (16 * n1 + c);
+            v[n1] = make_float2(sf[n] * wpad[n], sf[n + 1] * wpad[n + 1]);
+        }
+        dft16<false>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) tbuf[(fr * 16 + c) * kTPad + k1] = cmul(v[k1], tw256[c * k1]);
+    }
+    __syncthreads();
+    if (fr < nfr) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) v[n2] = tbuf[(fr * 16 + n2) * kTPad + c];
+        dft16<false>(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) work[fr * M + c + 16 * k2] = v[k2];
+    }
+    __syncthreads();
+
+    // split post-pass (as in the generic kernel): X[k] = Xe[k] + w^k Xo[k], X[M-k] = conj(Xe[k] - w^k Xo[k]); staged [k][frame]
+    float2* stage = tbuf;
+    const float scale = rsqrtf((float)N);
+    for (int i = tid; i < nfr * (M / 2 + 1); i += 256) {
+        const int f2 = i / (M / 2 + 1), k = i - f2 * (M / 2 + 1);
+        const float2 a = work[f2 * M + k];
+        const float2 bq = work[f2 * M + ((M - k) & (M - 1))];
+        const float2 xe = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
+        const float2 d = make_float2(0.5f * (a.x - bq.x), 0.5f * (a.y + bq.y));
+        const float2 xo = make_float2(d.y, -d.x);
+        const float2 t = cmul(twp[k], xo);
+        stage[k * kF512 + f2] = make_float2(scale * (xe.x + t.x), scale * (xe.y + t.y));
+        stage[(M - k) * kF512 + f2] = make_float2(scale * (xe.x - t.x), -scale * (xe.y - t.y));
+    }
+    __syncthreads();
+
+    float* zs = z + (int64_t)(sig / p.channels) * p.z_stride_b + (int64_t)(sig % p.channels) * p.z_stride_c;
+    float lsum = 0.f, lsq = 0.f;
+    for (int i = tid; i < p.bins_out * nfr; i += 256) {
+        const int k = i / nfr, f2 = i - k * nfr;
+        const float2 o = stage[k * kF512 + f2];
+        *reinterpret_cast<float2*>(zs + (int64_t)k * p.z_stride_k + (int64_t)(t0 + f2) * p.z_stride_t) = o;
+        lsum += o.x + o.y;
+        lsq += o.x * o.x + o.y * o.y;
+    }
+    if (stats != nullptr) {
+        __shared__ double red[2][8];
+        double ds = warp_sum((double)lsum), dq = warp_sum((double)lsq);
+        if ((tid & 31) == 0) { red[0][tid >> 5] = ds; red[1][tid >> 5] = dq; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0, b = 0;
+            for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+            atomicAdd(&stats[2 * (sig / p.channels)], a);
+            atomicAdd(&stats[2 * (sig / p.channels) + 1], b);
+        }
+    }
+}
+
+static int launch_stft512(const float* x, const float* window, float* z, double* stats, const aero_stft_params& p, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (kF512 * 256 + (size_t)kF512 * 16 * kTPad + 256 + 132) +
+                        sizeof(float) * (512 + (size_t)(kF512 - 1) * p.hop + 512);
+    cudaFuncSetAttribute(stft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(cdiv(p.frames, kF512), p.n_signals);
+    stft512_kernel<<<grid, 256, smem, st>>>(x, window, z, stats, p);
+    return check_launch("aero_stft_fwd(512)");
+}
+
+// inverse: 16 resident frames per CTA, same four-step transform with conjugate twiddles, then overlap-add
+__global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__ z, const float* __restrict__ window,
+                                                       float* __restrict__ y, const aero_istft_params p, const int OB,
+                                                       const int halo) {
+    constexpr int N = 512, M = 256, NF = kF512;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* work = reinterpret_cast<float2*>(smem_raw);                 // [16][256] -> real frames [16][512]
+    float2* xsb = work + NF * M;                                        // [16][257] spectra; later reused as the transpose buffer
+    float2* tw256 = xsb + NF * 16 * kTPad;                              // [256] exp(+2 pi i m / 256)  (xsb region sized for the transpose)
+    float2* twp = tw256 + M;                                            // [257] exp(+2 pi i k / 512), k <= 256
+    float* wpad = reinterpret_cast<float*>(twp + 260);                  // [512]
+
+    const int sig = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    const int t_lo = max(0, blk * OB - halo);
+    const int t_hi = min(p.frames - 1, blk * OB + OB - 1);
+    const int nfr = t_hi - t_lo + 1;
+    {
+        float sn, cs;
+        sincospif(2.0f * (float)tid / 256.0f, &sn, &cs);
+        tw256[tid] = make_float2(cs, sn);
+        sincospif(2.0f * (float)tid / 512.0f, &sn, &cs);
+        twp[tid] = make_float2(cs, sn);
+        if (tid == 0) twp[256] = make_float2(-1.f, 0.f);
+    }
+    const int wl = (N - p.win) / 2;
+    for (int n = tid; n < N; n += 256) { const int k = n - wl; wpad[n] = (k >= 0 && k < p.win) ? window[k] : 0.0f; }
+    const float* zs = z + (int64_t)(sig / p.channels) * p.z_stride_b + (int64_t)(sig % p.channels) * p.z_stride_c;
+    for (int i = tid; i < (M + 1) * nfr; i += 256) {
+        const int k = i / nfr, f2 = i - k * nfr;
+        float2 o = make_float2(0.f, 0.f);
+        if (k < p.bins_in) o = *reinterpret_cast<const float2*>(zs + (int64_t)k * p.z_stride_k + (int64_t)(t_lo + f2) * p.z_stride_t);
+        if (k == 0 || k == M) o.y = 0.f;
+        xsb[f2 * (M + 1) + k] = o;
+    }
+    __syncthreads();
+
+    const int fr = tid >> 4, c = tid & 15;
+    float2 v[16];
+    if (fr < nfr) {
+        // Y[k] = Xe[k] + i Xo[k], k = 16 k1' + c  (pass 1 runs over the "slow" index, as in the forward transform)
+        const float2* xf = xsb + fr * (M + 1);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int k = 16 * n1 + c;
+            const float2 a = xf[k], b = xf[M - k];
+            const float2 xe = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+            const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+            const float2 xo = cmul(twp[k], d);
+            v[n1] = make_float2(xe.x - xo.y, xe.y + xo.x);
+        }
+        dft16<true>(v);
+    }
+    __syncthreads();                                                      // all reads of xsb done: reuse it as the transpose buffer
+    float2* tbuf = xsb;
+    if (fr < nfr) {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) tbuf[(fr * 16 + c) * kTPad + k1] = cmul(v[k1], tw256[c * k1]);
+    }
+    __syncthreads();
+    if (fr < nfr) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) v[n2] = tbuf[(fr * 16 + n2) * kTPad + c];
+        dft16<true>(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) work[fr * M + c + 16 * k2] = v[k2];      // = (x[2n], x[2n+1]) * M, n = c + 16 k2
+    }
+    __syncthreads();
+
+    const float* frames = reinterpret_cast<const float*>(work);
+    const float scale = 2.0f * rsqrtf((float)N);
+    const int p0 = blk * OB * p.hop, span = OB * p.hop;
+    float* ys = y + (int64_t)sig * p.out_len;
+    for (int i = tid; i < span; i += 256) {
+        const int pos = p0 + i;
+        const int n_out = pos - N / 2;
+        if (n_out < 0 || n_out >= p.out_len) continue;
+        int ta = (pos - N + p.hop) / p.hop;
+        if (pos - N + 1 <= 0) ta = 0;
+        ta = max(ta, t_lo);
+        const int tb = min(pos / p.hop, t_hi);
+        float acc = 0.f, env = 0.f;
+        for (int t = ta; t <= tb; ++t) {
+            const int n = pos - t * p.hop;
+            const float w = wpad[n];
+            acc += frames[(t - t_lo) * N + n] * w;
+            env += w * w;
+        }
+        ys[n_out] = acc * scale / env;
+    }
+}
+
+static int launch_istft512(const float* z, const float* window, float* y, const aero_istft_params& p, cudaStream_t st, bool* taken) {
+    const int halo = 511 / p.hop;
+    const int OB = kF512 - halo;
+    *taken = OB >= 4;                                     // tiny hops fall back to the generic kernel (32 resident frames)
+    if (!*taken) return AERO_OK;
+    const size_t smem = sizeof(float2) * (kF512 * 256 + (size_t)kF512 * 16 * kTPad + 256 + 260) + sizeof(float) * 512;
+    cudaFuncSetAttribute(istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int last_pos = 256 + p.out_len - 1;
+    dim3 grid(last_pos / (OB * p.hop) + 1, p.n_signals);
+    istft512_kernel<<<grid, 256, smem, st>>>(z, window, y, p, OB, halo);
+    return check_launch("aero_istft_fwd(512)");
+}
+
 static int log2_exact(int n) {
     int l = 0;
     while ((1 << l) < n) ++l;
@@ -281,6 +543,7 @@ extern "C" int aero_stft_fwd(const float* x, const float* window, float* z, doub
     AERO_REQUIRE(((p->z_stride_b | p->z_stride_c | p->z_stride_k | p->z_stride_t) & 1) == 0 && ((uintptr_t)z & 7) == 0,
                  "aero_stft_fwd: output strides must keep float2 alignment");
     cudaStream_t st = (cudaStream_t)stream;
+    if (lg == 9 && (size_t)(kF512 - 1) * p->hop * 4 <= 96 * 1024) return launch_stft512(x, window, z, stats, *p, st);
     switch (lg) {
         case 6: return launch_stft<6>(x, window, z, stats, *p, st);
         case 7: return launch_stft<7>(x, window, z, stats, *p, st);
@@ -305,6 +568,11 @@ extern "C" int aero_istft_fwd(const float* z, const float* window, float* y, con
     AERO_REQUIRE(((p->z_stride_b | p->z_stride_c | p->z_stride_k | p->z_stride_t) & 1) == 0 && ((uintptr_t)z & 7) == 0,
                  "aero_istft_fwd: input strides must keep float2 alignment");
     cudaStream_t st = (cudaStream_t)stream;
+    if (lg == 9) {
+        bool taken = false;
+        const int rc = launch_istft512(z, window, y, *p, st, &taken);
+        if (taken || rc != AERO_OK) return rc;
+    }
     switch (lg) {
         case 6: return launch_istft<6>(z, window, y, *p, st);
         case 7: return launch_istft<7>(z, window, y, *p, st);

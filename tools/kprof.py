@@ -64,9 +64,36 @@ def run_lstm(args):
     print(f"{args.shape}: precision {args.precision} rows {rows} best {min(ms)*1e3:.1f} us -> {min(ms)*1e3/steps:.2f} us/step")
 
 
+def run_stft(args):
+    """The model's analysis / synthesis pair at BASELINE shapes: 32 x 8000 -> [32,256,501,2] -> 32 x 32000."""
+    m = Aero(**aero_kwargs("aero_4-16_512_64")).eval().cuda()
+    eng = AeroEngine(m)
+    B, L, T, Fq = args.batch, 8000, 501, 256
+    x = torch.randn(B, L, device="cuda")
+    z = torch.empty(B, Fq, T, 2, device="cuda")
+    y = torch.empty(B, 32000, device="cuda")
+    stats = torch.zeros(B, 2, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    for name, fn, nbytes in (
+            ("stft", lambda: eng.stft_into(x, z, stats, n_fft=512, hop=16, win=128, channels=1, bins_out=Fq, strides=(Fq * T * 2, 2, T * 2, 2)),
+             4 * B * L + 8 * B * Fq * T),
+            ("istft", lambda: eng.istft_into(z, y, n_fft=512, hop=64, win=512, channels=1, frames=T, bins_in=Fq, strides=(Fq * T * 2, 2, T * 2, 2)),
+             8 * B * Fq * T + 4 * B * 32000)):
+        ms = []
+        for i in range(args.iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(e0.elapsed_time(e1))
+        print(f"{name}: B={B} {nbytes/1e6:.1f} MB  best {min(ms)*1e3:.1f} us -> {nbytes/min(ms)/1e6:.1f} GB/s")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48"])
+    ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48", "stft"])
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
@@ -74,6 +101,8 @@ def main():
     torch.manual_seed(0)
     if args.shape.startswith("lstm"):
         return run_lstm(args)
+    if args.shape == "stft":
+        return run_stft(args)
     m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
     eng = AeroEngine(m)
     eng.precision = args.precision
