@@ -312,10 +312,9 @@ constexpr int kTPad = 17;            // padded row of the transpose buffer (floa
 __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ x, const float* __restrict__ window,
                                                       float* __restrict__ z, double* __restrict__ stats,
                                                       const aero_stft_params p) {
-    constexpr int N = 512, M = 256;
+    constexpr int N = 512, M = 256, ZP = 257;                           // ZP: padded frame pitch of Z (bank-conflict-free columns)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* work = reinterpret_cast<float2*>(smem_raw);                 // [16][256]  Z in natural order
-    float2* tbuf = work + kF512 * M;                                    // [16][16][17] pass-1 output; later the store stage [257][16]
+    float2* tbuf = reinterpret_cast<float2*>(smem_raw);                 // [16][16][17] pass-1 output, then Z [16][257] (same memory)
     float2* tw256 = tbuf + kF512 * 16 * kTPad;                          // [256] exp(-2 pi i m / 256)
     float2* twp = tw256 + M;                                            // [129] exp(-2 pi i k / 512)
     float* wpad = reinterpret_cast<float*>(twp + 132);                  // [512]
@@ -349,11 +348,12 @@ __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ 
     float2 v[16];
     if (fr < nfr) {
         // z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n = 16 n1 + n2
-        const float* sf = seg + fr * p.hop;
+        const float2* sf = reinterpret_cast<const float2*>(seg + fr * p.hop);      // hop even (checked by the launcher)
+        const float2* wf = reinterpret_cast<const float2*>(wpad);
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            const int n = 2 * (16 * n1 + c);
-            v[n1] = make_float2(sf[n] * wpad[n], sf[n + 1] * wpad[n + 1]);
+            const float2 xv = sf[16 * n1 + c], wv = wf[16 * n1 + c];
+            v[n1] = make_float2(xv.x * wv.x, xv.y * wv.y);
         }
         dft16<false>(v);
 #pragma unroll
@@ -364,35 +364,40 @@ __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ 
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) v[n2] = tbuf[(fr * 16 + n2) * kTPad + c];
         dft16<false>(v);
+    }
+    __syncthreads();                                  // every thread has its pass-2 inputs in registers: reuse the buffer for Z
+    float2* Z = tbuf;
+    if (fr < nfr) {
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) work[fr * M + c + 16 * k2] = v[k2];
+        for (int k2 = 0; k2 < 16; ++k2) Z[fr * ZP + c + 16 * k2] = v[k2];
     }
     __syncthreads();
 
-    // split post-pass (as in the generic kernel): X[k] = Xe[k] + w^k Xo[k], X[M-k] = conj(Xe[k] - w^k Xo[k]); staged [k][frame]
-    float2* stage = tbuf;
+    // split post-pass fused with the store: X[k] = Xe[k] + w^k Xo[k], X[M-k] = conj(Xe[k] - w^k Xo[k]).
+    // Consecutive lanes take consecutive frames of one bin: each bin row is a contiguous run in memory.
+    float* zs = z + (int64_t)(sig / p.channels) * p.z_stride_b + (int64_t)(sig % p.channels) * p.z_stride_c;
     const float scale = rsqrtf((float)N);
-    for (int i = tid; i < nfr * (M / 2 + 1); i += 256) {
-        const int f2 = i / (M / 2 + 1), k = i - f2 * (M / 2 + 1);
-        const float2 a = work[f2 * M + k];
-        const float2 bq = work[f2 * M + ((M - k) & (M - 1))];
+    float lsum = 0.f, lsq = 0.f;
+    for (int i = tid; i < (M / 2 + 1) * kF512; i += 256) {
+        const int k = i >> 4, f2 = i & 15;
+        if (f2 >= nfr) continue;
+        const float2 a = Z[f2 * ZP + k];
+        const float2 bq = Z[f2 * ZP + ((M - k) & (M - 1))];
         const float2 xe = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
         const float2 d = make_float2(0.5f * (a.x - bq.x), 0.5f * (a.y + bq.y));
         const float2 xo = make_float2(d.y, -d.x);
         const float2 t = cmul(twp[k], xo);
-        stage[k * kF512 + f2] = make_float2(scale * (xe.x + t.x), scale * (xe.y + t.y));
-        stage[(M - k) * kF512 + f2] = make_float2(scale * (xe.x - t.x), -scale * (xe.y - t.y));
-    }
-    __syncthreads();
-
-    float* zs = z + (int64_t)(sig / p.channels) * p.z_stride_b + (int64_t)(sig % p.channels) * p.z_stride_c;
-    float lsum = 0.f, lsq = 0.f;
-    for (int i = tid; i < p.bins_out * nfr; i += 256) {
-        const int k = i / nfr, f2 = i - k * nfr;
-        const float2 o = stage[k * kF512 + f2];
-        *reinterpret_cast<float2*>(zs + (int64_t)k * p.z_stride_k + (int64_t)(t0 + f2) * p.z_stride_t) = o;
-        lsum += o.x + o.y;
-        lsq += o.x * o.x + o.y * o.y;
+        const float2 lo = make_float2(scale * (xe.x + t.x), scale * (xe.y + t.y));
+        const float2 hi = make_float2(scale * (xe.x - t.x), -scale * (xe.y - t.y));
+        float* dst = zs + (int64_t)(t0 + f2) * p.z_stride_t;
+        if (k < p.bins_out) {
+            *reinterpret_cast<float2*>(dst + (int64_t)k * p.z_stride_k) = lo;
+            lsum += lo.x + lo.y; lsq += lo.x * lo.x + lo.y * lo.y;
+        }
+        if (k != M - k && (M - k) < p.bins_out) {
+            *reinterpret_cast<float2*>(dst + (int64_t)(M - k) * p.z_stride_k) = hi;
+            lsum += hi.x + hi.y; lsq += hi.x * hi.x + hi.y * hi.y;
+        }
     }
     if (stats != nullptr) {
         __shared__ double red[2][8];
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ 
 }
 
 static int launch_stft512(const float* x, const float* window, float* z, double* stats, const aero_stft_params& p, cudaStream_t st) {
-    const size_t smem = sizeof(float2) * (kF512 * 256 + (size_t)kF512 * 16 * kTPad + 256 + 132) +
+    const size_t smem = sizeof(float2) * ((size_t)kF512 * 16 * kTPad + 256 + 132) +
                         sizeof(float) * (512 + (size_t)(kF512 - 1) * p.hop + 512);
     cudaFuncSetAttribute(stft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(cdiv(p.frames, kF512), p.n_signals);
@@ -423,8 +428,7 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__
                                                        const int halo) {
     constexpr int N = 512, M = 256, NF = kF512;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* work = reinterpret_cast<float2*>(smem_raw);                 // [16][256] -> real frames [16][512]
-    float2* xsb = work + NF * M;                                        // [16][257] spectra; later reused as the transpose buffer
+    float2* xsb = reinterpret_cast<float2*>(smem_raw);                  // [16][257] spectra -> transpose buffer -> real frames [16][512]
     float2* tw256 = xsb + NF * 16 * kTPad;                              // [256] exp(+2 pi i m / 256)  (xsb region sized for the transpose)
     float2* twp = tw256 + M;                                            // [257] exp(+2 pi i k / 512), k <= 256
     float* wpad = reinterpret_cast<float*>(twp + 260);                  // [512]
@@ -480,6 +484,10 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) v[n2] = tbuf[(fr * 16 + n2) * kTPad + c];
         dft16<true>(v);
+    }
+    __syncthreads();                                                      // pass-2 inputs are in registers: reuse the buffer
+    float2* work = xsb;
+    if (fr < nfr) {
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) work[fr * M + c + 16 * k2] = v[k2];      // = (x[2n], x[2n+1]) * M, n = c + 16 k2
     }
@@ -513,7 +521,7 @@ static int launch_istft512(const float* z, const float* window, float* y, const 
     const int OB = kF512 - halo;
     *taken = OB >= 4;                                     // tiny hops fall back to the generic kernel (32 resident frames)
     if (!*taken) return AERO_OK;
-    const size_t smem = sizeof(float2) * (kF512 * 256 + (size_t)kF512 * 16 * kTPad + 256 + 260) + sizeof(float) * 512;
+    const size_t smem = sizeof(float2) * ((size_t)kF512 * 16 * kTPad + 256 + 260) + sizeof(float) * 512;
     cudaFuncSetAttribute(istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int last_pos = 256 + p.out_len - 1;
     dim3 grid(last_pos / (OB * p.hop) + 1, p.n_signals);
@@ -543,7 +551,7 @@ extern "C" int aero_stft_fwd(const float* x, const float* window, float* z, doub
     AERO_REQUIRE(((p->z_stride_b | p->z_stride_c | p->z_stride_k | p->z_stride_t) & 1) == 0 && ((uintptr_t)z & 7) == 0,
                  "aero_stft_fwd: output strides must keep float2 alignment");
     cudaStream_t st = (cudaStream_t)stream;
-    if (lg == 9 && (size_t)(kF512 - 1) * p->hop * 4 <= 96 * 1024) return launch_stft512(x, window, z, stats, *p, st);
+    if (lg == 9 && p->hop % 2 == 0 && (size_t)(kF512 - 1) * p->hop * 4 <= 96 * 1024) return launch_stft512(x, window, z, stats, *p, st);
     switch (lg) {
         case 6: return launch_stft<6>(x, window, z, stats, *p, st);
         case 7: return launch_stft<7>(x, window, z, stats, *p, st);
