@@ -93,6 +93,7 @@ static int launch_attn(const float* qkvd, float* out, const aero_attn_params& p,
     return check_launch("aero_local_attn_fwd");
 }
 
+int local_attn_mma_launch(const float* qkvd, float* out, const aero_attn_params& p, cudaStream_t st, bool* taken);
 }  // namespace aero
 
 extern "C" int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream) {
@@ -102,6 +103,11 @@ extern "C" int aero_local_attn_fwd(const float* qkvd, float* out, const aero_att
     AERO_REQUIRE(p->ld >= 3 * p->H + p->heads * p->ndecay, "aero_local_attn_fwd: ld=%d too small", p->ld);
     AERO_REQUIRE(p->rows >= 1 && p->rows <= 65535 && p->T >= 1, "aero_local_attn_fwd: rows=%d", p->rows);
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->round_tf32) {            // tensor-core mode: TF32 mma.sync kernel (attention_mma.cu)
+        bool taken = false;
+        const int rc = local_attn_mma_launch(qkvd, out, *p, st, &taken);
+        if (taken || rc != AERO_OK) return rc;
+    }
     switch (p->H / p->heads) {
         case 3: return launch_attn<3>(qkvd, out, *p, st);
         case 6: return launch_attn<6>(qkvd, out, *p, st);

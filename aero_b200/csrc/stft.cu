@@ -423,10 +423,11 @@ static int launch_stft512(const float* x, const float* window, float* z, double*
 }
 
 // inverse: 16 resident frames per CTA, same four-step transform with conjugate twiddles, then overlap-add
-__global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__ z, const float* __restrict__ window,
-                                                       float* __restrict__ y, const aero_istft_params p, const int OB,
-                                                       const int halo) {
-    constexpr int N = 512, M = 256, NF = kF512;
+template <int NF>    // resident frames per CTA (16 threads each)
+__global__ void __launch_bounds__(NF * 16) istft512_kernel(const float* __restrict__ z, const float* __restrict__ window,
+                                                           float* __restrict__ y, const aero_istft_params p, const int OB,
+                                                           const int halo) {
+    constexpr int N = 512, M = 256, NTH = NF * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xsb = reinterpret_cast<float2*>(smem_raw);                  // [16][257] spectra -> transpose buffer -> real frames [16][512]
     float2* tw256 = xsb + NF * 16 * kTPad;                              // [256] exp(+2 pi i m / 256)  (xsb region sized for the transpose)
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__
     const int t_lo = max(0, blk * OB - halo);
     const int t_hi = min(p.frames - 1, blk * OB + OB - 1);
     const int nfr = t_hi - t_lo + 1;
-    {
+    if (tid < 256) {
         float sn, cs;
         sincospif(2.0f * (float)tid / 256.0f, &sn, &cs);
         tw256[tid] = make_float2(cs, sn);
@@ -446,9 +447,9 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__
         if (tid == 0) twp[256] = make_float2(-1.f, 0.f);
     }
     const int wl = (N - p.win) / 2;
-    for (int n = tid; n < N; n += 256) { const int k = n - wl; wpad[n] = (k >= 0 && k < p.win) ? window[k] : 0.0f; }
+    for (int n = tid; n < N; n += NTH) { const int k = n - wl; wpad[n] = (k >= 0 && k < p.win) ? window[k] : 0.0f; }
     const float* zs = z + (int64_t)(sig / p.channels) * p.z_stride_b + (int64_t)(sig % p.channels) * p.z_stride_c;
-    for (int i = tid; i < (M + 1) * nfr; i += 256) {
+    for (int i = tid; i < (M + 1) * nfr; i += NTH) {
         const int k = i / nfr, f2 = i - k * nfr;
         float2 o = make_float2(0.f, 0.f);
         if (k < p.bins_in) o = *reinterpret_cast<const float2*>(zs + (int64_t)k * p.z_stride_k + (int64_t)(t_lo + f2) * p.z_stride_t);
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__
     const float scale = 2.0f * rsqrtf((float)N);
     const int p0 = blk * OB * p.hop, span = OB * p.hop;
     float* ys = y + (int64_t)sig * p.out_len;
-    for (int i = tid; i < span; i += 256) {
+    for (int i = tid; i < span; i += NTH) {
         const int pos = p0 + i;
         const int n_out = pos - N / 2;
         if (n_out < 0 || n_out >= p.out_len) continue;
@@ -517,15 +518,16 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float* __restrict__
 }
 
 static int launch_istft512(const float* z, const float* window, float* y, const aero_istft_params& p, cudaStream_t st, bool* taken) {
+    constexpr int NF = 32;                                // 25 output hops per 32 transformed frames at hop = n_fft/8
     const int halo = 511 / p.hop;
-    const int OB = kF512 - halo;
-    *taken = OB >= 4;                                     // tiny hops fall back to the generic kernel (32 resident frames)
+    const int OB = NF - halo;
+    *taken = OB >= 8;                                     // tiny hops fall back to the generic kernel
     if (!*taken) return AERO_OK;
-    const size_t smem = sizeof(float2) * ((size_t)kF512 * 16 * kTPad + 256 + 260) + sizeof(float) * 512;
-    cudaFuncSetAttribute(istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(float2) * ((size_t)NF * 16 * kTPad + 256 + 260) + sizeof(float) * 512;
+    cudaFuncSetAttribute(istft512_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int last_pos = 256 + p.out_len - 1;
     dim3 grid(last_pos / (OB * p.hop) + 1, p.n_signals);
-    istft512_kernel<<<grid, 256, smem, st>>>(z, window, y, p, OB, halo);
+    istft512_kernel<NF><<<grid, NF * 16, smem, st>>>(z, window, y, p, OB, halo);
     return check_launch("aero_istft_fwd(512)");
 }
 

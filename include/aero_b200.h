@@ -207,7 +207,8 @@ int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh,
  */
 typedef struct {
     int32_t rows, T, H, heads, ndecay, ld;
-    int32_t round_tf32;
+    int32_t round_tf32;               /* 1: tensor-core mode -- QK^T and PV on mma.sync TF32 (fp32 accumulate, head dim 12 / 24),
+                                         outputs rounded to TF32 for the projection GEMM; 0: exact fp32 SIMT kernel */
 } aero_attn_params;
 int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream);
 

@@ -335,3 +335,24 @@ def test_freq_mix_tcgen05_mn_major(engines, B, Fq, T, Cc):
     ref = torch.einsum("gf,bftc->bgtc", wfc.double(), x.double()) * gate[:, None].double()
     assert torch.isfinite(y).all()
     assert rel_l2(y.cpu(), ref) < 5e-6
+
+
+@pytest.mark.parametrize("H,T,rows", [(48, 501, 3), (96, 251, 2), (48, 700, 1), (96, 33, 4), (48, 130, 2)])
+def test_local_attention_tensor_core(engines, H, T, rows):
+    """mma.sync TF32 attention (engine tensor-core mode) against the fp64 statement of modules.py:104-124."""
+    gpu, emu = engines
+    ld = 3 * H + 16
+    qkvd = rnd(rows * T, ld, seed=1)
+    qkvd[:, 3 * H:] = qkvd[:, 3 * H:] * 1.5 - 1.0
+    ref = torch.zeros(rows * T, H)
+    emu._attn(qkvd, ref, rows=rows, T=T, H=H, heads=4, ndecay=4, ld=ld)
+    o = torch.full((rows * T, H), float("nan"), device="cuda")
+    gpu.precision = 1
+    try:
+        gpu._attn(qkvd.cuda(), o, rows=rows, T=T, H=H, heads=4, ndecay=4, ld=ld)
+        torch.cuda.synchronize()
+    finally:
+        gpu.precision = 0
+    err = rel_l2(o.cpu(), ref)
+    print(f"attention mma H={H} T={T}: rel_l2 {err:.2e}")
+    assert torch.isfinite(o).all() and err < 1.5e-3

@@ -64,6 +64,26 @@ def run_lstm(args):
     print(f"{args.shape}: precision {args.precision} rows {rows} best {min(ms)*1e3:.1f} us -> {min(ms)*1e3/steps:.2f} us/step")
 
 
+def run_attn(args):
+    H = 96 if args.shape == "attn96" else 48
+    rows = (4 if H == 96 else 8) * args.batch
+    T = 501
+    m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
+    eng = AeroEngine(m)
+    eng.precision = args.precision
+    ld = 3 * H + 16
+    qkvd = torch.randn(rows * T, ld, device="cuda")
+    out = torch.empty(rows * T, H, device="cuda")
+    ms = []
+    for i in range(args.iters + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng._attn(qkvd, out, rows=rows, T=T, H=H, heads=4, ndecay=4, ld=ld); e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    print(f"{args.shape}: precision {args.precision} rows {rows} best {min(ms)*1e3:.1f} us")
+
+
 def run_stft(args):
     """The model's analysis / synthesis pair at BASELINE shapes: 32 x 8000 -> [32,256,501,2] -> 32 x 32000."""
     m = Aero(**aero_kwargs("aero_4-16_512_64")).eval().cuda()
@@ -93,7 +113,7 @@ def run_stft(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48", "stft"])
+    ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48", "stft", "attn96", "attn48"])
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
@@ -103,6 +123,8 @@ def main():
         return run_lstm(args)
     if args.shape == "stft":
         return run_stft(args)
+    if args.shape.startswith("attn"):
+        return run_attn(args)
     m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
     eng = AeroEngine(m)
     eng.precision = args.precision
