@@ -110,11 +110,14 @@ class AeroEngine:
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
         self._prof, self._prof_tags = None, set()
         self._wk, self._wname = {}, {}
+        self.use_graph = False      # replay the launch sequence from a CUDA graph (per input shape); see forward()
+        self._graphs = {}
 
     # ------------------------------------------------------------------ plumbing
     def invalidate(self):
         self._packed = None
         self._bufs = {}
+        self._graphs = {}
 
     def _device(self):
         return next(self.model.parameters()).device
@@ -563,6 +566,35 @@ class AeroEngine:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, mix, return_spec=False, return_lr_spec=False):
+        """Public entry (behind Aero.forward).  With ``use_graph`` the ~110 launches of one forward are captured once per
+        input shape into a CUDA graph and replayed: identical kernels and results, no per-launch host cost (this is what
+        matters at batch 1, where the eager path is host-bound)."""
+        if not self.use_graph or return_spec or self._prof is not None:
+            return self._forward(mix, return_spec, return_lr_spec)
+        self._require(mix)
+        key = (tuple(mix.shape), tuple(p._version for p in self.model.parameters()), self.precision, self.fp32_tags)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = mix.contiguous().clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                       # allocate workspaces / pack weights / encode tensor maps outside capture
+                    self._forward(static_in, False, False)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward(static_in, False, False)
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(mix)
+        graph.replay()
+        return static_out.clone()
+
+    @torch.no_grad()
+    def _forward(self, mix, return_spec=False, return_lr_spec=False):
         model = self.model
         self._require(mix)
         if model.training:

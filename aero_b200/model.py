@@ -336,6 +336,11 @@ class Aero(nn.Module):
             self._engine_obj.invalidate()
         return out
 
+    def use_cuda_graph(self, enabled=True):
+        """Replay each forward from a CUDA graph captured per input shape (inference; same kernels, same results)."""
+        self._engine().use_graph = bool(enabled)
+        return self
+
     # ------------------------------------------------------------------ public surface
     def _spec(self, x, scale=False):
         """Complex spectrogram ``[..., nfft/2, frames]`` (Nyquist bin dropped), reference

@@ -212,6 +212,15 @@ typedef struct {
 } aero_attn_params;
 int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Log-spectral distance (reference src/metrics.py:37-70 `get_lsd`, STFTMag(2048, 512)).
+ * z_ref, z_est : planar complex spectrograms [B][bins][frames] (float2) as written by aero_stft_fwd (normalized);
+ * out_sum += sum over (b, t) of sqrt(mean_f (log10 max(n_fft|z_ref|^2, 1e-8) - log10 max(n_fft|z_est|^2, 1e-8))^2).
+ * The caller zeroes out_sum and divides by B * frames.
+ */
+int aero_lsd_fwd(const float* z_ref, const float* z_est, double* out_sum, int32_t B, int32_t bins, int32_t frames,
+                 int32_t n_fft, aero_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

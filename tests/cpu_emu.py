@@ -33,6 +33,8 @@ class EmuEngine(AeroEngine):
         self._prof, self._prof_tags = None, set()
         self._wk, self._wname = {}, {}
         self.fp32_tags = ()
+        self.use_graph = False
+        self._graphs = {}
         self.calls = []
 
     def _require(self, x):

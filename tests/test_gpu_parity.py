@@ -95,3 +95,39 @@ def test_forward_tf32_tensor_core_path_within_tolerance(golden_dir, case):
     print(f"{case} [tf32]: rel_l2 wave {err:.3e} spec {rel_l2(zc_r, g['spec_val']):.3e}")
     assert torch.isfinite(out).all()
     assert err < TOL
+
+
+def test_lsd_metric_matches_reference_formula():
+    """reference src/metrics.py:59-70 (with the torch>=2 `return_complex` shim applied to its STFTMag)."""
+    from aero_b200.metrics import get_lsd
+    ref_sig, out_sig = white_noise((3, 32000), seed=11), white_noise((3, 32000), seed=12) * 0.7
+    out_sig[:, :4000] = 0.0                                        # exercise the 1e-8 clamp
+    win = torch.hann_window(2048)
+
+    def mag2(x):
+        return torch.stft(x, 2048, 512, window=win, return_complex=True).abs().square().clamp(1e-8)
+    want = (torch.log10(mag2(ref_sig)) - torch.log10(mag2(out_sig))).square().mean(dim=1).sqrt().mean()
+    got = get_lsd(ref_sig.cuda(), out_sig.cuda())
+    assert abs(float(got) - float(want)) / float(want) < 1e-4
+
+
+def test_enhance_long_on_gpu_equals_serial():
+    from aero_b200.enhance import enhance_long
+    m = build("aero_4-16_512_256").cuda()
+    m._engine().precision = 0
+    sig = white_noise((1, 9000))
+    got = enhance_long(m, sig.cuda(), sr=4000, segment_sec=0.5, max_batch=3)
+    serial = torch.cat([m(sig[None, :, i:i + 2000].cuda())[0] for i in range(0, 9000, 2000)], -1)
+    assert got.shape == serial.shape == (1, 36000) and rel_l2(got.cpu(), serial.cpu()) < 1e-6
+
+
+def test_cuda_graph_replay_matches_eager():
+    m = build("aero_4-16_512_256").cuda()
+    a, b = white_noise((2, 1, 8000)).cuda(), white_noise((2, 1, 8000), seed=5).cuda()
+    ea, eb = m(a).clone(), m(b).clone()
+    m.use_cuda_graph(True)
+    ga = m(a)
+    gb = m(b)
+    ga2 = m(a)
+    assert rel_l2(ga.cpu(), ea.cpu()) < 2e-4 and rel_l2(gb.cpu(), eb.cpu()) < 2e-4 and rel_l2(ga2.cpu(), ea.cpu()) < 2e-4
+    assert not torch.equal(ga, gb)

@@ -68,3 +68,18 @@ def test_train_mode_and_cpu_fail_loudly():
     emulated(m).train()
     with pytest.raises(NotImplementedError, match="eval"):
         m(torch.zeros(1, 1, 4000))
+
+
+def test_enhance_long_equals_serial_chunks():
+    """Batched long-file inference == the reference's chunk-by-chunk loop (predict.py:61-80)."""
+    from aero_b200.enhance import enhance_long, get_estimate
+    m = make("aero_4-16_512_256")
+    sig = white_noise((1, 1, 9000))[0]                     # [C=1, L]; chunks of 0.5 s = 2000 samples -> 4 full + 1000 tail
+    got = enhance_long(m, sig, sr=4000, segment_sec=0.5, max_batch=3)
+    serial = []
+    with torch.no_grad():
+        for i in range(0, 9000, 2000):
+            serial.append(O.aero_forward(m.state_dict(), m.geom, sig[None, :, i:i + 2000])[0])
+    ref = torch.cat(serial, -1)
+    assert got.shape == ref.shape and rel_l2(got, ref) < 2e-5
+    assert torch.equal(get_estimate(m, sig[None, :, :2000]), m(sig[None, :, :2000]))
