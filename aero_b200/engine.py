@@ -541,7 +541,8 @@ class AeroEngine:
             self._norm_act(raw, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fq, T=T, C_=4 * Cc,
                            groups=kw["norm_groups"], scope=1, op=NA_GLU, rnd=True)
         else:
-            self._gemm(y, W[p + ".rw.w"], glu=1, rnd=True, **common)
+            # the last layer's transposed conv runs on the exact-fp32 thin kernel: do not round its input
+            self._gemm(y, W[p + ".rw.w"], glu=1, rnd=not last, **common)
         cout = g.dec_cout
         f_full = (Fq - 1) * g.stride + g.kernel
         f_keep = f_full - 2 * g.pad

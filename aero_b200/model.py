@@ -12,7 +12,7 @@ The module tree below only *holds parameters*; none of the ``nn`` layers'
 ``forward`` methods are used on the product path.  The tree is created in the
 same order as the reference constructor so that, for a given
 ``torch.manual_seed``, parameter values are bit-identical to the reference's
-(verified in ``tests/test_boundary.py``), which is what lets parity tests seed
+(verified in ``tests/test_oracle.py::test_oracle_vs_live_reference_blocks``), which is what lets parity tests seed
 both sides instead of shipping 78 MB of weights.
 """
 from __future__ import annotations
