@@ -607,8 +607,11 @@ class AeroEngine:
         if mix.dim() != 3 or mix.shape[1] != kw["in_channels"]:
             raise ValueError(f"expected input [B, {kw['in_channels']}, L], got {tuple(mix.shape)}")
         W = self._weights()
-        if self._stats is None or self._stats.buf.device != mix.device:
-            self._stats = _Stats(mix.device)
+        B_ = mix.shape[0]
+        need = B_ + sum((2 * B_ * kw["norm_groups"] if lg.norm else 0) * 2 +
+                        (2 * kw["dconv_depth"] * B_ * lg.f_out if lg.dconv else 0) for lg in g.layers) + 64
+        if self._stats is None or self._stats.buf.device != mix.device or self._stats.buf.shape[0] < need:
+            self._stats = _Stats(mix.device, capacity=max(1 << 16, need))
         self._stats.reset()
 
         B, Cin, length = mix.shape
