@@ -45,12 +45,15 @@ __global__ void __launch_bounds__(256) sample_norm_kernel(const float* __restric
 // ------------------------------------------------------------------------- norm_act
 constexpr int kMaxGroups = 8;
 
+// Thread mapping: a thread owns ONE channel quad c (gamma / beta / LayerScale loaded once) and walks over pixels
+// (t, then output rows) with a fixed stride -- no per-element index arithmetic, 16-byte accesses, consecutive lanes on
+// consecutive channel quads of the same pixel (then the next pixel), i.e. fully coalesced.
 template <int OP>
 __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ snake_a, const float* __restrict__ scale,
                                                        const float* __restrict__ residual, float* __restrict__ y,
-                                                       const aero_norm_act_params p, const int64_t seg4) {
+                                                       const aero_norm_act_params p) {
     constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
     const int seg = blockIdx.x;                       // scope 1: b ; scope 2: b*F_in + f
     __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
@@ -66,43 +69,50 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
     __syncthreads();
     const int Cout = GLU ? p.C / 2 : p.C;
     const int c4n = Cout >> 2;
+    const int ppp = 256 / c4n;                        // pixels per pass of the CTA (host guarantees c4n <= 256)
+    const int cq = threadIdx.x % c4n, dp = threadIdx.x / c4n;
+    if (dp >= ppp) return;
+    const int c = cq * 4;
     const int gw = p.C / p.groups;
-    int b, f_fixed;
-    if (p.scope == 1) { b = seg; f_fixed = -1; } else { b = seg / p.F_in; f_fixed = seg % p.F_in; }
+    int b, f_lo, f_hi;                                // output rows handled by this segment
+    if (p.scope == 1) { b = seg; f_lo = 0; f_hi = p.F_out; } else { b = seg / p.F_in; f_lo = seg % p.F_in; f_hi = f_lo + 1; }
 
-    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < seg4; i += (int64_t)gridDim.y * blockDim.x) {
-        const int c = (int)(i % c4n) * 4;
-        const int64_t r = i / c4n;
-        const int t = (int)(r % p.T);
-        const int fl = (p.scope == 1) ? (int)(r / p.T) : f_fixed;      // output row
+    // per-channel constants: y = (x - m) * r * gamma + beta  ==  x * k + o
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    const float m0 = s_mean[c / gw], r0 = s_rstd[c / gw];
+    const float4 k0 = make_float4(r0 * ga.x, r0 * ga.y, r0 * ga.z, r0 * ga.w);
+    const float4 o0 = make_float4(be.x - m0 * k0.x, be.y - m0 * k0.y, be.z - m0 * k0.z, be.w - m0 * k0.w);
+    float4 k1 = k0, o1 = o0, sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (GLU) {
+        const int c2 = c + Cout;
+        const float4 ga2 = *reinterpret_cast<const float4*>(gamma + c2);
+        const float4 be2 = *reinterpret_cast<const float4*>(beta + c2);
+        const float m1 = s_mean[c2 / gw], r1 = s_rstd[c2 / gw];
+        k1 = make_float4(r1 * ga2.x, r1 * ga2.y, r1 * ga2.z, r1 * ga2.w);
+        o1 = make_float4(be2.x - m1 * k1.x, be2.y - m1 * k1.y, be2.z - m1 * k1.z, be2.w - m1 * k1.w);
+        if (OP == AERO_NA_GLU_SCALE_RES) sc = *reinterpret_cast<const float4*>(scale + c);
+    }
+    const bool rnd = p.round_tf32;
+    const int64_t npix = (int64_t)(f_hi - f_lo) * p.T;                       // pixels of this segment (row-major f, t)
+    for (int64_t pix = (int64_t)blockIdx.y * ppp + dp; pix < npix; pix += (int64_t)gridDim.y * ppp) {
+        const int fl = f_lo + (int)(pix / p.T);                              // one division per pixel, not per element
+        const int t = (int)(pix - (int64_t)(fl - f_lo) * p.T);
         const int fin = fl + p.f_off;
         const float* xp = x + (((int64_t)b * p.F_in + fin) * p.T + t) * p.C;
         const int64_t oidx = (((int64_t)b * p.F_out + fl) * p.T + t) * Cout + c;
-
         const float4 v = *reinterpret_cast<const float4*>(xp + c);
-        const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
-        const float4 be = *reinterpret_cast<const float4*>(beta + c);
-        const int g0 = c / gw;
-        const float m0 = s_mean[g0], r0 = s_rstd[g0];
-        float a[4] = {(v.x - m0) * r0 * ga.x + be.x, (v.y - m0) * r0 * ga.y + be.y,
-                      (v.z - m0) * r0 * ga.z + be.z, (v.w - m0) * r0 * ga.w + be.w};
+        float a[4] = {fmaf(v.x, k0.x, o0.x), fmaf(v.y, k0.y, o0.y), fmaf(v.z, k0.z, o0.z), fmaf(v.w, k0.w, o0.w)};
         float o[4];
         if (GLU) {
-            const int c2 = c + Cout;
-            const float4 v2 = *reinterpret_cast<const float4*>(xp + c2);
-            const float4 ga2 = *reinterpret_cast<const float4*>(gamma + c2);
-            const float4 be2 = *reinterpret_cast<const float4*>(beta + c2);
-            const int g1 = c2 / gw;
-            const float m1 = s_mean[g1], r1 = s_rstd[g1];
-            const float gt[4] = {(v2.x - m1) * r1 * ga2.x + be2.x, (v2.y - m1) * r1 * ga2.y + be2.y,
-                                 (v2.z - m1) * r1 * ga2.z + be2.z, (v2.w - m1) * r1 * ga2.w + be2.w};
+            const float4 v2 = *reinterpret_cast<const float4*>(xp + c + Cout);
+            const float gt[4] = {fmaf(v2.x, k1.x, o1.x), fmaf(v2.y, k1.y, o1.y), fmaf(v2.z, k1.z, o1.z), fmaf(v2.w, k1.w, o1.w)};
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = a[u] * sigmoid_f(gt[u]);
             if (OP == AERO_NA_GLU_SCALE_RES) {
-                const float4 sc = *reinterpret_cast<const float4*>(scale + c);
                 const float4 rs = *reinterpret_cast<const float4*>(residual + oidx);
-                o[0] = rs.x + sc.x * o[0]; o[1] = rs.y + sc.y * o[1];
-                o[2] = rs.z + sc.z * o[2]; o[3] = rs.w + sc.w * o[3];
+                o[0] = fmaf(sc.x, o[0], rs.x); o[1] = fmaf(sc.y, o[1], rs.y);
+                o[2] = fmaf(sc.z, o[2], rs.z); o[3] = fmaf(sc.w, o[3], rs.w);
             }
         } else if (OP == AERO_NA_GELU) {
 #pragma unroll
@@ -112,14 +122,14 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
             const float ia = 1.0f / al;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float s = sinf(a[u] * al);
-                o[u] = a[u] + ia * s * s;
+                const float sn = sinf(a[u] * al);
+                o[u] = a[u] + ia * sn * sn;
             }
         } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = a[u];
         }
-        if (p.round_tf32) {
+        if (rnd) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = round_tf32_rna(o[u]);
         }
@@ -157,14 +167,17 @@ extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const floa
     AERO_REQUIRE(p->op != AERO_NA_SNAKE || snake_a, "aero_norm_act_fwd: snake needs a[]");
     AERO_REQUIRE(p->op != AERO_NA_GLU_SCALE_RES || (scale && residual), "aero_norm_act_fwd: missing scale/residual");
     const int Cout = glu ? p->C / 2 : p->C;
-    const int64_t seg4 = (p->scope == 1 ? (int64_t)p->F_out * p->T : (int64_t)p->T) * (Cout / 4);
+    AERO_REQUIRE(Cout / 4 <= 256, "aero_norm_act_fwd: at most 1024 output channels (got %d)", Cout);
+    const int ppp = 256 / (Cout / 4);
+    const int64_t npix = (p->scope == 1 ? (int64_t)p->F_out * p->T : (int64_t)p->T);
     const int nseg = p->scope == 1 ? p->B : p->B * p->F_in;
-    int chunks = (int)((seg4 + 256 * 4 - 1) / (256 * 4));
+    // ~8 pixels per thread; keep at least a few CTAs per SM in flight across all segments
+    int chunks = (int)((npix + (int64_t)ppp * 8 - 1) / ((int64_t)ppp * 8));
     if (chunks < 1) chunks = 1;
     if (chunks > 65535) chunks = 65535;
     dim3 grid(nseg, chunks);
     cudaStream_t st = (cudaStream_t)stream;
-#define AERO_NA_LAUNCH(OP) norm_act_kernel<OP><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, residual, y, *p, seg4)
+#define AERO_NA_LAUNCH(OP) norm_act_kernel<OP><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, residual, y, *p)
     switch (p->op) {
         case AERO_NA_NONE: AERO_NA_LAUNCH(AERO_NA_NONE); break;
         case AERO_NA_GELU: AERO_NA_LAUNCH(AERO_NA_GELU); break;

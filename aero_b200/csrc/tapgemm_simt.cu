@@ -293,28 +293,38 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
     }
 }
 
-// thin-K (K <= 4, single tap: pre_conv 2->48): one thread per (pixel, 4 output columns), 16-byte stores.
+// thin-K (K <= 4, single tap: pre_conv 2->48): a thread owns one quad of output columns (its weights and bias stay in
+// registers) and walks over pixels; consecutive lanes = consecutive column quads of one pixel -> 16-byte coalesced stores.
 __global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g) {
     const aero_tapgemm_params& p = g.p;
     const int K = p.C1;
     const int n4 = p.N >> 2;
-    const int64_t total = (int64_t)p.B * p.F_out * p.T * n4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i % n4) * 4;
-        const int64_t pix = i / n4;
+    const int ppp = 256 / n4;                             // pixels per pass (host guarantees n4 <= 256)
+    const int nq = threadIdx.x % n4, dp = threadIdx.x / n4;
+    if (dp >= ppp) return;
+    const int n = nq * 4;
+    float4 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = k < K ? *reinterpret_cast<const float4*>(g.w + (int64_t)k * g.ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bias = g.bias ? *reinterpret_cast<const float4*>(g.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool rnd = p.flags & 1;
+    const int64_t npix = (int64_t)p.B * p.F_out * p.T;
+    for (int64_t pix = (int64_t)blockIdx.x * ppp + dp; pix < npix; pix += (int64_t)gridDim.x * ppp) {
         const int t = (int)(pix % p.T);
         const int64_t rowi = pix / p.T;
         const int fo = (int)(rowi % p.F_out), b = (int)(rowi / p.F_out);
         const float* a = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fo * p.a1_sf + (int64_t)t * p.a1_st;
-        float4 acc = g.bias ? *reinterpret_cast<const float4*>(g.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < K; ++k) {
-            const float av = a[k];
-            const float4 w = *reinterpret_cast<const float4*>(g.w + (int64_t)k * g.ldw + n);
-            acc.x = fmaf(av, w.x, acc.x); acc.y = fmaf(av, w.y, acc.y); acc.z = fmaf(av, w.z, acc.z); acc.w = fmaf(av, w.w, acc.w);
+        float4 acc = bias;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < K) {
+                const float av = a[k];
+                acc.x = fmaf(av, w[k].x, acc.x); acc.y = fmaf(av, w[k].y, acc.y); acc.z = fmaf(av, w[k].z, acc.z); acc.w = fmaf(av, w[k].w, acc.w);
+            }
         }
         if (p.act == AERO_ACT_GELU) { acc.x = gelu_exact(acc.x); acc.y = gelu_exact(acc.y); acc.z = gelu_exact(acc.z); acc.w = gelu_exact(acc.w); }
         else if (p.act == AERO_ACT_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-        if (p.flags & 1) { acc.x = round_tf32_rna(acc.x); acc.y = round_tf32_rna(acc.y); acc.z = round_tf32_rna(acc.z); acc.w = round_tf32_rna(acc.w); }
+        if (rnd) { acc.x = round_tf32_rna(acc.x); acc.y = round_tf32_rna(acc.y); acc.z = round_tf32_rna(acc.z); acc.w = round_tf32_rna(acc.w); }
         *reinterpret_cast<float4*>(g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n) = acc;
     }
 }
@@ -405,10 +415,12 @@ int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
         return check_launch("aero_tapgemm_fwd(thin-n)");
     }
     if (plain && p.mode == AERO_TAPS_CONV && p.kf == 1 && p.kt == 1 && p.stride_f == 1 && p.pad_f == 0 && p.C2 == 0 && p.C1 <= 4 &&
-        p.N % 4 == 0 && g.vec_o && !g.residual && !g.samp_affine && p.F_in == p.F_out) {
-        const int64_t total = (int64_t)p.B * p.F_out * p.T * (p.N / 4);
-        int blocks = (int)((total + 255) / 256);
+        p.N % 4 == 0 && p.N <= 1024 && g.vec_o && !g.residual && !g.samp_affine && p.F_in == p.F_out) {
+        const int ppp = 256 / (p.N / 4);
+        const int64_t npix = (int64_t)p.B * p.F_out * p.T;
+        int blocks = (int)((npix + (int64_t)ppp * 8 - 1) / ((int64_t)ppp * 8));
         if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks < 1) blocks = 1;
         tapgemm_thin_k_kernel<<<blocks, 256, 0, st>>>(a);
         return check_launch("aero_tapgemm_fwd(thin-k)");
     }
