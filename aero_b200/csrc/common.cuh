@@ -24,10 +24,11 @@ __device__ __forceinline__ float gelu_exact(float x) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Round to TF32 (10-bit mantissa), nearest with ties away from zero -- the result of cvt.rna.tf32.f32 for every finite input,
+// in two integer instructions (ptxas expands the cvt into ~5 with Inf/NaN special-casing; Inf and NaN also survive this form:
+// their low 13 mantissa bits are simply cleared).  Matches aero_b200.engine.tf32_round on the host bit for bit.
 __device__ __forceinline__ float round_tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

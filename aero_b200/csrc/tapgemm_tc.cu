@@ -91,8 +91,8 @@ __device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, 
 // staging tile.  Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
 // (residual loads and stores are whole 32-byte sectors of one row), adds the row-wise terms, rounds, accumulates statistics.
 template <int AMODE>
-__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], float (*stg)[20], int lane, const float* __restrict__ bias,
-                                                 int nb, int N) {
+__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], uint32_t stg_row, const float* __restrict__ bias,
+                                                 int nb, int N) {    // stg_row: shared-space address of this lane's staging row
     const bool full = nb + 16 <= N;
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -113,10 +113,9 @@ __device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], float 
             else if (AMODE == 2) v[u] = fmaxf(v[u], 0.f);
         }
         if (AMODE == 3) {
-            stg[lane][j / 2] = v[0] * sigmoid_f(v[1]);
-            stg[lane][j / 2 + 1] = v[2] * sigmoid_f(v[3]);
+            sts64(stg_row + (j / 2) * 4, v[0] * sigmoid_f(v[1]), v[2] * sigmoid_f(v[3]));
         } else {
-            *reinterpret_cast<float4*>(&stg[lane][j]) = make_float4(v[0], v[1], v[2], v[3]);
+            sts128(stg_row + j * 4, make_float4(v[0], v[1], v[2], v[3]));
         }
     }
 }
@@ -128,7 +127,7 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
     constexpr int CNT = (AMODE == 3) ? 8 : 16;          // staged output columns per 16 accumulator columns
     constexpr int LPR = CNT / 4;                         // lanes per row (one float4 each)
     constexpr int RPI = 32 / LPR;                        // rows per pass
-    float (*stg)[20] = sh->stage[ew];
+    const uint32_t stg = smem_u32(&sh->stage[ew][0][0]);       // [32][20] floats, addressed in the shared window
     const bool rnd = p.flags & 1;
     float sa = 1.f, sb = 0.f;
     if (g.samp_affine) { sa = g.samp_affine[2 * tc.b]; sb = g.samp_affine[2 * tc.b + 1]; }
@@ -149,27 +148,30 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = 0u;
         }
-        epilogue_stage_a<AMODE>(r, stg, lane, g.bias, nb, p.N);
+        epilogue_stage_a<AMODE>(r, stg + (uint32_t)lane * 80u, g.bias, nb, p.N);
         __syncwarp();
         const int no0 = (AMODE == 3) ? nb >> 1 : nb;
         const int nn = no0 + 4 * cq;
         float ls = 0.f, lq = 0.f;
         if (nn < Nout) {                                 // Nout % 4 == 0 (vec_o)
             float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (adp) ad = *reinterpret_cast<const float4*>(adp + nn);
+            const bool has_ad = adp != nullptr, affine = g.samp_affine != nullptr;
+            if (has_ad) ad = *reinterpret_cast<const float4*>(adp + nn);
+            uint32_t sp = stg + (uint32_t)(ro * 80 + cq * 16);
             float* op = obase + (int64_t)ro * p.o_st + nn;
             const float* rp = RES ? rbase + (int64_t)ro * p.r_st + nn : nullptr;
             const int64_t ostep = (int64_t)RPI * p.o_st, rstep = (int64_t)RPI * p.r_st;
 #pragma unroll 2
             for (int rr = ro; rr < rows; rr += RPI) {
-                float4 x = *reinterpret_cast<const float4*>(&stg[rr][4 * cq]);
-                x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+                float4 x = lds128(sp);
+                sp += RPI * 80;
+                if (has_ad) { x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w; }
                 if (RES) {
                     const float4 rs = *reinterpret_cast<const float4*>(rp);
                     x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
                     rp += rstep;
                 }
-                x.x = fmaf(x.x, sa, sb); x.y = fmaf(x.y, sa, sb); x.z = fmaf(x.z, sa, sb); x.w = fmaf(x.w, sa, sb);
+                if (affine) { x.x = fmaf(x.x, sa, sb); x.y = fmaf(x.y, sa, sb); x.z = fmaf(x.z, sa, sb); x.w = fmaf(x.w, sa, sb); }
                 if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
                 if (STATS) {
                     ls += (x.x + x.y) + (x.z + x.w);
