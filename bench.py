@@ -39,8 +39,8 @@ GFLOP_PER_CLIP = 124.16          # reference-equivalent; 102.9 wi
 GFLOP_PER_CLIP_REQUIRED = 102.9
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the family (decoder.0 rewrite, B=32) from the
 # `ncu --set full` capture summarised in profiles/ (algorithmic bytes of that launch: 514 MB); None until captured
-TRAFFIC_NCU = {"kernel": "tapgemm_tc_kernel decoder.0.rw B=32", "bytes_per_launch": 966.3e6, "algorithmic_bytes": 514.0e6,
-               "source": "profiles/r1_dec0rw_tc_ncu.md"}
+TRAFFIC_NCU = {"kernel": "tapgemm_tc_kernel<0,0,1> decoder.0.rw B=32", "bytes_per_launch": 473.8e6, "algorithmic_bytes": 513.7e6,
+               "tensor_pipe_pct": 80.8, "source": "profiles/r1_dec0rw_tc_ncu.md"}
 
 
 def peaks():

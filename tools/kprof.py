@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-stats", action="store_true")
     args = ap.parse_args()
     torch.manual_seed(0)
     if args.shape.startswith("lstm"):
@@ -129,6 +130,8 @@ def main():
     eng = AeroEngine(m)
     eng.precision = args.precision
     cfg = dict(SHAPES[args.shape])
+    if args.no_stats:
+        cfg.pop("stats_mode", None); cfg.pop("groups", None)
     B = args.batch
     Tt = cfg.pop("T", T)
     F_out, N, C1 = cfg.pop("F_out"), cfg.pop("N"), cfg.pop("C1")
