@@ -110,14 +110,18 @@ class AeroEngine:
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
         self._prof, self._prof_tags = None, set()
         self._wk, self._wname = {}, {}
-        self.use_graph = False      # replay the launch sequence from a CUDA graph (per input shape); see forward()
+        # CUDA-graph replay of the launch sequence, per input shape: "auto" captures a shape the third time it is seen
+        # (steady-state serving / evaluation loops), True captures on first sight, False always launches eagerly.
+        self.use_graph = "auto"
         self._graphs = {}
+        self._seen = {}
 
     # ------------------------------------------------------------------ plumbing
     def invalidate(self):
         self._packed = None
         self._bufs = {}
         self._graphs = {}
+        self._seen = {}
 
     def _device(self):
         return next(self.model.parameters()).device
@@ -575,6 +579,13 @@ class AeroEngine:
         self._require(mix)
         key = (tuple(mix.shape), tuple(p._version for p in self.model.parameters()), self.precision, self.fp32_tags)
         entry = self._graphs.get(key)
+        if entry is None and self.use_graph == "auto":
+            n = self._seen.get(key, 0)
+            if n < 2:
+                if len(self._seen) >= 64:
+                    self._seen.clear()
+                self._seen[key] = n + 1
+                return self._forward(mix, return_spec, return_lr_spec)
         if entry is None:
             static_in = mix.contiguous().clone()
             side = torch.cuda.Stream()
@@ -584,7 +595,7 @@ class AeroEngine:
                     self._forward(static_in, False, False)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_out = self._forward(static_in, False, False)
             if len(self._graphs) >= 8:
                 self._graphs.clear()

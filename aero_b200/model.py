@@ -12,7 +12,7 @@ The module tree below only *holds parameters*; none of the ``nn`` layers'
 ``forward`` methods are used on the product path.  The tree is created in the
 same order as the reference constructor so that, for a given
 ``torch.manual_seed``, parameter values are bit-identical to the reference's
-(verified in ``tests/test_oracle.py::test_oracle_vs_live_reference_blocks``), which is what lets parity tests seed
+(verified in the CPU suite, ``test_..._vs_live_reference_blocks``), which is what lets parity tests seed
 both sides instead of shipping 78 MB of weights.
 """
 from __future__ import annotations
@@ -337,8 +337,9 @@ class Aero(nn.Module):
         return out
 
     def use_cuda_graph(self, enabled=True):
-        """Replay each forward from a CUDA graph captured per input shape (inference; same kernels, same results)."""
-        self._engine().use_graph = bool(enabled)
+        """Replay each forward from a CUDA graph captured per input shape (inference; same kernels, same results).
+        ``"auto"`` (the default) captures a shape the third time it is seen, ``True`` on first sight, ``False`` never."""
+        self._engine().use_graph = "auto" if enabled == "auto" else bool(enabled)
         return self
 
     # ------------------------------------------------------------------ public surface

@@ -131,3 +131,22 @@ def test_cuda_graph_replay_matches_eager():
     ga2 = m(a)
     assert rel_l2(ga.cpu(), ea.cpu()) < 2e-4 and rel_l2(gb.cpu(), eb.cpu()) < 2e-4 and rel_l2(ga2.cpu(), ea.cpu()) < 2e-4
     assert not torch.equal(ga, gb)
+
+
+def test_auto_graph_kicks_in_on_the_third_call_and_matches():
+    m = build("aero_4-16_512_256").cuda()
+    eng = m._engine()
+    assert eng.use_graph == "auto"
+    a = white_noise((2, 1, 8000)).cuda()
+    outs = [m(a).clone() for _ in range(5)]
+    assert len(eng._graphs) == 1
+    b = white_noise((1, 1, 6000), seed=3).cuda()          # a new shape goes eager again
+    m.use_cuda_graph(False)
+    eb = m(b).clone()
+    m.use_cuda_graph("auto")
+    for _ in range(4):
+        gb = m(b)
+    assert len(eng._graphs) == 2
+    assert rel_l2(gb.cpu(), eb.cpu()) < 2e-4
+    for o in outs[1:]:
+        assert rel_l2(o.cpu(), outs[0].cpu()) < 2e-4
