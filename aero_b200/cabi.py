@@ -42,20 +42,22 @@ class TapGemmParams(C.Structure):
 
 class NormActParams(C.Structure):
     _fields_ = [("B", i32), ("F_in", i32), ("F_out", i32), ("f_off", i32), ("T", i32), ("C", i32),
-                ("groups", i32), ("scope", i32), ("op", i32), ("eps", f32), ("round_tf32", i32)]
+                ("groups", i32), ("scope", i32), ("op", i32), ("eps", f32), ("flags", i32)]
 
 
 class LstmParams(C.Structure):
     _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("n_win", i32), ("steps", i32), ("win_stride", i32),
-                ("in_windowed", i32), ("out_windowed", i32), ("round_tf32", i32), ("precision", i32)]
+                ("in_windowed", i32), ("out_windowed", i32), ("flags", i32), ("precision", i32)]
 
 
 class AttnParams(C.Structure):
-    _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32), ("round_tf32", i32)]
+    _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32), ("flags", i32)]
 
 
+ABI_VERSION = 2
 TAPS_CONV, TAPS_CONVT, TAPS_MIX = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+TG_ROUND_TF32, TG_A_F16, TG_OUT_F16 = 1, 2, 4      # storage-type flags (AERO_TG_*)
 NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES = 0, 1, 2, 3, 4
 
 # every symbol include/aero_b200.h declares (tests/test_cabi.py checks the library exports them all)
@@ -100,6 +102,9 @@ def load(path=None):
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
+    if lib.aero_abi_version() != ABI_VERSION:
+        raise AeroLibraryError(f"{path} has ABI version {lib.aero_abi_version()}, this package needs {ABI_VERSION}: "
+                               "rebuild with `python -m aero_b200.build`")
     _lib = lib
     return lib
 

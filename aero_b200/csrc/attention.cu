@@ -8,8 +8,8 @@ namespace aero {
 constexpr int kQB = 128;     // queries per CTA (one per thread)
 constexpr int kKT = 256;     // keys per shared-memory tile
 
-template <int D>
-__global__ void __launch_bounds__(kQB) local_attn_kernel(const float* __restrict__ qkvd, float* __restrict__ out,
+template <int D, typename TO>
+__global__ void __launch_bounds__(kQB) local_attn_kernel(const float* __restrict__ qkvd, TO* __restrict__ out,
                                                          const aero_attn_params p) {
     __shared__ __align__(16) float Ks[kKT * D];
     __shared__ __align__(16) float Vs[kKT * D];
@@ -80,30 +80,32 @@ __global__ void __launch_bounds__(kQB) local_attn_kernel(const float* __restrict
     }
     if (valid) {
         const float il = 1.0f / l;
-        float* o = out + ((int64_t)row * p.T + s) * p.H + h * D;
+        TO* o = out + ((int64_t)row * p.T + s) * p.H + h * D;
+        const bool rnd = (p.flags & AERO_TG_ROUND_TF32) && sizeof(TO) == 4;
 #pragma unroll
-        for (int c = 0; c < D; ++c) o[c] = p.round_tf32 ? round_tf32_rna(acc[c] * il) : acc[c] * il;
+        for (int c = 0; c < D; ++c) stf(o + c, rnd ? round_tf32_rna(acc[c] * il) : acc[c] * il);
     }
 }
 
 template <int D>
-static int launch_attn(const float* qkvd, float* out, const aero_attn_params& p, cudaStream_t st) {
+static int launch_attn(const float* qkvd, void* out, const aero_attn_params& p, cudaStream_t st) {
     dim3 grid(cdiv(p.T, kQB), p.heads, p.rows);
-    local_attn_kernel<D><<<grid, kQB, 0, st>>>(qkvd, out, p);
+    if (p.flags & AERO_TG_OUT_F16) local_attn_kernel<D, __half><<<grid, kQB, 0, st>>>(qkvd, static_cast<__half*>(out), p);
+    else local_attn_kernel<D, float><<<grid, kQB, 0, st>>>(qkvd, static_cast<float*>(out), p);
     return check_launch("aero_local_attn_fwd");
 }
 
-int local_attn_mma_launch(const float* qkvd, float* out, const aero_attn_params& p, cudaStream_t st, bool* taken);
+int local_attn_mma_launch(const float* qkvd, void* out, const aero_attn_params& p, cudaStream_t st, bool* taken);
 }  // namespace aero
 
-extern "C" int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream) {
+extern "C" int aero_local_attn_fwd(const float* qkvd, void* out, const aero_attn_params* p, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(qkvd && out && p, "aero_local_attn_fwd: null argument");
     AERO_REQUIRE(p->heads >= 1 && p->H % p->heads == 0 && p->ndecay >= 1 && p->ndecay <= 16, "aero_local_attn_fwd: heads/ndecay");
     AERO_REQUIRE(p->ld >= 3 * p->H + p->heads * p->ndecay, "aero_local_attn_fwd: ld=%d too small", p->ld);
     AERO_REQUIRE(p->rows >= 1 && p->rows <= 65535 && p->T >= 1, "aero_local_attn_fwd: rows=%d", p->rows);
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->round_tf32) {            // tensor-core mode: TF32 mma.sync kernel (attention_mma.cu)
+    if (p->flags & AERO_TG_ROUND_TF32) {            // tensor-core mode: TF32 mma.sync kernel (attention_mma.cu)
         bool taken = false;
         const int rc = local_attn_mma_launch(qkvd, out, *p, st, &taken);
         if (taken || rc != AERO_OK) return rc;

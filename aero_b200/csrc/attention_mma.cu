@@ -1,5 +1,5 @@
 // LocalState attention core on the warp-level tensor path (mma.sync m16n8k8 TF32, fp32 accumulate), FA2-style.
-// Used when aero_attn_params.round_tf32 is set (the engine's tensor-core mode); attention.cu is the exact-fp32 twin.
+// Used when aero_attn_params.flags has AERO_TG_ROUND_TF32 (the engine's tensor-core mode); attention.cu is the exact-fp32 twin.
 //
 // One CTA = one (row, head) and 64 queries (4 warps x 16).  K and V of that (row, head) stream through shared memory in
 // tiles of 128 keys, rounded to TF32 once while staging.  Per block of 8 keys a warp issues
@@ -33,8 +33,8 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
-template <int D>   // head dim: 12 or 24
-__global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __restrict__ qkvd, float* __restrict__ out,
+template <int D, typename TO>   // head dim: 12 or 24
+__global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __restrict__ qkvd, TO* __restrict__ out,
                                                              const aero_attn_params p) {
     constexpr int DP = (D + 7) / 8 * 8;                  // 16 or 24
     constexpr int KS = DP / 8;                           // k-steps of QK^T == n-tiles of PV
@@ -166,26 +166,31 @@ __global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __rest
         const int c = nt * 8 + 2 * tig;
         if (c < D) {
             if (s_lo < p.T) {
-                float* op = out + ((int64_t)row * p.T + s_lo) * p.H + h * D + c;
-                op[0] = round_tf32_rna(o[nt][0] * il_lo);
-                if (c + 1 < D) op[1] = round_tf32_rna(o[nt][1] * il_lo);
+                TO* op = out + ((int64_t)row * p.T + s_lo) * p.H + h * D + c;
+                stf(op, round_tf32_rna(o[nt][0] * il_lo));
+                if (c + 1 < D) stf(op + 1, round_tf32_rna(o[nt][1] * il_lo));
             }
             if (s_hi < p.T) {
-                float* op = out + ((int64_t)row * p.T + s_hi) * p.H + h * D + c;
-                op[0] = round_tf32_rna(o[nt][2] * il_hi);
-                if (c + 1 < D) op[1] = round_tf32_rna(o[nt][3] * il_hi);
+                TO* op = out + ((int64_t)row * p.T + s_hi) * p.H + h * D + c;
+                stf(op, round_tf32_rna(o[nt][2] * il_hi));
+                if (c + 1 < D) stf(op + 1, round_tf32_rna(o[nt][3] * il_hi));
             }
         }
     }
 }
 
-int local_attn_mma_launch(const float* qkvd, float* out, const aero_attn_params& p, cudaStream_t st, bool* taken) {
+int local_attn_mma_launch(const float* qkvd, void* out, const aero_attn_params& p, cudaStream_t st, bool* taken) {
     const int d = p.H / p.heads;
     *taken = (d == 12 || d == 24);
     if (!*taken) return AERO_OK;
     dim3 grid(cdiv(p.T, kAQ), p.heads, p.rows);
-    if (d == 12) local_attn_mma_kernel<12><<<grid, 128, 0, st>>>(qkvd, out, p);
-    else local_attn_mma_kernel<24><<<grid, 128, 0, st>>>(qkvd, out, p);
+    if (p.flags & AERO_TG_OUT_F16) {
+        if (d == 12) local_attn_mma_kernel<12, __half><<<grid, 128, 0, st>>>(qkvd, static_cast<__half*>(out), p);
+        else local_attn_mma_kernel<24, __half><<<grid, 128, 0, st>>>(qkvd, static_cast<__half*>(out), p);
+    } else {
+        if (d == 12) local_attn_mma_kernel<12, float><<<grid, 128, 0, st>>>(qkvd, static_cast<float*>(out), p);
+        else local_attn_mma_kernel<24, float><<<grid, 128, 0, st>>>(qkvd, static_cast<float*>(out), p);
+    }
     return check_launch("aero_local_attn_fwd(mma)");
 }
 

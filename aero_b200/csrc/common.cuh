@@ -1,6 +1,7 @@
 // Shared helpers for libaero_b200 (sm_100a).  No torch / ATen types anywhere in csrc/.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -30,6 +31,33 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 __device__ __forceinline__ float round_tf32_rna(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+
+// ---- activation storage types.  Tensors that feed a tensor-core GEMM are stored either as fp32 rounded to TF32 or as
+// FP16 (same 10-bit mantissa, half the bytes, twice the tensor-core rate); arithmetic between loads and stores is fp32.
+// FP16 stores saturate to +-65504 instead of producing Inf.
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __half* p) {            // 8-byte aligned
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__half* p, float4 v) {           // 8-byte aligned
+    const __half2 a = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+    const __half2 b = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+// value as it will be read back from storage of type T (statistics must see the stored value)
+__device__ __forceinline__ float stored(float v, const float*) { return v; }
+__device__ __forceinline__ float stored(float v, const __half*) { return __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f))); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

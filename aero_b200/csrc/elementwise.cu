@@ -48,11 +48,11 @@ constexpr int kMaxGroups = 8;
 // Thread mapping: a thread owns ONE channel quad c (gamma / beta / LayerScale loaded once) and walks over pixels
 // (t, then output rows) with a fixed stride -- no per-element index arithmetic, 16-byte accesses, consecutive lanes on
 // consecutive channel quads of the same pixel (then the next pixel), i.e. fully coalesced.
-template <int OP>
+template <int OP, typename TO>
 __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ snake_a, const float* __restrict__ scale,
-                                                       const float* __restrict__ residual, float* __restrict__ y,
+                                                       const TO* residual, TO* y,
                                                        const aero_norm_act_params p) {
     constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
     const int seg = blockIdx.x;                       // scope 1: b ; scope 2: b*F_in + f
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
         o1 = make_float4(be2.x - m1 * k1.x, be2.y - m1 * k1.y, be2.z - m1 * k1.z, be2.w - m1 * k1.w);
         if (OP == AERO_NA_GLU_SCALE_RES) sc = *reinterpret_cast<const float4*>(scale + c);
     }
-    const bool rnd = p.round_tf32;
+    const bool rnd = (p.flags & AERO_TG_ROUND_TF32) && sizeof(TO) == 4;
     const int64_t npix = (int64_t)(f_hi - f_lo) * p.T;                       // pixels of this segment (row-major f, t)
     for (int64_t pix = (int64_t)blockIdx.y * ppp + dp; pix < npix; pix += (int64_t)gridDim.y * ppp) {
         const int fl = f_lo + (int)(pix / p.T);                              // one division per pixel, not per element
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = a[u] * sigmoid_f(gt[u]);
             if (OP == AERO_NA_GLU_SCALE_RES) {
-                const float4 rs = *reinterpret_cast<const float4*>(residual + oidx);
+                const float4 rs = ld4(residual + oidx);
                 o[0] = fmaf(sc.x, o[0], rs.x); o[1] = fmaf(sc.y, o[1], rs.y);
                 o[2] = fmaf(sc.z, o[2], rs.z); o[3] = fmaf(sc.w, o[3], rs.w);
             }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = round_tf32_rna(o[u]);
         }
-        *reinterpret_cast<float4*>(y + oidx) = make_float4(o[0], o[1], o[2], o[3]);
+        st4(y + oidx, make_float4(o[0], o[1], o[2], o[3]));
     }
 }
 
@@ -152,7 +152,7 @@ extern "C" int aero_sample_norm_fwd(const float* x, const double* stats, float* 
 }
 
 extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
-                                 const float* snake_a, const float* scale, const float* residual, float* y,
+                                 const float* snake_a, const float* scale, const void* residual, void* y,
                                  const aero_norm_act_params* p, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(x && stats && gamma && beta && y && p, "aero_norm_act_fwd: null argument");
@@ -177,7 +177,10 @@ extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const floa
     if (chunks > 65535) chunks = 65535;
     dim3 grid(nseg, chunks);
     cudaStream_t st = (cudaStream_t)stream;
-#define AERO_NA_LAUNCH(OP) norm_act_kernel<OP><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, residual, y, *p)
+    const bool o16 = p->flags & AERO_TG_OUT_F16;
+#define AERO_NA_LAUNCH(OP)                                                                                                  \
+    if (o16) norm_act_kernel<OP, __half><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, (const __half*)residual, (__half*)y, *p); \
+    else norm_act_kernel<OP, float><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, (const float*)residual, (float*)y, *p)
     switch (p->op) {
         case AERO_NA_NONE: AERO_NA_LAUNCH(AERO_NA_NONE); break;
         case AERO_NA_GELU: AERO_NA_LAUNCH(AERO_NA_GELU); break;

@@ -10,9 +10,9 @@
 
 namespace aero {
 
-template <int H, int NT>
+template <int H, int NT, typename TO>
 __global__ void __launch_bounds__(4 * H) lstm_rec_kernel(const float* __restrict__ gin, const float* __restrict__ bias_pad,
-                                                         const float* __restrict__ whh, float* __restrict__ hout,
+                                                         const float* __restrict__ whh, TO* __restrict__ hout,
                                                          const aero_lstm_params p) {
     constexpr int G = 4 * H;
     constexpr int Q = (NT * H) / G;                    // cell items per thread = NT/4
@@ -104,16 +104,16 @@ __global__ void __launch_bounds__(4 * H) lstm_rec_kernel(const float* __restrict
             c_state[q] = c;
             const float h = og * tanhf(c);
             hs[j * NT + n] = h;
-            const float hw = p.round_tf32 ? round_tf32_rna(h) : h;
+            const float hw = ((p.flags & AERO_TG_ROUND_TF32) && sizeof(TO) == 4) ? round_tf32_rna(h) : h;
             if (seq_ok[q]) {
                 if (p.out_windowed) {
-                    hout[out_base[q] + (int64_t)pos * 2 * H + dir * H + j] = hw;
+                    stf(hout + out_base[q] + (int64_t)pos * 2 * H + dir * H + j, hw);
                 } else {
                     const int frame = seq_k[q] * p.win_stride + pos;
                     const int lo = (seq_k[q] == 0) ? 0 : half;
                     const int hi = (seq_k[q] == p.n_win - 1) ? p.steps : p.steps - half;
                     if (pos >= lo && pos < hi && frame < p.T)
-                        hout[out_base[q] + (int64_t)frame * 2 * H + dir * H + j] = hw;
+                        stf(hout + out_base[q] + (int64_t)frame * 2 * H + dir * H + j, hw);
                 }
             }
         }
@@ -122,21 +122,26 @@ __global__ void __launch_bounds__(4 * H) lstm_rec_kernel(const float* __restrict
 }
 
 template <int H, int NT>
-static int launch_lstm(const float* gin, const float* bias_pad, const float* whh, float* hout, const aero_lstm_params& p,
+static int launch_lstm(const float* gin, const float* bias_pad, const float* whh, void* hout, const aero_lstm_params& p,
                        cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)H * 4 * H + (size_t)H * NT + (size_t)NT * 4 * H);
-    cudaFuncSetAttribute(lstm_rec_kernel<H, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_seq = p.rows * p.n_win;
     dim3 grid(cdiv(n_seq, NT), 2);
-    lstm_rec_kernel<H, NT><<<grid, 4 * H, smem, st>>>(gin, bias_pad, whh, hout, p);
+    if (p.flags & AERO_TG_OUT_F16) {
+        cudaFuncSetAttribute(lstm_rec_kernel<H, NT, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_rec_kernel<H, NT, __half><<<grid, 4 * H, smem, st>>>(gin, bias_pad, whh, static_cast<__half*>(hout), p);
+    } else {
+        cudaFuncSetAttribute(lstm_rec_kernel<H, NT, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_rec_kernel<H, NT, float><<<grid, 4 * H, smem, st>>>(gin, bias_pad, whh, static_cast<float*>(hout), p);
+    }
     return check_launch("aero_lstm_rec_fwd");
 }
 
-int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, float* hout, const aero_lstm_params& p,
+int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
                    cudaStream_t st);
 }  // namespace aero
 
-extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout,
+extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const void* whh, void* hout,
                                  const aero_lstm_params* p, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(gin && whh && hout && p, "aero_lstm_rec_fwd: null argument");
@@ -150,10 +155,10 @@ extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const 
         return lstm_tc_launch(gin, bias_pad, whh, hout, *p, st);
     }
     switch (p->H) {
-        case 12: return launch_lstm<12, 16>(gin, bias_pad, whh, hout, *p, st);
-        case 24: return launch_lstm<24, 16>(gin, bias_pad, whh, hout, *p, st);
-        case 48: return launch_lstm<48, 16>(gin, bias_pad, whh, hout, *p, st);
-        case 96: return launch_lstm<96, 16>(gin, bias_pad, whh, hout, *p, st);
+        case 12: return launch_lstm<12, 16>(gin, bias_pad, (const float*)whh, hout, *p, st);
+        case 24: return launch_lstm<24, 16>(gin, bias_pad, (const float*)whh, hout, *p, st);
+        case 48: return launch_lstm<48, 16>(gin, bias_pad, (const float*)whh, hout, *p, st);
+        case 96: return launch_lstm<96, 16>(gin, bias_pad, (const float*)whh, hout, *p, st);
         default:
             set_error("aero_lstm_rec_fwd: hidden size %d not instantiated (12, 24, 48, 96)", p->H);
             return AERO_ERR_UNSUPPORTED;

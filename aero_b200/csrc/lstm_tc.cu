@@ -53,15 +53,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
         : "memory");
 }
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 template <int NSQ>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NSQ]);
 template <>
@@ -77,10 +68,10 @@ __device__ __forceinline__ void tmem_ld_n<4>(uint32_t taddr, uint32_t (&r)[4]) {
 }
 
 // GPT: gates per 128-row tile.  NEW: cell-update warps (NEW/4 per TMEM lane quarter, each owning 64/NEW sequences).
-template <int GPT, int NEW>
+template <int GPT, int NEW, typename TO>
 __global__ void __launch_bounds__(64 + 32 * NEW, (GPT == 1 ? 1 : 2))
 lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ gin, const float* __restrict__ bias_pad,
-               float* __restrict__ hout, const aero_lstm_params p, const int nK) {
+               TO* __restrict__ hout, const aero_lstm_params p, const int nK) {
     constexpr int NM = 4 / GPT;                          // M tiles
     constexpr int CPW = 32 / GPT;                        // cells per warp
     constexpr int kNS = 64 / NEW;                        // sequences per cell-update warp
@@ -255,7 +246,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                         const unsigned short hh = __half_as_ushort(__float2half_rn(h));
                         asm volatile("st.shared.u16 [%0], %1;" ::"r"(baddr[i]), "h"(hh) : "memory");
                     }
-                    if ((unsigned)(s - w_lo[i]) < (unsigned)w_len[i]) hout[ooff[i]] = h;
+                    if ((unsigned)(s - w_lo[i]) < (unsigned)w_len[i]) stf(hout + ooff[i], h);
                 }
                 ooff[i] += ostep;
             }
@@ -273,7 +264,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
     }
 }
 
-int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, float* hout, const aero_lstm_params& p,
+template <int GPT, int NEW, typename TO>
+static void lstm_tc_go(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mW, const float* gin, const float* bias_pad, void* hout,
+                       const aero_lstm_params& p, int nK) {
+    cudaFuncSetAttribute(lstm_tc_kernel<GPT, NEW, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_tc_kernel<GPT, NEW, TO><<<grid, 64 + 32 * NEW, smem, st>>>(mW, gin, bias_pad, static_cast<TO*>(hout), p, nK);
+}
+
+int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
                    cudaStream_t st) {
     const int H = p.H;
     if (H % 4 || H <= 32 || H > 128) {
@@ -301,12 +299,13 @@ int lstm_tc_launch(const float* gin, const float* bias_pad, const float* whh_r, 
         return AERO_ERR_UNSUPPORTED;
     }
     dim3 grid(cdiv(n_seq, kNT), 2);
+    const bool o16 = p.flags & AERO_TG_OUT_F16;
     if (gpt == 1) {
-        cudaFuncSetAttribute(lstm_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lstm_tc_kernel<1, 16><<<grid, 64 + 32 * 16, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
+        if (o16) lstm_tc_go<1, 16, __half>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
+        else lstm_tc_go<1, 16, float>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
     } else {
-        cudaFuncSetAttribute(lstm_tc_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lstm_tc_kernel<2, 8><<<grid, 64 + 32 * 8, smem, st>>>(mW, gin, bias_pad, hout, p, nK);
+        if (o16) lstm_tc_go<2, 8, __half>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
+        else lstm_tc_go<2, 8, float>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
     }
     return check_launch("aero_lstm_rec_fwd(tcgen05)");
 }

@@ -2,9 +2,9 @@
 #include "tapgemm.cuh"
 
 
-extern "C" int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w, const float* bias,
-                                const float* addend_fn, const float* colscale, const float* residual,
-                                const float* samp_affine, float* out, double* stats,
+extern "C" int aero_tapgemm_fwd(const void* a1, const void* a2, const void* w, const float* bias,
+                                const float* addend_fn, const float* colscale, const void* residual,
+                                const float* samp_affine, void* out, double* stats,
                                 const aero_tapgemm_params* pp, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(w && out && pp, "aero_tapgemm_fwd: null argument");
@@ -20,7 +20,7 @@ extern "C" int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w
         AERO_REQUIRE(p.kt == 1 && p.kf % p.stride_f == 0, "aero_tapgemm_fwd: transposed conv needs kt=1 and kf %% stride == 0");
         ntaps = p.kf / p.stride_f;
     } else if (p.mode == AERO_TAPS_MIX) {
-        AERO_REQUIRE(p.precision == 1, "aero_tapgemm_fwd: AERO_TAPS_MIX exists on the tcgen05 path only (precision 1)");
+        AERO_REQUIRE(p.precision == 1 || p.precision == 2, "aero_tapgemm_fwd: AERO_TAPS_MIX exists on the tcgen05 path only (precision 1 / 2)");
         ntaps = 1;
     } else {
         set_error("aero_tapgemm_fwd: mode=%d", p.mode);
@@ -54,9 +54,12 @@ extern "C" int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w
               (!residual || (al16(residual) && p.r_sb % 4 == 0 && p.r_sf % 4 == 0 && p.r_st % 4 == 0)) &&
               (!addend_fn || al16(addend_fn));
     AERO_REQUIRE(al16(w) && p.w_sb % 4 == 0, "aero_tapgemm_fwd: weights must be 16-byte aligned");
-    if (p.precision == 1) {
+    AERO_REQUIRE(p.precision >= 0 && p.precision <= 2, "aero_tapgemm_fwd: precision=%d", p.precision);
+    AERO_REQUIRE((p.precision != 1 || !(p.flags & AERO_TG_A_F16)) && (p.precision != 2 || (p.flags & AERO_TG_A_F16)),
+                 "aero_tapgemm_fwd: precision 1 reads fp32 sources, precision 2 FP16 sources (flags=%d)", p.flags);
+    if (p.precision >= 1) {
         if (!tapgemm_tc_eligible(p)) {
-            set_error("aero_tapgemm_fwd: precision=1 requested for a shape the tcgen05 path does not take (N=%d K=%d)", p.N, p.C1 + p.C2);
+            set_error("aero_tapgemm_fwd: tcgen05 path requested for a shape the tcgen05 path does not take (N=%d K=%d)", p.N, p.C1 + p.C2);
             return AERO_ERR_UNSUPPORTED;
         }
         AERO_REQUIRE((p.C1 == 0 || al16(a1)) && (p.C2 == 0 || al16(a2)), "aero_tapgemm_fwd: TMA sources must be 16-byte aligned");

@@ -4,15 +4,15 @@
 
 namespace aero {
 struct TapGemmArgs {
-    const float* a1;
-    const float* a2;
-    const float* w;
+    const void* a1;           // fp32, or FP16 when p.flags & AERO_TG_A_F16
+    const void* a2;
+    const void* w;            // fp32 (precision 0 / 1) or FP16 (precision 2)
     const float* bias;
     const float* addend_fn;
     const float* colscale;
-    const float* residual;
+    const void* residual;     // same type as out
     const float* samp_affine;
-    float* out;
+    void* out;                // fp32, or FP16 when p.flags & AERO_TG_OUT_F16
     double* stats;
     aero_tapgemm_params p;
     int ntaps;

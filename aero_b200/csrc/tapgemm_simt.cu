@@ -10,7 +10,7 @@ namespace aero {
 constexpr int kBK = 16;
 
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, typename TA, typename TO>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(const TapGemmArgs g) {
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int TX = BN / TN;
@@ -37,7 +37,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    const float* wb = g.w + (int64_t)b * p.w_sb;
+    const float* wb = static_cast<const float*>(g.w) + (int64_t)b * p.w_sb;
+    const TA* const ga1 = static_cast<const TA*>(g.a1);
+    const TA* const ga2 = static_cast<const TA*>(g.a2);
 
     for (int tap = 0; tap < g.ntaps; ++tap) {
         int fi, dt, slab;
@@ -54,8 +56,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
             slab = kidx;
         }
         if (fi < 0 || fi >= p.F_in) continue;          // uniform across the CTA
-        const float* s1 = g.a1 ? g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf : nullptr;
-        const float* s2 = g.a2 ? g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf : nullptr;
+        const TA* s1 = ga1 ? ga1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf : nullptr;
+        const TA* s2 = ga2 ? ga2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf : nullptr;
         const float* wslab = wb + (int64_t)slab * K * g.ldw;
 
         for (int kc = 0; kc < K; kc += kBK) {
@@ -69,17 +71,17 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (ti >= 0 && ti < p.T_in && (t0 + m) < p.T) {
                     if (g.vec_a && c + 3 < p.C1) {
-                        const float4 q = *reinterpret_cast<const float4*>(s1 + (int64_t)ti * p.a1_st + c);
+                        const float4 q = ld4(s1 + (int64_t)ti * p.a1_st + c);
                         v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
                     } else if (g.vec_a && c >= p.C1 && c + 3 < K) {
-                        const float4 q = *reinterpret_cast<const float4*>(s2 + (int64_t)ti * p.a2_st + (c - p.C1));
+                        const float4 q = ld4(s2 + (int64_t)ti * p.a2_st + (c - p.C1));
                         v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
                     } else {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int cc = c + u;
-                            if (cc < p.C1) v[u] = s1[(int64_t)ti * p.a1_st + cc];
-                            else if (cc < K) v[u] = s2[(int64_t)ti * p.a2_st + (cc - p.C1)];
+                            if (cc < p.C1) v[u] = ldf(s1 + (int64_t)ti * p.a1_st + cc);
+                            else if (cc < K) v[u] = ldf(s2 + (int64_t)ti * p.a2_st + (cc - p.C1));
                         }
                     }
                 }
@@ -164,27 +166,28 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
 #pragma unroll
             for (int j = 0; j < TN; ++j) o[j] = v[j];
         }
-        float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
-        const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+        TO* op = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+        const TO* rp = g.residual ? static_cast<const TO*>(g.residual) + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
 #pragma unroll
         for (int j = 0; j < TNO_MAX; ++j) {
             if (j < cnt && no0 + j < Nout) {
                 float x = o[j];
                 if (g.addend_fn) x += g.addend_fn[(int64_t)fo * Nout + no0 + j];
-                if (rp) x += rp[no0 + j];
+                if (rp) x += ldf(rp + no0 + j);
                 x = x * sa + sb;
-                if (p.flags & 1) x = round_tf32_rna(x);
+                if ((p.flags & 1) && sizeof(TO) == 4) x = round_tf32_rna(x);
+                x = stored(x, op);
                 o[j] = x;
                 ssum += x;
                 ssq += x * x;
             }
         }
         if (g.vec_o && !p.glu && TN == 4 && no0 + 3 < Nout) {
-            *reinterpret_cast<float4*>(op + no0) = make_float4(o[0], o[1], o[2], o[3]);
+            st4(op + no0, make_float4(o[0], o[1], o[2], o[3]));
         } else {
 #pragma unroll
             for (int j = 0; j < TNO_MAX; ++j)
-                if (j < cnt && no0 + j < Nout) op[no0 + j] = o[j];
+                if (j < cnt && no0 + j < Nout) stf(op + no0 + j, o[j]);
         }
     }
 
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tapgemm_simt_kernel(con
 // columns over all taps; the weights live in shared memory ([tap][c][8]) and are read as broadcasts.
 constexpr int kThinN = 8;
 
+template <typename TA, typename TO>
 __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g) {
     extern __shared__ __align__(16) float wsm[];          // [nslab][K][8]
     const aero_tapgemm_params& p = g.p;
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
     const int nslab = (p.mode == AERO_TAPS_CONVT) ? p.kf : p.kf * p.kt;
     for (int i = threadIdx.x; i < nslab * K * kThinN; i += blockDim.x) {
         const int n = i % kThinN, rk = i / kThinN;
-        wsm[i] = n < p.N ? g.w[(int64_t)rk * g.ldw + n] : 0.f;
+        wsm[i] = n < p.N ? static_cast<const float*>(g.w)[(int64_t)rk * g.ldw + n] : 0.f;
     }
     __syncthreads();
     const int64_t npix = (int64_t)p.B * p.F_out * p.T;
@@ -256,11 +260,11 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
             for (int src = 0; src < 2; ++src) {
                 const int Cs = src ? p.C2 : p.C1;
                 if (Cs == 0) continue;
-                const float* a = src ? g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (int64_t)ti * p.a2_st
-                                     : g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)ti * p.a1_st;
+                const TA* a = src ? static_cast<const TA*>(g.a2) + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (int64_t)ti * p.a2_st
+                                  : static_cast<const TA*>(g.a1) + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)ti * p.a1_st;
                 const float* wc = wt + (src ? p.C1 : 0) * kThinN;
                 for (int c = 0; c < Cs; c += 4) {
-                    const float4 av = *reinterpret_cast<const float4*>(a + c);       // vec_a holds (host check)
+                    const float4 av = ld4(a + c);       // vec_a holds (host check)
                     const float avs[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -276,18 +280,18 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
         }
         float sa = 1.f, sb = 0.f;
         if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
-        float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
-        const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+        TO* op = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+        const TO* rp = g.residual ? static_cast<const TO*>(g.residual) + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
 #pragma unroll
         for (int n = 0; n < kThinN; ++n) {
             if (n < p.N) {
                 float x = acc[n] + (g.bias ? g.bias[n] : 0.f);
                 if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
                 else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
-                if (rp) x += rp[n];
+                if (rp) x += ldf(rp + n);
                 x = x * sa + sb;
-                if (p.flags & 1) x = round_tf32_rna(x);
-                op[n] = x;
+                if ((p.flags & 1) && sizeof(TO) == 4) x = round_tf32_rna(x);
+                stf(op + n, x);
             }
         }
     }
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
 
 // thin-K (K <= 4, single tap: pre_conv 2->48): a thread owns one quad of output columns (its weights and bias stay in
 // registers) and walks over pixels; consecutive lanes = consecutive column quads of one pixel -> 16-byte coalesced stores.
+template <typename TA, typename TO>
 __global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g) {
     const aero_tapgemm_params& p = g.p;
     const int K = p.C1;
@@ -305,27 +310,27 @@ __global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g
     const int n = nq * 4;
     float4 w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = k < K ? *reinterpret_cast<const float4*>(g.w + (int64_t)k * g.ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) w[k] = k < K ? *reinterpret_cast<const float4*>(static_cast<const float*>(g.w) + (int64_t)k * g.ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 bias = g.bias ? *reinterpret_cast<const float4*>(g.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool rnd = p.flags & 1;
+    const bool rnd = (p.flags & 1) && sizeof(TO) == 4;
     const int64_t npix = (int64_t)p.B * p.F_out * p.T;
     for (int64_t pix = (int64_t)blockIdx.x * ppp + dp; pix < npix; pix += (int64_t)gridDim.x * ppp) {
         const int t = (int)(pix % p.T);
         const int64_t rowi = pix / p.T;
         const int fo = (int)(rowi % p.F_out), b = (int)(rowi / p.F_out);
-        const float* a = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fo * p.a1_sf + (int64_t)t * p.a1_st;
+        const TA* a = static_cast<const TA*>(g.a1) + (int64_t)b * p.a1_sb + (int64_t)fo * p.a1_sf + (int64_t)t * p.a1_st;
         float4 acc = bias;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k < K) {
-                const float av = a[k];
+                const float av = ldf(a + k);
                 acc.x = fmaf(av, w[k].x, acc.x); acc.y = fmaf(av, w[k].y, acc.y); acc.z = fmaf(av, w[k].z, acc.z); acc.w = fmaf(av, w[k].w, acc.w);
             }
         }
         if (p.act == AERO_ACT_GELU) { acc.x = gelu_exact(acc.x); acc.y = gelu_exact(acc.y); acc.z = gelu_exact(acc.z); acc.w = gelu_exact(acc.w); }
         else if (p.act == AERO_ACT_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
         if (rnd) { acc.x = round_tf32_rna(acc.x); acc.y = round_tf32_rna(acc.y); acc.z = round_tf32_rna(acc.z); acc.w = round_tf32_rna(acc.w); }
-        *reinterpret_cast<float4*>(g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n) = acc;
+        st4(static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n, acc);
     }
 }
 
@@ -333,6 +338,7 @@ __global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g
 // input row pair are computed together.  With a = fo' / s the taps are fi = a - j, slab = r + j*s for output row
 // fo' = a*s + r: treat (r, n) as 8 "virtual columns" of a plain conv over j.  Every input row is then read k/s times
 // instead of k times, and each thread keeps all its accumulators.
+template <typename TA, typename TO>
 __global__ void __launch_bounds__(256) tapgemm_thin_convt_kernel(const TapGemmArgs g, const int a_lo, const int n_a) {
     extern __shared__ __align__(16) float wsm[];          // [ntaps][K][8]: column v = r*N + n
     const aero_tapgemm_params& p = g.p;
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(256) tapgemm_thin_convt_kernel(const TapGemmAr
     for (int i = threadIdx.x; i < ntaps * K * kThinN; i += blockDim.x) {
         const int v = i % kThinN, c = (i / kThinN) % K, j = i / (kThinN * K);
         const int r = v / p.N, n = v % p.N;
-        wsm[i] = (r < s) ? g.w[((int64_t)(r + j * s) * K + c) * g.ldw + n] : 0.f;
+        wsm[i] = (r < s) ? static_cast<const float*>(g.w)[((int64_t)(r + j * s) * K + c) * g.ldw + n] : 0.f;
     }
     __syncthreads();
     const int64_t npix = (int64_t)p.B * n_a * p.T;
@@ -354,10 +360,10 @@ __global__ void __launch_bounds__(256) tapgemm_thin_convt_kernel(const TapGemmAr
         for (int j = 0; j < ntaps; ++j) {
             const int fi = a - j;
             if (fi < 0 || fi >= p.F_in) continue;
-            const float* src = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)t * p.a1_st;
+            const TA* src = static_cast<const TA*>(g.a1) + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)t * p.a1_st;
             const float* wt = wsm + (int64_t)j * K * kThinN;
             for (int c = 0; c < K; c += 4) {
-                const float4 av = *reinterpret_cast<const float4*>(src + c);
+                const float4 av = ld4(src + c);
                 const float avs[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -381,14 +387,15 @@ __global__ void __launch_bounds__(256) tapgemm_thin_convt_kernel(const TapGemmAr
                 if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
                 else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
                 x = x * sa + sb;
-                if (p.flags & 1) x = round_tf32_rna(x);
-                g.out[(int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n] = x;
+                if ((p.flags & 1) && sizeof(TO) == 4) x = round_tf32_rna(x);
+                stf(static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + n, x);
             }
         }
     }
 }
 
-int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
+template <typename TA, typename TO>
+static int tapgemm_simt_launch_t(const TapGemmArgs& g, cudaStream_t st) {
     const aero_tapgemm_params& p = g.p;
     TapGemmArgs a = g;
     const bool plain = !p.glu && p.stats_mode == 0 && !g.addend_fn && !g.colscale && p.w_sb == 0;
@@ -396,22 +403,22 @@ int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
     if (plain && p.mode == AERO_TAPS_CONVT && p.stride_f * p.N <= kThinN && p.C2 == 0 && g.vec_a && !g.residual &&
         (size_t)(p.kf / p.stride_f) * p.C1 * kThinN * 4 <= 96 * 1024) {
         const size_t smem = (size_t)(p.kf / p.stride_f) * p.C1 * kThinN * 4;
-        cudaFuncSetAttribute(tapgemm_thin_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(tapgemm_thin_convt_kernel<TA, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int a_lo = p.f_out_offset / p.stride_f, a_hi = (p.f_out_offset + p.F_out - 1) / p.stride_f;
         const int n_a = a_hi - a_lo + 1;
         const int64_t npix = (int64_t)p.B * n_a * p.T;
         int blocks = (int)((npix + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        tapgemm_thin_convt_kernel<<<blocks, 256, smem, st>>>(a, a_lo, n_a);
+        tapgemm_thin_convt_kernel<TA, TO><<<blocks, 256, smem, st>>>(a, a_lo, n_a);
         return check_launch("aero_tapgemm_fwd(thin-convt)");
     }
     if (plain && p.N <= kThinN && g.vec_a && (size_t)nslab * (p.C1 + p.C2) * kThinN * 4 <= 96 * 1024) {
         const size_t smem = (size_t)nslab * (p.C1 + p.C2) * kThinN * 4;
-        cudaFuncSetAttribute(tapgemm_thin_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(tapgemm_thin_n_kernel<TA, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int64_t npix = (int64_t)p.B * p.F_out * p.T;
         int blocks = (int)((npix + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        tapgemm_thin_n_kernel<<<blocks, 256, smem, st>>>(a);
+        tapgemm_thin_n_kernel<TA, TO><<<blocks, 256, smem, st>>>(a);
         return check_launch("aero_tapgemm_fwd(thin-n)");
     }
     if (plain && p.mode == AERO_TAPS_CONV && p.kf == 1 && p.kt == 1 && p.stride_f == 1 && p.pad_f == 0 && p.C2 == 0 && p.C1 <= 4 &&
@@ -421,7 +428,7 @@ int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
         int blocks = (int)((npix + (int64_t)ppp * 8 - 1) / ((int64_t)ppp * 8));
         if (blocks > 148 * 32) blocks = 148 * 32;
         if (blocks < 1) blocks = 1;
-        tapgemm_thin_k_kernel<<<blocks, 256, 0, st>>>(a);
+        tapgemm_thin_k_kernel<TA, TO><<<blocks, 256, 0, st>>>(a);
         return check_launch("aero_tapgemm_fwd(thin-k)");
     }
     const bool thin = p.N <= 16;
@@ -431,12 +438,18 @@ int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
     if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
     if (thin) {
         dim3 grid((unsigned)tiles, cdiv(p.N, 16));
-        tapgemm_simt_kernel<128, 16, 8, 1><<<grid, 256, 0, st>>>(a);
+        tapgemm_simt_kernel<128, 16, 8, 1, TA, TO><<<grid, 256, 0, st>>>(a);
     } else {
         dim3 grid((unsigned)tiles, cdiv(p.N, 64));
-        tapgemm_simt_kernel<128, 64, 8, 4><<<grid, 256, 0, st>>>(a);
+        tapgemm_simt_kernel<128, 64, 8, 4, TA, TO><<<grid, 256, 0, st>>>(a);
     }
     return check_launch("aero_tapgemm_fwd(simt)");
+}
+
+int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st) {
+    const bool a16 = g.p.flags & AERO_TG_A_F16, o16 = g.p.flags & AERO_TG_OUT_F16;
+    if (a16) return o16 ? tapgemm_simt_launch_t<__half, __half>(g, st) : tapgemm_simt_launch_t<__half, float>(g, st);
+    return o16 ? tapgemm_simt_launch_t<float, __half>(g, st) : tapgemm_simt_launch_t<float, float>(g, st);
 }
 
 }  // namespace aero

@@ -10,7 +10,12 @@
 // warps 2..5 = epilogue (one TMEM lane quarter each).  STAGES-deep mbarrier ring between
 // producer and MMA; tcgen05.commit frees a stage / publishes the accumulator.
 //
-// Operands are read as fp32 bit patterns with the low 13 mantissa bits ignored by the tensor core,
+// Operand kinds: kind::tf32 (fp32 storage, 32 channels per 128-byte row, UMMA_K = 8) or kind::f16 (FP16 storage, 64 channels
+// per row, UMMA_K = 16): the shared-memory image is identical in bytes (128 rows x 128 B per k-block, four UMMAs of 32 B along
+// K), so one kernel serves both.  FP16 has TF32's 10-bit mantissa at half the HBM bytes and twice the tensor-core rate.
+// Outputs are fp32 or FP16 independently of the operand kind.
+//
+// TF32 operands are read as fp32 bit patterns with the low 13 mantissa bits ignored by the tensor core,
 // so producers round activations to TF32 (round-to-nearest) when they store them and the host
 // rounds the weights when it packs them: truncation would bias every dot product low.
 #include <cuda.h>
@@ -18,6 +23,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <type_traits>
 
 #include "tapgemm.cuh"
 #include "tc_common.cuh"
@@ -25,7 +31,7 @@
 namespace aero {
 
 constexpr int kBM = 128;
-constexpr int kBKc = 32;                 // fp32 elements per 128-byte swizzle row
+template <bool F16A> struct OperandKind { static constexpr int kBK = F16A ? 64 : 32; };   // elements per 128-byte swizzle row
 constexpr int kMaxStages = 6;
 constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, alternating 16-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -120,7 +126,7 @@ __device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], uint32
     }
 }
 
-template <int AMODE, bool RES, bool STATS>
+template <int AMODE, bool RES, bool STATS, typename TO>
 __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmArgs& g, const TileCoord& tc, uint32_t tacc, int BN, int q,
                                                    int ew, int lane, int Nout, int gw) {
     const aero_tapgemm_params& p = g.p;
@@ -128,15 +134,15 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
     constexpr int LPR = CNT / 4;                         // lanes per row (one float4 each)
     constexpr int RPI = 32 / LPR;                        // rows per pass
     const uint32_t stg = smem_u32(&sh->stage[ew][0][0]);       // [32][20] floats, addressed in the shared window
-    const bool rnd = p.flags & 1;
+    const bool rnd = (p.flags & 1) && sizeof(TO) == 4;
     float sa = 1.f, sb = 0.f;
     if (g.samp_affine) { sa = g.samp_affine[2 * tc.b]; sb = g.samp_affine[2 * tc.b + 1]; }
     const int cq = lane % LPR, ro = lane / LPR;
     const int row0 = tc.t0 + q * 32;                     // first output row (t) of this warp's lane quarter
     const int rows = min(32, p.T - row0);                // valid rows (<= 0: nothing to store)
     const int g_lo = ((AMODE == 3) ? tc.n0 >> 1 : tc.n0) / gw;
-    float* const obase = g.out + (int64_t)tc.b * p.o_sb + (int64_t)tc.fo * p.o_sf + (int64_t)row0 * p.o_st;
-    const float* const rbase = RES ? g.residual + (int64_t)tc.b * p.r_sb + (int64_t)tc.fo * p.r_sf + (int64_t)row0 * p.r_st : nullptr;
+    TO* const obase = static_cast<TO*>(g.out) + (int64_t)tc.b * p.o_sb + (int64_t)tc.fo * p.o_sf + (int64_t)row0 * p.o_st;
+    const TO* const rbase = RES ? static_cast<const TO*>(g.residual) + (int64_t)tc.b * p.r_sb + (int64_t)tc.fo * p.r_sf + (int64_t)row0 * p.r_st : nullptr;
     const float* const adp = g.addend_fn ? g.addend_fn + (int64_t)tc.fo * Nout : nullptr;
     for (int c0 = (ew >> 2) * 16; c0 < BN; c0 += 32) {   // the two warps of a lane quarter alternate 16-column chunks
         const int nb = tc.n0 + c0;
@@ -158,8 +164,8 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
             const bool has_ad = adp != nullptr, affine = g.samp_affine != nullptr;
             if (has_ad) ad = *reinterpret_cast<const float4*>(adp + nn);
             uint32_t sp = stg + (uint32_t)(ro * 80 + cq * 16);
-            float* op = obase + (int64_t)ro * p.o_st + nn;
-            const float* rp = RES ? rbase + (int64_t)ro * p.r_st + nn : nullptr;
+            TO* op = obase + (int64_t)ro * p.o_st + nn;
+            const TO* rp = RES ? rbase + (int64_t)ro * p.r_st + nn : nullptr;
             const int64_t ostep = (int64_t)RPI * p.o_st, rstep = (int64_t)RPI * p.r_st;
 #pragma unroll 2
             for (int rr = ro; rr < rows; rr += RPI) {
@@ -167,7 +173,7 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
                 sp += RPI * 80;
                 if (has_ad) { x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w; }
                 if (RES) {
-                    const float4 rs = *reinterpret_cast<const float4*>(rp);
+                    const float4 rs = ld4(rp);
                     x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
                     rp += rstep;
                 }
@@ -177,7 +183,7 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
                     ls += (x.x + x.y) + (x.z + x.w);
                     lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
                 }
-                *reinterpret_cast<float4*>(op) = x;
+                st4(op, x);
                 op += ostep;
             }
         }
@@ -209,7 +215,7 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
 
 // Persistent: CTA c processes tiles c, c + gridDim.x, ...  The TMA producer runs ahead across tile boundaries; the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
-template <int AMODE, bool RES, bool STATS>
+template <int AMODE, bool RES, bool STATS, bool F16A, bool F16O>
 __global__ void __launch_bounds__(kThreads)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                   const __grid_constant__ CUtensorMap mapW, const TapGemmArgs g, const int BN, const uint32_t idesc,
@@ -219,6 +225,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
     const int stage_bytes = kATileBytes + BN * 128;
     TcShared* sh = reinterpret_cast<TcShared*>(smem + kStages * stage_bytes);
 
+    using TO = typename std::conditional<F16O, __half, float>::type;
+    constexpr int kBKc = OperandKind<F16A>::kBK;
     const aero_tapgemm_params& p = g.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nch1 = (p.C1 + kBKc - 1) / kBKc, nch2 = (p.C2 + kBKc - 1) / kBKc;
@@ -252,14 +260,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
                 const TileCoord c = tile_coord(g, tile, n_tiles, BN, nch1, nch2);
                 if (mix) {
-                    // A = activations [K rows][M contiguous]: four 32(m) x 32(k) boxes form one MN-major 128 x 32 operand tile
+                    // A = activations [K rows][M contiguous].  tf32: four 32(m) x 32(k) boxes, f16: two 64(m) x 64(k) boxes
+                    // form one MN-major 128(m) x kBK(k) operand tile of 16 KB
                     for (int kc = 0; kc < nch1; ++kc) {
                         mbar_wait(&sh->empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * stage_bytes;
                         mbar_expect_tx(&sh->full[stage], tx);
+                        constexpr int kBoxM = F16A ? 64 : 32;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tma_load_3d(sa + j * 4096, &mapA1, &sh->full[stage], c.t0 + 32 * j, kc * kBKc, c.b);
+                        for (int j = 0; j < 128 / kBoxM; ++j)
+                            tma_load_3d(sa + j * (kATileBytes / (128 / kBoxM)), &mapA1, &sh->full[stage], c.t0 + kBoxM * j, kc * kBKc, c.b);
                         tma_load_3d(sa + kATileBytes, &mapW, &sh->full[stage], kc * kBKc, c.n0, 0);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
@@ -301,7 +311,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint64_t db = make_desc_sw128(sa + kATileBytes);
-                    if (mix) {
+                    if (mix && F16A) {
+                        // MN-major f16 A, plain SWIZZLE_128B (cute Layout_MN_SW128_Atom<half>): atoms of 64 elements along M
+                        // (128 B) x 8 rows along K = 1024 B.  A 64(m) x 64(k) TMA box is 8 K-atoms stacked (SBO = 1024 B); the two
+                        // boxes of a stage are the M atoms (LBO = 8192 B).  One UMMA (K = 16) consumes two K atoms = 2048 B.
+                        const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                                            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma<F16A>(tacc, da + (uint64_t)(k * (2048 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    } else if (mix) {
                         // MN-major tf32 A: the only legal layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom: 32 elements
                         // along M x 4 rows along K = 512 B atoms, 32-byte chunks XOR-swizzled by row%4; TMA SWIZZLE_128B_ATOM_32B
                         // writes exactly that).  A 32(m) x 32(k) TMA box is 8 K-atoms stacked (SBO = 512 B); the four boxes of a
@@ -309,13 +328,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         const uint64_t da = (uint64_t)((sa >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
                                             ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 #pragma unroll
-                        for (int k = 0; k < kBKc / 8; ++k)
-                            umma_tf32(tacc, da + (uint64_t)(k * (1024 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            umma<F16A>(tacc, da + (uint64_t)(k * (1024 >> 4)), db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     } else {
                         const uint64_t da = make_desc_sw128(sa);
 #pragma unroll
-                        for (int k = 0; k < kBKc / 8; ++k)      // UMMA_K = 8 for tf32: 32 bytes along the swizzled row
-                            umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)             // one UMMA = 32 bytes along the swizzled row (K = 8 tf32 / 16 f16)
+                            umma<F16A>(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&sh->empty[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -330,7 +349,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
         const int m = q * 32 + lane;
         const int Nout = p.glu ? p.N / 2 : p.N;
         const int gw = (p.stats_mode == 1) ? Nout / p.groups : Nout;
-        const bool rnd = p.flags & 1;
+        const bool rnd = (p.flags & 1) && !F16O;
         const bool fast = !mix && g.vec_o && !g.colscale && (p.stats_mode == 0 || gw % 4 == 0);
         int local = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
@@ -344,8 +363,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             tcgen05_fence_after();
             float sa = 1.f, sb = 0.f;
             if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
-            float* op = g.out + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
-            const float* rp = g.residual ? g.residual + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+            TO* op = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+            const TO* rp = g.residual ? static_cast<const TO*>(g.residual) + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
             const float* csp = g.colscale ? g.colscale + (int64_t)b * p.cs_sb + (int64_t)t * p.cs_st : nullptr;
             const float* adp = g.addend_fn ? g.addend_fn + (int64_t)fo * Nout : nullptr;
             int cur_g = -1;
@@ -355,7 +374,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             if (mix) {
                 // transposed store: lane = pixel m (contiguous in memory), column = output row n
                 const float gate = (row_ok && g.colscale) ? g.colscale[(int64_t)b * p.cs_sb + t] : 1.f;
-                float* ob = g.out + (int64_t)b * p.o_sb + t;
+                TO* ob = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + t;
                 for (int c0 = (ew >> 2) * 16; c0 < BN; c0 += 32) {
                     uint32_t r[16];
                     tmem_ld16(tacc + (uint32_t)c0, r);
@@ -366,13 +385,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                             if (n < p.N) {
                                 float x = __uint_as_float(r[j]) * gate;
                                 if (rnd) x = round_tf32_rna(x);
-                                ob[(int64_t)n * p.o_st] = x;
+                                stf(ob + (int64_t)n * p.o_st, x);
                             }
                         }
                     }
                 }
             } else if (fast) {
-                epilogue_fast_tile<AMODE, RES, STATS>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw);
+                epilogue_fast_tile<AMODE, RES, STATS, TO>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw);
             } else {
                 // generic (unaligned outputs / colscale) epilogue: lane = row, scattered stores; one warp per lane quarter
                 for (int c0 = 0; c0 < (ew < 4 ? BN : 0); c0 += 16) {
@@ -433,7 +452,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                             if (row_ok && nn < Nout) {
                                 float x = o[jj];
                                 if (adp) x += adp[nn];
-                                if (rp) x += rp[nn];
+                                if (rp) x += ldf(rp + nn);
                                 x = x * sa + sb;
                                 if (rnd) x = round_tf32_rna(x);
                                 o[jj] = x;
@@ -445,7 +464,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (j < cnt && no0 + j < Nout) op[no0 + j] = o[j];
+                            if (j < cnt && no0 + j < Nout) stf(op + no0 + j, o[j]);
                     }
                 }
                 if (p.stats_mode != 0 && cur_g >= 0) {
@@ -561,15 +580,19 @@ static int pick_bn(int N) {
     return (per + 15) & ~15;
 }
 
+// precision 1: fp32 sources (kind::tf32); precision 2: FP16 sources (kind::f16).  TMA needs 16-byte global strides:
+// channel counts / strides in multiples of 4 fp32 or 8 halves.
 bool tapgemm_tc_eligible(const aero_tapgemm_params& p) {
+    const bool f16 = (p.flags & AERO_TG_A_F16) != 0;
+    const int q = f16 ? 8 : 4;
     if (p.mode == AERO_TAPS_MIX)
-        return p.w_sb == 0 && p.C1 % 4 == 0 && p.C2 == 0 && p.T % 4 == 0 && p.a1_st % 4 == 0 && p.a1_sb % 4 == 0 && p.N >= 8 &&
+        return p.w_sb == 0 && p.C1 % q == 0 && p.C2 == 0 && p.T % q == 0 && p.a1_st % q == 0 && p.a1_sb % q == 0 && p.N >= 8 &&
                p.stats_mode == 0 && !p.glu && p.F_out == 1 && p.F_in == 1;
     if (p.w_sb != 0) return false;                                   // activations-as-weights (FTB frequency mix)
     if (p.N < 8) return false;                                       // thin outputs stay on the SIMT path
     const int K = p.C1 + p.C2;
-    if (K < 8 || (p.C1 % 4) || (p.C2 % 4)) return false;             // TMA needs 16-byte global strides
-    auto ok_strides = [](int64_t sb, int64_t sf, int64_t st) { return sb % 4 == 0 && sf % 4 == 0 && st % 4 == 0 && st > 0; };
+    if (K < 8 || (p.C1 % q) || (p.C2 % q)) return false;
+    auto ok_strides = [q](int64_t sb, int64_t sf, int64_t st) { return sb % q == 0 && sf % q == 0 && st % q == 0 && st > 0; };
     if (p.C1 && !ok_strides(p.a1_sb, p.a1_sf, p.a1_st)) return false;
     if (p.C2 && !ok_strides(p.a2_sb, p.a2_sf, p.a2_st)) return false;
     if (p.stats_mode == 1) {
@@ -582,19 +605,58 @@ bool tapgemm_tc_eligible(const aero_tapgemm_params& p) {
     return true;
 }
 
-static int make_a_map(CUtensorMap* m, const float* base, int C, const aero_tapgemm_params& p, int64_t sb, int64_t sf, int64_t st) {
+static int make_a_map(CUtensorMap* m, const void* base, int C, const aero_tapgemm_params& p, int64_t sb, int64_t sf, int64_t st, int esz) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.T_in, (uint64_t)p.F_in, (uint64_t)p.B};
     int64_t s1 = st, s2 = sf, s3 = sb;
     if (s2 <= 0) s2 = s1 * p.T_in;              // size-1 dimensions: any legal stride
     if (s3 <= 0) s3 = s2 * p.F_in;
-    uint64_t strides[3] = {(uint64_t)s1 * 4, (uint64_t)s2 * 4, (uint64_t)s3 * 4};
-    uint32_t box[4] = {(uint32_t)kBKc, (uint32_t)kBM, 1, 1};
-    return encode_map(m, base, 4, dims, strides, box);
+    uint64_t strides[3] = {(uint64_t)s1 * esz, (uint64_t)s2 * esz, (uint64_t)s3 * esz};
+    uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)kBM, 1, 1};
+    return encode_map(m, base, 4, dims, strides, box, false, esz);
+}
+
+using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, TapGemmArgs, int, uint32_t, uint32_t, int, int, int);
+
+// kernel variants: [operand kind][output type][AMODE][RES][STATS]; only the combinations the host code can produce are
+// instantiated for the FP16 kinds (statistics and fp32 outputs go together: GroupNorm inputs stay fp32)
+template <bool F16A, bool F16O>
+static KernelFn pick_kernel(int amode, bool res, bool stats) {
+#define AERO_TC_K(A, R, S) tapgemm_tc_kernel<A, R, S, F16A, F16O>
+    if constexpr (!F16A && !F16O) {
+        static const KernelFn table[4][2][2] = {
+            {{AERO_TC_K(0, false, false), AERO_TC_K(0, false, true)}, {AERO_TC_K(0, true, false), AERO_TC_K(0, true, true)}},
+            {{AERO_TC_K(1, false, false), AERO_TC_K(1, false, true)}, {AERO_TC_K(1, true, false), AERO_TC_K(1, true, true)}},
+            {{AERO_TC_K(2, false, false), AERO_TC_K(2, false, true)}, {AERO_TC_K(2, true, false), AERO_TC_K(2, true, true)}},
+            {{AERO_TC_K(3, false, false), AERO_TC_K(3, false, true)}, {AERO_TC_K(3, true, false), AERO_TC_K(3, true, true)}}};
+        return table[amode][res][stats];
+    } else if constexpr (F16O) {                   // FP16 outputs: no statistics; residual only without activation
+        if (stats) return nullptr;
+        if (res) return amode == 0 ? AERO_TC_K(0, true, false) : nullptr;
+        switch (amode) {
+            case 0: return AERO_TC_K(0, false, false);
+            case 1: return AERO_TC_K(1, false, false);
+            case 2: return AERO_TC_K(2, false, false);
+            default: return AERO_TC_K(3, false, false);
+        }
+    } else {
+        // FP16 operands, fp32 outputs: pre-normalisation outputs (with statistics), LSTM gate inputs, attention q/k/v, FTB gate
+        if (res) return nullptr;
+        if (stats) return amode == 0 ? AERO_TC_K(0, false, true) : nullptr;
+        switch (amode) {
+            case 0: return AERO_TC_K(0, false, false);
+            case 1: return AERO_TC_K(1, false, false);
+            case 2: return AERO_TC_K(2, false, false);
+            default: return nullptr;
+        }
+    }
+#undef AERO_TC_K
 }
 
 int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     TapGemmArgs g = g0;
     const aero_tapgemm_params& p = g.p;
+    const bool f16a = p.precision == 2, f16o = (p.flags & AERO_TG_OUT_F16) != 0;
+    const int esz = f16a ? 2 : 4, kBKc = 128 / esz;
     const int K = p.C1 + p.C2;
     const int BN = pick_bn(p.N);
     const int nslab = (p.mode == AERO_TAPS_CONVT) ? p.kf : p.kf * p.kt;
@@ -604,19 +666,21 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     if (mix) {
         // activations as [K = C1 rows][M = T contiguous] per batch item
         uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.C1, (uint64_t)p.B};
-        uint64_t strides[2] = {(uint64_t)p.a1_st * 4, (uint64_t)(p.a1_sb > 0 ? p.a1_sb : (int64_t)p.a1_st * p.C1) * 4};
-        uint32_t box[3] = {32, 32, 1};
-        if ((rc = encode_map(&mA1, g.a1, 3, dims, strides, box, true)) != AERO_OK) return rc;
-    } else if (p.C1) { if ((rc = make_a_map(&mA1, g.a1, p.C1, p, p.a1_sb, p.a1_sf, p.a1_st)) != AERO_OK) return rc; }
-    if (p.C2) { if ((rc = make_a_map(&mA2, g.a2, p.C2, p, p.a2_sb, p.a2_sf, p.a2_st)) != AERO_OK) return rc; }
+        uint64_t strides[2] = {(uint64_t)p.a1_st * esz, (uint64_t)(p.a1_sb > 0 ? p.a1_sb : (int64_t)p.a1_st * p.C1) * esz};
+        uint32_t box[3] = {(uint32_t)(f16a ? 64 : 32), (uint32_t)kBKc, 1};
+        if ((rc = encode_map(&mA1, g.a1, 3, dims, strides, box, !f16a, esz)) != AERO_OK) return rc;
+    } else if (p.C1) { if ((rc = make_a_map(&mA1, g.a1, p.C1, p, p.a1_sb, p.a1_sf, p.a1_st, esz)) != AERO_OK) return rc; }
+    if (p.C2) { if ((rc = make_a_map(&mA2, g.a2, p.C2, p, p.a2_sb, p.a2_sf, p.a2_st, esz)) != AERO_OK) return rc; }
     if (!p.C1) mA1 = mA2;
     if (!p.C2) mA2 = mA1;
     {
-        const uint64_t npad = (uint64_t)((p.N + 3) & ~3);          // weights are stored W[slab][pad4(N)][K]
+        // weights are stored K-major W[slab][pad4(N)][Kp], Kp = K (fp32) or K rounded up to 8 (FP16: 16-byte rows)
+        const uint64_t npad = (uint64_t)((p.N + 3) & ~3);
+        const uint64_t kp = f16a ? (uint64_t)((K + 7) & ~7) : (uint64_t)K;
         uint64_t dims[3] = {(uint64_t)K, npad, (uint64_t)nslab};
-        uint64_t strides[2] = {(uint64_t)K * 4, (uint64_t)K * npad * 4};
+        uint64_t strides[2] = {kp * esz, kp * npad * esz};
         uint32_t box[3] = {(uint32_t)kBKc, (uint32_t)BN, 1};
-        if ((rc = encode_map(&mW, g.w, 3, dims, strides, box)) != AERO_OK) return rc;
+        if ((rc = encode_map(&mW, g.w, 3, dims, strides, box, false, esz)) != AERO_OK) return rc;
     }
     g.tiles_t = cdiv(p.T, kBM);
     const int64_t tiles = (int64_t)p.B * p.F_out * g.tiles_t;
@@ -624,11 +688,11 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     uint32_t tmem_cols = 32;                       // two accumulator buffers (double-buffered epilogue)
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
     tmem_cols <<= 1;
-    // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24) |
+    // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A/B format at [7,10)/[10,13) (F16 = 0, TF32 = 2), K-major both,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t fmt = f16a ? 0u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24) |
                            (mix ? (1u << 15) : 0u);                 // bit 15: A is MN-major
-    // pipeline depth: deep for long K loops; shallow for short ones so that several CTAs share an SM and
-    // hide each other's prologue / epilogue (these layers are latency- and HBM-bound, not tensor-bound)
     const int nch = (p.C1 + kBKc - 1) / kBKc + (p.C2 + kBKc - 1) / kBKc;
     const int max_iters = nch * ((p.mode == AERO_TAPS_CONVT) ? p.kf / p.stride_f : p.kf * p.kt);
     const int stage_bytes = kATileBytes + BN * 128;
@@ -636,7 +700,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     // Long K loops get as many stages as fit; short, HBM-bound layers keep ~64 KB in flight and leave room for 2-3 CTAs/SM.
     const int fixed = (int)sizeof(TcShared) + 1024;
     int kStages;
-    if (max_iters >= 24) {
+    if (max_iters >= (f16a ? 12 : 24)) {
         kStages = (227 * 1024 - fixed) / stage_bytes;
     } else {
         kStages = (72 * 1024) / stage_bytes;
@@ -644,15 +708,16 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     if (kStages > kMaxStages) kStages = kMaxStages;
     if (kStages < 2) kStages = 2;
     const size_t smem = (size_t)kStages * stage_bytes + sizeof(TcShared) + 1024;
-    using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, TapGemmArgs, int, uint32_t, uint32_t, int, int, int);
-    static const KernelFn table[4][2][2] = {
-        {{tapgemm_tc_kernel<0, false, false>, tapgemm_tc_kernel<0, false, true>}, {tapgemm_tc_kernel<0, true, false>, tapgemm_tc_kernel<0, true, true>}},
-        {{tapgemm_tc_kernel<1, false, false>, tapgemm_tc_kernel<1, false, true>}, {tapgemm_tc_kernel<1, true, false>, tapgemm_tc_kernel<1, true, true>}},
-        {{tapgemm_tc_kernel<2, false, false>, tapgemm_tc_kernel<2, false, true>}, {tapgemm_tc_kernel<2, true, false>, tapgemm_tc_kernel<2, true, true>}},
-        {{tapgemm_tc_kernel<3, false, false>, tapgemm_tc_kernel<3, false, true>}, {tapgemm_tc_kernel<3, true, false>, tapgemm_tc_kernel<3, true, true>}}};
     const int amode = p.glu ? 3 : p.act;                 // the engine never combines GLU with an activation
     if (p.glu && p.act != AERO_ACT_NONE) { set_error("aero_tapgemm_fwd(tcgen05): GLU with an activation is not supported"); return AERO_ERR_UNSUPPORTED; }
-    const KernelFn kern = table[amode][g.residual ? 1 : 0][p.stats_mode ? 1 : 0];
+    const bool res = g.residual != nullptr, stats = p.stats_mode != 0;
+    const KernelFn kern = f16a ? (f16o ? pick_kernel<true, true>(amode, res, stats) : pick_kernel<true, false>(amode, res, stats))
+                               : (f16o ? pick_kernel<false, true>(amode, res, stats) : pick_kernel<false, false>(amode, res, stats));
+    if (!kern) {
+        set_error("aero_tapgemm_fwd(tcgen05): epilogue (act %d, residual %d, stats %d) is not built for operands %s / outputs %s",
+                  amode, (int)res, (int)stats, f16a ? "f16" : "tf32", f16o ? "f16" : "f32");
+        return AERO_ERR_UNSUPPORTED;
+    }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     // persistent grid: as many CTAs as can be co-resident (shared memory and TMEM columns), never more than tiles
     static int num_sms = 0;

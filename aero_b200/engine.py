@@ -71,6 +71,14 @@ def lstm_whh_fp16(whh_rows):
     return out.contiguous()
 
 
+def pack_kmajor_fp16(w_tkn):
+    """[taps, K, pad4(N)] fp32 -> [taps, pad4(N), pad8(K)] fp16: the kind::f16 tcgen05 weight layout (16-byte rows for TMA)."""
+    taps, k, n = w_tkn.shape
+    out = torch.zeros(taps, n, (k + 7) & ~7, dtype=torch.float16, device=w_tkn.device)
+    out[:, :, :k] = w_tkn.permute(0, 2, 1).to(torch.float16)
+    return out.contiguous()
+
+
 def glu_perm(n, device):
     """Column order that puts GLU partners (j, j + n/2) next to each other."""
     half = n // 2
@@ -106,10 +114,14 @@ class AeroEngine:
         self._bufs = {}
         self._windows = {}
         self._stats = None
-        self.precision = 1          # 1: TF32 tcgen05 tensor-core path where eligible (default); 0: all-fp32 SIMT path
+        # 2 (default): FP16-stored activations / tcgen05 kind::f16 operands, fp32 accumulate, fp32 GroupNorm inputs and
+        #    gate pre-activations -- TF32's 10-bit mantissa at half the HBM bytes and twice the tensor-core rate;
+        # 1: fp32-stored activations rounded to TF32 / tcgen05 kind::tf32;  0: exact fp32 SIMT kernels everywhere.
+        self.precision = 2
+        self.last_glu_fp32 = False  # keep the last decoder layer's GLU output (input of the final transposed conv) in fp32
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
         self._prof, self._prof_tags = None, set()
-        self._wk, self._wname = {}, {}
+        self._wk, self._wh, self._wname = {}, {}, {}
         # CUDA-graph replay of the launch sequence, per input shape: "auto" captures a shape the third time it is seen
         # (steady-state serving / evaluation loops), True captures on first sight, False always launches eagerly.
         self.use_graph = "auto"
@@ -140,13 +152,22 @@ class AeroEngine:
         if x.dtype != torch.float32:
             raise TypeError(f"aero_b200 computes in fp32; got {x.dtype}")
 
-    def _buf(self, name, *shape):
-        key = (name, shape)
+    def _buf(self, name, *shape, dtype=torch.float32):
+        key = (name, shape, dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=torch.float32, device=self._device())
+            t = torch.empty(shape, dtype=dtype, device=self._device())
             self._bufs[key] = t
         return t
+
+    def _adt(self, channels):
+        """Storage type of an activation tensor that feeds a tensor-core GEMM: FP16 in precision 2 when its rows are
+        16-byte multiples (TMA), else fp32 (rounded to TF32 by its producer when precision >= 1)."""
+        return torch.float16 if (self.precision == 2 and channels % 8 == 0) else torch.float32
+
+    def _raw(self, like, name):
+        """fp32 buffer for a pre-normalisation GEMM output whose normalised form is `like` (in place when `like` is fp32)."""
+        return like if like.dtype == torch.float32 else self._buf(name, *like.shape)
 
     def _window(self, win):
         key = (win, self._device())
@@ -268,12 +289,16 @@ class AeroEngine:
             W[p + ".ct.b"] = sd[p + ".conv_tr.bias"].contiguous()
         out = {k: (v.to(dev) if v.dtype == torch.float16 else v.to(device=dev, dtype=torch.float32)) for k, v in W.items()}
         # K-major TF32 twins of every tap-GEMM weight for the tcgen05 path: [taps, K, pad4(N)] -> [taps, pad4(N), K]
-        self._wk, self._wname = {}, {}
+        # ... and FP16 twins [taps, pad4(N), pad8(K)] for kind::f16
+        self._wk, self._wh, self._wname = {}, {}, {}
         for k in [k for k in out if k.endswith("ftbfc.w")]:
             out[k + "@k"] = tf32_round(out[k])          # [F', F] is already K-contiguous
+            out[k + "@h"] = pack_kmajor_fp16(out[k].t()[None].contiguous())[0]
         for k in [k for k in out if k.endswith(".w") and out[k].dim() == 3]:
             out[k + "@k"] = tf32_round(out[k].permute(0, 2, 1).contiguous())
+            out[k + "@h"] = pack_kmajor_fp16(out[k])
             self._wk[out[k].data_ptr()] = out[k + "@k"]
+            self._wh[out[k].data_ptr()] = out[k + "@h"]
             self._wname[out[k].data_ptr()] = k[:-2]
         return out
 
@@ -293,15 +318,23 @@ class AeroEngine:
         o_s = o_s or (F_out * T * n_out, T * n_out, n_out)
         r_s = r_s or (o_s if residual is not None else (0, 0, 0))
         tag = tag or self._wname.get(w.data_ptr())
-        flags = 1 if (rnd and self.precision == 1) else 0
+        src = a1 if a1 is not None else a2
+        a16 = src.dtype == torch.float16
+        o16 = out.dtype == torch.float16
+        if a1 is not None and a2 is not None and a1.dtype != a2.dtype:
+            raise TypeError("aero_b200: the two sources of a tap-GEMM must share a storage type")
+        if residual is not None and residual.dtype != out.dtype:
+            raise TypeError("aero_b200: residual and output of a tap-GEMM must share a storage type")
+        flags = (cabi.TG_ROUND_TF32 if (rnd and self.precision >= 1 and not o16) else 0) | (cabi.TG_A_F16 if a16 else 0) | \
+                (cabi.TG_OUT_F16 if o16 else 0)
         p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
                                act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 0, flags)
         if mode == cabi.TAPS_MIX:
-            p.precision = 1                      # tcgen05-only mode; `w` is already K-major / TF32
-        elif self.precision == 1 and w_sb == 0 and not (tag and self.fp32_tags and tag.startswith(self.fp32_tags)):
-            wk = self._wk.get(w.data_ptr())
+            p.precision = 2 if a16 else 1        # tcgen05-only mode; `w` is already the K-major twin of the right kind
+        elif self.precision >= 1 and w_sb == 0 and not (tag and self.fp32_tags and tag.startswith(self.fp32_tags)):
+            wk = (self._wh if a16 else self._wk).get(w.data_ptr())
             if wk is not None and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
-                p.precision, w = 1, wk
+                p.precision, w = (2 if a16 else 1), wk
         timed = self._prof is not None and tag in self._prof_tags
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,8 +370,12 @@ class AeroEngine:
 
     def _norm_act(self, x, stats, gamma, beta, y, *, B, F_in, T, C_, groups, scope, op, F_out=None, f_off=0,
                   snake_a=None, scale=None, residual=None, rnd=False):
+        o16 = y.dtype == torch.float16
+        if x.dtype != torch.float32 or (residual is not None and residual.dtype != y.dtype):
+            raise TypeError("aero_b200: norm_act reads fp32 and its residual shares the output's storage type")
         p = cabi.NormActParams(B, F_in, F_in if F_out is None else F_out, f_off, T, C_, groups, scope, op, 1e-5,
-                               1 if (rnd and self.precision == 1) else 0)
+                               (cabi.TG_ROUND_TF32 if (rnd and self.precision >= 1 and not o16) else 0) |
+                               (cabi.TG_OUT_F16 if o16 else 0))
         rc = self.lib.aero_norm_act_fwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(snake_a), _ptr(scale),
                                         _ptr(residual), _ptr(y), C.byref(p), self._stream())
         cabi.check(rc, self.lib)
@@ -346,13 +383,16 @@ class AeroEngine:
 
     def _lstm_rec(self, gin, bias_pad, whh, hout, *, rows, T, H, n_win, steps, stride, in_windowed, out_windowed,
                   tc=False):
+        o16 = hout.dtype == torch.float16
         p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed,
-                            1 if self.precision == 1 else 0, 1 if tc else 0)
+                            (cabi.TG_ROUND_TF32 if (self.precision >= 1 and not o16) else 0) | (cabi.TG_OUT_F16 if o16 else 0),
+                            1 if tc else 0)
         cabi.check(self.lib.aero_lstm_rec_fwd(_ptr(gin), _ptr(bias_pad), _ptr(whh), _ptr(hout), C.byref(p),
                                               self._stream()), self.lib)
 
     def _attn(self, qkvd, out, *, rows, T, H, heads, ndecay, ld):
-        p = cabi.AttnParams(rows, T, H, heads, ndecay, ld, 1 if self.precision == 1 else 0)
+        p = cabi.AttnParams(rows, T, H, heads, ndecay, ld, (cabi.TG_ROUND_TF32 if self.precision >= 1 else 0) |
+                            (cabi.TG_OUT_F16 if out.dtype == torch.float16 else 0))
         cabi.check(self.lib.aero_local_attn_fwd(_ptr(qkvd), _ptr(out), C.byref(p), self._stream()), self.lib)
 
     def _sample_norm(self, x, stats, y, affine, B, per_sample):
@@ -407,24 +447,27 @@ class AeroEngine:
     def _ftb(self, x, W, p, B, Fq, T, Cc, tag):
         """reference modules.py:304-325 (eval BatchNorm folded into the convs at pack time)."""
         r = 5
-        R = self._buf(tag + ".R", B, T, Fq * r)
+        R = self._buf(tag + ".R", B, T, Fq * r, dtype=self._adt(Fq * r))
         self._gemm(R, W[p + ".ftb1.w"], a1=x, B=B, F_out=Fq, T=T, N=r, C1=Cc, bias=W[p + ".ftb1.b"], act=ACT_RELU,
                    o_s=(T * Fq * r, r, Fq * r), rnd=True)
         G = self._buf(tag + ".G", B, T, Cc)
         self._gemm(G, W[p + ".ftb1d.w"], a1=R, B=B, F_out=1, T=T, N=Cc, C1=Fq * r, kt=9, pad_t=4,
                    bias=W[p + ".ftb1d.b"], act=ACT_RELU, a1_s=(T * Fq * r, 0, Fq * r), o_s=(T * Cc, 0, Cc))
-        Y = self._buf(tag + ".Y", B, Fq, T, Cc)
-        if self.precision == 1 and Fq % 4 == 0 and Fq >= 8 and not (self.fp32_tags and (p + ".ftbfc").startswith(self.fp32_tags)):
+        Y = self._buf(tag + ".Y", B, Fq, T, Cc, dtype=x.dtype)
+        x16 = x.dtype == torch.float16
+        q = 8 if x16 else 4
+        if self.precision >= 1 and Fq % q == 0 and Fq >= 8 and (T * Cc) % q == 0 and \
+                not (self.fp32_tags and (p + ".ftbfc").startswith(self.fp32_tags)):
             # frequency mixing on the tensor cores: contraction over the row axis, activations as the MN-major operand
-            self._gemm(Y, W[p + ".ftbfc.w@k"], a1=x, mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc, N=Fq, C1=Fq,
-                       a1_s=(Fq * T * Cc, 0, T * Cc), o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True,
-                       tag=p + ".ftbfc")
+            self._gemm(Y, W[p + (".ftbfc.w@h" if x16 else ".ftbfc.w@k")], a1=x, mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc,
+                       N=Fq, C1=Fq, a1_s=(Fq * T * Cc, 0, T * Cc), o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0),
+                       rnd=True, tag=p + ".ftbfc")
         else:
             # fp32 path: a GEMM whose "weights" are the activations: out[f'] = sum_f Wfc[f',f] x[f], times the gate
-            self._gemm(Y, x, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq, a1_s=(0, 0, Fq),
-                       w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True,
+            self._gemm(Y, x.float() if x16 else x, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * Cc, C1=Fq,
+                       a1_s=(0, 0, Fq), w_sb=Fq * T * Cc, o_s=(Fq * T * Cc, 0, T * Cc), colscale=G, cs_s=(T * Cc, 0), rnd=True,
                        tag=p + ".ftbfc")
-        out = self._buf(tag + ".out", B, Fq, T, Cc)
+        out = self._buf(tag + ".out", B, Fq, T, Cc, dtype=x.dtype)
         self._gemm(out, W[p + ".ftb2.w"], a1=Y, a2=x, B=1, F_out=1, T=B * Fq * T, N=Cc, C1=Cc, C2=Cc,
                    bias=W[p + ".ftb2.b"], act=ACT_RELU, rnd=True)
         return out
@@ -437,16 +480,16 @@ class AeroEngine:
         else:
             steps, stride, n_win = T, 0, 1
         n_seq = rows * n_win
-        tc = self.precision == 1 and H % 4 == 0 and 32 < H <= 96
+        tc = self.precision >= 1 and H % 4 == 0 and 32 < H <= 96
         L0, L1, G = ("lstm0r", "lstm1r", 2 * (2 if H <= 64 else 4) * 128) if tc else ("lstm0", "lstm1", 8 * H)
         gin1 = self._buf(tag + ".gin1", rows * T, G)
         self._gemm_flat(gin1, h, W[f"{o}.{L0}.ih.w"], rows * T, H, G, bias=W[f"{o}.{L0}.b"])
-        h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H)
+        h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H, dtype=self._adt(2 * H))
         self._lstm_rec(gin1, W[f"{o}.{L0}.b"], W[f"{o}.{L0}.whh"], h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
                        stride=stride, in_windowed=0, out_windowed=1, tc=tc)
         gin2 = self._buf(tag + ".gin2", n_seq * steps, G)
         self._gemm_flat(gin2, h1, W[f"{o}.{L1}.ih.w"], n_seq * steps, 2 * H, G, bias=W[f"{o}.{L1}.b"])
-        h2 = self._buf(tag + ".h2", rows * T, 2 * H)
+        h2 = self._buf(tag + ".h2", rows * T, 2 * H, dtype=self._adt(2 * H))
         self._lstm_rec(gin2, W[f"{o}.{L1}.b"], W[f"{o}.{L1}.whh"], h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
                        stride=stride, in_windowed=1, out_windowed=0, tc=tc)
         self._gemm_flat(h, h2, W[o + ".lin.w"], rows * T, 2 * H, H, bias=W[o + ".lin.b"], residual=h, rnd=True)
@@ -457,7 +500,7 @@ class AeroEngine:
         ld = 3 * H + _ATTN_HEADS * _ATTN_NDECAY
         qkvd = self._buf(tag + ".qkvd", rows * T, ld)
         self._gemm_flat(qkvd, h, W[o + ".qkvd.w"], rows * T, H, ld, bias=W[o + ".qkvd.b"])
-        r = self._buf(tag + ".attn", rows * T, H)
+        r = self._buf(tag + ".attn", rows * T, H, dtype=self._adt(H))
         self._attn(qkvd, r, rows=rows, T=T, H=H, heads=_ATTN_HEADS, ndecay=_ATTN_NDECAY, ld=ld)
         self._gemm_flat(h, r, W[o + ".proj.w"], rows * T, H, H, bias=W[o + ".proj.b"], residual=h, rnd=True)
         return h
@@ -472,10 +515,11 @@ class AeroEngine:
             o = f"encoder.{g.index}.dc{d}"
             dil = 2 ** d
             st1 = self._stats.take(rows)
-            h = self._buf(f"{tag}.h", B, Fq, T, hid)
-            self._gemm(h, W[o + ".c1.w"], a1=y, B=B, F_out=Fq, T=T, N=hid, C1=Cc, kt=3, dil_t=dil, pad_t=dil,
+            h = self._buf(f"{tag}.h", B, Fq, T, hid, dtype=self._adt(hid))
+            h_raw = self._raw(h, f"{tag}.h32")
+            self._gemm(h_raw, W[o + ".c1.w"], a1=y, B=B, F_out=Fq, T=T, N=hid, C1=Cc, kt=3, dil_t=dil, pad_t=dil,
                        bias=W[o + ".c1.b"], stats=st1, stats_mode=2)
-            self._norm_act(h, st1, W[o + ".n1.g"], W[o + ".n1.b"], h, B=B, F_in=Fq, T=T, C_=hid, groups=1, scope=2,
+            self._norm_act(h_raw, st1, W[o + ".n1.g"], W[o + ".n1.b"], h, B=B, F_in=Fq, T=T, C_=hid, groups=1, scope=2,
                            op=NA_SNAKE, snake_a=W[o + ".a"], rnd=True)
             if g.lstm:
                 self._blstm(h, W, o, rows, T, hid, f"{tag}.lstm")
@@ -497,25 +541,26 @@ class AeroEngine:
         Fi, Fo, Cc = g.f_in, g.f_out, g.ch
         cin = g.enc_cin
         if g.index == 0:
-            pre = self._buf(tag + ".pre", B, Fi, T, Cc)
+            pre = self._buf(tag + ".pre", B, Fi, T, Cc, dtype=self._adt(Cc))
             self._gemm_flat(pre, x, W[p + ".pre.w"], B * Fi * T, cin, Cc, bias=W[p + ".pre.b"], rnd=True)
             x, cin = pre, Cc
         if g.ftb:
             x = self._ftb(x, W, p, B, Fi, T, cin, tag + ".ftb")
-        y = self._buf(tag + ".conv", B, Fo, T, Cc)
+        y = self._buf(tag + ".conv", B, Fo, T, Cc, dtype=self._adt(Cc))
         if g.norm:
             st = self._stats.take(B * kw["norm_groups"])
-            self._gemm(y, W[p + ".conv.w"], a1=x, B=B, F_out=Fo, F_in=Fi, T=T, N=Cc, C1=cin, kf=g.kernel,
+            y_raw = self._raw(y, tag + ".conv32")
+            self._gemm(y_raw, W[p + ".conv.w"], a1=x, B=B, F_out=Fo, F_in=Fi, T=T, N=Cc, C1=cin, kf=g.kernel,
                        stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], stats=st, stats_mode=1,
                        groups=kw["norm_groups"])
-            self._norm_act(y, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fo, T=T, C_=Cc,
+            self._norm_act(y_raw, st, W[p + ".norm1.g"], W[p + ".norm1.b"], y, B=B, F_in=Fo, T=T, C_=Cc,
                            groups=kw["norm_groups"], scope=1, op=NA_GELU, rnd=True)
         else:
             self._gemm(y, W[p + ".conv.w"], a1=x, B=B, F_out=Fo, F_in=Fi, T=T, N=Cc, C1=cin, kf=g.kernel,
                        stride_f=g.stride, pad_f=g.pad, bias=W[p + ".conv.b"], act=ACT_GELU, rnd=True)
         if g.dconv:
             y = self._dconv(y, W, g, B, T, tag + ".dc")
-        out = self._buf(tag + ".out", B, Fo, T, Cc)
+        out = self._buf(tag + ".out", B, Fo, T, Cc, dtype=self._adt(Cc))
         if g.norm:
             st = self._stats.take(B * kw["norm_groups"])
             raw = self._buf(tag + ".rw", B, Fo, T, 2 * Cc)
@@ -535,7 +580,8 @@ class AeroEngine:
         tag = f"d{j}"
         Fq, Cc = g.f_out, g.ch
         c1 = 0 if x is None else Cc
-        y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc)
+        y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc,
+                      dtype=torch.float32 if (last and self.last_glu_fp32) else self._adt(2 * Cc))
         common = dict(a1=x, a2=skip, B=B, F_out=Fq, T=T, N=4 * Cc, C1=c1, C2=Cc, kf=3, kt=3, pad_f=1, pad_t=1,
                       bias=W[p + ".rw.b"])
         if g.norm:
@@ -550,7 +596,7 @@ class AeroEngine:
         cout = g.dec_cout
         f_full = (Fq - 1) * g.stride + g.kernel
         f_keep = f_full - 2 * g.pad
-        z = self._buf(tag + ".out", B, f_keep, T, cout)
+        z = self._buf(tag + ".out", B, f_keep, T, cout, dtype=torch.float32 if last else self._adt(cout))
         if g.norm:
             st = self._stats.take(B * kw["norm_groups"])
             raw = self._buf(tag + ".ct", B, f_full, T, cout)

@@ -39,8 +39,9 @@ GFLOP_PER_CLIP = 124.16          # reference-equivalent; 102.9 wi
 GFLOP_PER_CLIP_REQUIRED = 102.9
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the family (decoder.0 rewrite, B=32) from the
 # `ncu --set full` capture summarised in profiles/ (algorithmic bytes of that launch: 514 MB); None until captured
-TRAFFIC_NCU = {"kernel": "tapgemm_tc_kernel<0,0,1> decoder.0.rw B=32", "bytes_per_launch": 473.8e6, "algorithmic_bytes": 513.7e6,
-               "tensor_pipe_pct": 80.8, "source": "profiles/r1_dec0rw_tc_ncu.md"}
+TRAFFIC_NCU = {1: {"kernel": "tapgemm_tc_kernel<0,0,1,tf32> decoder.0.rw B=32", "bytes_per_launch": 473.8e6, "algorithmic_bytes": 513.7e6,
+                   "tensor_pipe_pct": 80.8, "source": "profiles/r1_dec0rw_tc_ncu.md"},
+               2: None}
 
 
 def peaks():
@@ -56,7 +57,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.period = index, [], False, 0.02
 
     def run(self):
         try:                                   # NVML in-process: millisecond polls, no fork on the launching host
@@ -75,7 +76,7 @@ class ClockSampler(threading.Thread):
                 for bit, col in bits:
                     row[col] = "Active" if r & bit else "Not Active"
                 self.rows.append(row)
-                time.sleep(0.02)
+                time.sleep(self.period)
             return
         except Exception:
             pass
@@ -193,7 +194,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=None,
-                    help="engine precision: 1 (default) TF32 tcgen05 tensor-core path, 0 every kernel in exact fp32")
+                    help="engine precision: 2 (default) FP16-stored activations / kind::f16 tcgen05, 1 fp32 storage / kind::tf32, "
+                         "0 every kernel in exact fp32")
     ap.add_argument("--_cpu_probe", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args._cpu_probe:
@@ -254,7 +256,9 @@ def main():
     prof = eng.stop_profile()
     ms_dev = ev0.elapsed_time(ev1) / args.steps
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with host buffers (NVML queries contend with CUDA API calls for driver locks:
+    #      poll slowly while every step synchronises)
+    sampler.period = 0.1
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
@@ -280,25 +284,29 @@ def main():
         flops = sum(v["flops"] for v in prof.values())
         ms_k = sum(v["ms"] for v in prof.values())
         n_l = sum(v["launches"] for v in prof.values())
-        tf32 = eng.precision == 1
-        peak = pk["bf16_tflops"] / 2
+        prec = eng.precision
+        tf32 = prec == 1
+        # kind::f16 runs at the bf16 rate the driver measured with cuBLAS; kind::tf32 at half of it (no TF32 figure is measured)
+        peak = pk["bf16_tflops"] / (2 if tf32 else 1)
         clk = sampler.summary()
-        pipe = 4096 * 148 * (clk.get("sm_mhz") or 1965) * 1e6 / 1e12     # tcgen05 kind::tf32: 4096 flop/clk/SM (ncu sm__inst pipe rate)
+        pipe = (4096 if tf32 else 8192) * 148 * (clk.get("sm_mhz") or 1965) * 1e6 / 1e12     # tcgen05 flop/clk/SM (ncu pipe rate)
         ach = flops / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "tap-GEMM, decoder 3x3 rewrite convs (4 launches/step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "peak_source": pk["source"] + "; TF32 dense peak taken as half the measured bf16 cuBLAS throughput (no TF32 figure is "
+                "peak_source": pk["source"] + ("; TF32 dense peak taken as half the measured bf16 cuBLAS throughput (no TF32 figure is "
                                "measured; cuBLAS bf16 is power-capped near 1.37 GHz while this kernel holds max clock, so the fraction can "
-                               "read above 1: frac_tf32_pipe is the stricter fraction of the tensor pipe's own rate at the sampled clock)",
-                "peak_tf32_pipe": pipe, "frac_tf32_pipe": ach / pipe,
-                "precision": "tf32 tcgen05" if tf32 else "fp32 SIMT (no tensor pipe)",
+                               "read above 1)" if tf32 else "; cuBLAS bf16 = the kind::f16 rate") +
+                               "; frac_tensor_pipe is the stricter fraction of the tensor pipe's own rate at the sampled clock",
+                "peak_tensor_pipe": pipe, "frac_tensor_pipe": ach / pipe,
+                "precision": {2: "f16 operands tcgen05 (kind::f16), fp32 accumulate", 1: "tf32 tcgen05", 0: "fp32 SIMT (no tensor pipe)"}[prec],
                 "ms_per_step_in_kernel": ms_k / args.steps, "share_of_step": (ms_k / args.steps) / ms_dev,
                 "launches_timed": n_l,
                 "per_layer_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0) for k, v in sorted(prof.items())},
-                "traffic": TRAFFIC_NCU}
+                "traffic": TRAFFIC_NCU.get(prec)}
         line = {"metric": "audio-seconds/sec forward", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)" if tf32 else "f32", "data": "synthetic",
+                "dtype": {2: "f16 tensor-core operands and activation storage (10-bit mantissa = tf32), fp32 accumulate / norm inputs / cell state",
+                          1: "f32 (tf32 tensor-core operands, fp32 accumulate)", 0: "f32"}[prec], "data": "synthetic",
                 "config": {"workload": f"{EXPERIMENT} inference forward, batch {B}/GPU x 2 s white-noise clips 4->16 kHz",
                            "global_batch": total_clips, "parallelism": f"batch-sharded x{world}, no collective",
                            "l2": "activations (>700 MB/step) exceed the 126 MB L2; no explicit flush",

@@ -38,7 +38,7 @@ enum aero_status {
     AERO_ERR_NO_DEVICE = -4
 };
 
-int aero_abi_version(void);
+int aero_abi_version(void);            /* 2: storage-type flags (AERO_TG_*), precision 2 */
 const char* aero_last_error(void);
 /* compute capability of the current device as 10*major+minor (100 on B200); <0 if no device */
 int aero_device_arch(void);
@@ -93,7 +93,7 @@ int aero_istft_fwd(const float* z, const float* window, float* y,
  *   mode AERO_TAPS_CONVT : fo' = fo + f_out_offset (row in the uncropped output),
  *                          jf in [0, kf/stride_f): kf_idx = fo' % stride_f + jf*stride_f,
  *                          fi = fo' / stride_f - jf,  slab = kf_idx  (nn.ConvTranspose2d [k,1]/[s,1])
- *   mode AERO_TAPS_MIX   : (precision 1 only) contraction over the ROW axis of a channels-last tensor, FTB's
+ *   mode AERO_TAPS_MIX   : (precision 1 / 2 only) contraction over the ROW axis of a channels-last tensor, FTB's
  *                          `freq_fc` (modules.py:296,317-320):  out[b][n][m] = colscale[b][m] * sum_{k<C1} a1[b][k][m] * W[n][k],
  *                          m < T pixels (contiguous), a1 element (b,k,m) at a1 + b*a1_sb + k*a1_st + m, out element
  *                          at out + b*o_sb + n*o_st + m, colscale at colscale + b*cs_sb + m.  F_out = F_in = 1.
@@ -107,7 +107,7 @@ int aero_istft_fwd(const float* z, const float* window, float* y,
  *   v = residual[b][fo][t][n'] + v  ;  v = v * samp_affine[b][0] + samp_affine[b][1] (aero.py:497-498);
  *   statistics of the stored value:  stats_mode 1: per (b, group), group = n' / (N' / groups);
  *   stats_mode 2: per (b, fo) row.   N' = N/2 with GLU, else N.
- * Generic strides (in floats) let one kernel serve NCHW-free layouts: element (b,f,t,c) of a
+ * Generic strides (in elements) let one kernel serve NCHW-free layouts: element (b,f,t,c) of a
  * source is at  src + b*sb + f*sf + t*st + c.
  */
 enum { AERO_TAPS_CONV = 0, AERO_TAPS_CONVT = 1, AERO_TAPS_MIX = 2 };
@@ -124,16 +124,25 @@ typedef struct {
     int64_t o_sb, o_sf, o_st;
     int64_t r_sb, r_sf, r_st;         /* residual strides */
     int64_t cs_sb, cs_st;             /* colscale strides */
-    int32_t precision;                /* 0: fp32 SIMT tiles, weights N-contiguous  W[slab][K][pad4(N)];
-                                         1: TF32 tcgen05 tiles, weights K-contiguous W[slab][pad4(N)][K] rounded to TF32;
-                                            AERO_ERR_UNSUPPORTED unless aero_tapgemm_tc_eligible() */
-    int32_t flags;                    /* bit 0: round stored outputs to TF32 (round-to-nearest) for a tensor-core consumer */
+    int32_t precision;                /* 0: fp32 SIMT tiles, fp32 weights N-contiguous  W[slab][K][pad4(N)] (sources / outputs of either type);
+                                         1: tcgen05 kind::tf32, fp32 sources, fp32 weights K-contiguous W[slab][pad4(N)][K] rounded to TF32;
+                                         2: tcgen05 kind::f16, FP16 sources, FP16 weights K-contiguous W[slab][pad4(N)][pad8(K)];
+                                            1 / 2: AERO_ERR_UNSUPPORTED unless aero_tapgemm_tc_eligible() */
+    int32_t flags;                    /* AERO_TG_* */
 } aero_tapgemm_params;
-int aero_tapgemm_fwd(const float* a1, const float* a2, const float* w, const float* bias,
-                     const float* addend_fn, const float* colscale, const float* residual,
-                     const float* samp_affine, float* out, double* stats,
+/* Storage types.  Activations that feed a tensor-core GEMM are stored either as fp32 rounded to TF32 or as FP16 (the same
+ * 10-bit mantissa at half the bytes; stores saturate at +-65504); every kernel computes in fp32 between load and store.
+ * Strides are in ELEMENTS of the tensor they address. */
+enum {
+    AERO_TG_ROUND_TF32 = 1,           /* fp32 outputs: round stored values to TF32 (round-to-nearest) for a kind::tf32 consumer */
+    AERO_TG_A_F16 = 2,                /* a1 / a2 are FP16 */
+    AERO_TG_OUT_F16 = 4               /* out and residual are FP16 */
+};
+int aero_tapgemm_fwd(const void* a1, const void* a2, const void* w, const float* bias,
+                     const float* addend_fn, const float* colscale, const void* residual,
+                     const float* samp_affine, void* out, double* stats,
                      const aero_tapgemm_params* p, aero_stream_t stream);
-/* 1 when the shape can run on the tcgen05 path (precision 1), else 0 */
+/* 1 when the shape can run on the tcgen05 path (kind::tf32, or kind::f16 when flags has AERO_TG_A_F16), else 0 */
 int aero_tapgemm_tc_eligible(const aero_tapgemm_params* p);
 
 /* ------------------------------------------------------------------------------------------
@@ -161,10 +170,11 @@ typedef struct {
     int32_t B, F_in, F_out, f_off, T, C;
     int32_t groups, scope, op;
     float eps;
-    int32_t round_tf32;               /* round stored outputs to TF32 for a tensor-core consumer */
+    int32_t flags;                    /* AERO_TG_ROUND_TF32: round stored fp32 outputs to TF32 for a tensor-core consumer;
+                                         AERO_TG_OUT_F16: y and residual are FP16 (x is always fp32: GroupNorm inputs stay fp32) */
 } aero_norm_act_params;
 int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
-                      const float* snake_a, const float* scale, const float* residual, float* y,
+                      const float* snake_a, const float* scale, const void* residual, void* y,
                       const aero_norm_act_params* p, aero_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -186,7 +196,7 @@ typedef struct {
     int32_t rows, T, H;
     int32_t n_win, steps, win_stride;
     int32_t in_windowed, out_windowed;
-    int32_t round_tf32;
+    int32_t flags;                    /* AERO_TG_ROUND_TF32: round the stored fp32 h to TF32; AERO_TG_OUT_F16: hout is FP16 */
     int32_t precision;                /* 0: fp32 SIMT recurrence (layouts above);
                                          1: tcgen05 recurrence, FP16 operands (h in (-1,1), W_hh O(1): same 10-bit mantissa as TF32), fp32 accumulate.  Gate rows are re-ordered into 4/GPT tiles of 128 per
                                             direction (GPT = 2 if H <= 64 else 1): GPT=1: tile g = gate g, row = cell;
@@ -195,7 +205,7 @@ typedef struct {
                                             Kp = 64*ceil(H/64) (zero rows beyond H, zero columns beyond H) and `gin` / `bias_pad` rows have
                                             2*(4/GPT)*128 columns in the same order.  H % 4 == 0, 32 < H <= 96. */
 } aero_lstm_params;
-int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout,
+int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const void* whh, void* hout,
                       const aero_lstm_params* p, aero_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -207,10 +217,11 @@ int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const float* whh,
  */
 typedef struct {
     int32_t rows, T, H, heads, ndecay, ld;
-    int32_t round_tf32;               /* 1: tensor-core mode -- QK^T and PV on mma.sync TF32 (fp32 accumulate, head dim 12 / 24),
-                                         outputs rounded to TF32 for the projection GEMM; 0: exact fp32 SIMT kernel */
+    int32_t flags;                    /* AERO_TG_ROUND_TF32: tensor-core mode -- QK^T and PV on mma.sync TF32 (fp32 accumulate, head dim
+                                         12 / 24), outputs rounded to TF32 for the projection GEMM; without it the exact fp32 SIMT kernel.
+                                         AERO_TG_OUT_F16: out is FP16 */
 } aero_attn_params;
-int aero_local_attn_fwd(const float* qkvd, float* out, const aero_attn_params* p, aero_stream_t stream);
+int aero_local_attn_fwd(const float* qkvd, void* out, const aero_attn_params* p, aero_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Log-spectral distance (reference src/metrics.py:37-70 `get_lsd`, STFTMag(2048, 512)).

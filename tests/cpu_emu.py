@@ -30,6 +30,9 @@ class EmuEngine(AeroEngine):
         self._windows = {}
         self._stats = None
         self.precision = 0
+        self.last_glu_fp32 = False
+        self._seen = {}
+        self._wh = {}
         self._prof, self._prof_tags = None, set()
         self._wk, self._wname = {}, {}
         self.fp32_tags = ()

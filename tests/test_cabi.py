@@ -36,7 +36,7 @@ def test_no_torch_types_in_abi():
 
 
 def test_version_and_error_channel(lib):
-    assert lib.aero_abi_version() == 1
+    assert lib.aero_abi_version() == 2
     # parameter validation happens before any device work: a null call must fail cleanly
     rc = lib.aero_stft_fwd(None, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.aero_last_error()

@@ -221,57 +221,88 @@ TC_CASES = [c for c in GEMM_CASES if c[0] not in ("k2_thin_in", "thin_out_relu",
 ]
 
 
-@pytest.mark.parametrize("name,cfg", TC_CASES, ids=[c[0] for c in TC_CASES])
-def test_tapgemm_tcgen05(engines, name, cfg):
-    from aero_b200.engine import tf32_round
-    gpu, emu = engines
+def _run_gemm_case(gpu, emu, cfg, storage, precision):
+    """One tap-GEMM case on the GPU with the given activation storage ('tf32': fp32 rounded to TF32, 'f16': FP16 sources,
+    FP16 outputs unless the case collects statistics) against the fp64 CPU statement on the same (pre-rounded) numbers."""
+    from aero_b200.engine import pack_kmajor_fp16, tf32_round
     cfg = dict(cfg)
     B, F_out, T, N, C1 = cfg["B"], cfg["F_out"], cfg["T"], cfg["N"], cfg["C1"]
     C2, F_in = cfg.get("C2", 0), cfg.get("F_in", F_out)
     mode = cfg.get("mode", cabi.TAPS_CONV)
     nslab = cfg.get("kf", 1) * cfg.get("kt", 1)
     K = C1 + C2
-    w = tf32_round(pack_taps(rnd(N, K, nslab, seed=1) / math.sqrt(K * (nslab if mode == cabi.TAPS_CONV else 2))))
-    a1 = tf32_round(rnd(B, F_in, T, C1, seed=2)) if C1 else None
-    a2 = tf32_round(rnd(B, F_in, T, C2, seed=3)) if C2 else None
+    f16 = storage == "f16"
+    a_f16 = f16 and C1 % 4 == 0 and C2 % 4 == 0 and K > 4          # the K=2 layer reads the fp32 spectrogram
+    q = (lambda t: t.half().float()) if f16 else tf32_round
+    w = q(pack_taps(rnd(N, K, nslab, seed=1) / math.sqrt(K * (nslab if mode == cabi.TAPS_CONV else 2))))
+    a1 = (q(rnd(B, F_in, T, C1, seed=2)) if a_f16 or not f16 else rnd(B, F_in, T, C1, seed=2)) if C1 else None
+    a2 = q(rnd(B, F_in, T, C2, seed=3)) if C2 else None
     bias = rnd(N, seed=4)
     glu = cfg.get("glu", 0)
     n_out = N // 2 if glu else N
     extra = {}
     if cfg.pop("residual", False):
-        extra["residual"] = rnd(B, F_out, T, n_out, seed=5)
+        extra["residual"] = q(rnd(B, F_out, T, n_out, seed=5))
     if cfg.pop("addend", False):
         extra["addend"] = rnd(F_out, n_out, seed=6)
+    if cfg.pop("affine", False):
+        extra["samp_affine"] = rnd(B, 2, seed=7).abs() + 0.5
     sm = cfg.get("stats_mode", 0)
+    o_f16 = f16 and sm == 0 and "samp_affine" not in extra
     nslots = {0: 0, 1: B * cfg.get("groups", 1), 2: B * F_out}[sm]
     for k in ("B", "F_out", "T", "N", "C1"):
         cfg.pop(k)
     res = {}
     for tag, eng, dev in (("cpu", emu, "cpu"), ("gpu", gpu, "cuda")):
-        def mv(t):
-            return None if t is None else t.to(dev)
-        out = torch.full((B, F_out, T, n_out), float("nan"), device=dev)
+        on_gpu = tag == "gpu"
+
+        def mv(t, half=False):
+            if t is None:
+                return None
+            t = t.to(dev)
+            return t.half() if (half and on_gpu) else t
+        out = torch.full((B, F_out, T, n_out), float("nan"), device=dev, dtype=torch.float16 if (o_f16 and on_gpu) else torch.float32)
         stats = torch.zeros(max(nslots, 1), 2, dtype=torch.float64, device=dev)
         wd = mv(w)
-        if tag == "gpu":
-            eng.precision = 1
+        kw = {k: mv(v, half=(k == "residual" and o_f16)) for k, v in extra.items()}
+        if on_gpu:
+            eng.precision = precision
             eng._wk[wd.data_ptr()] = tf32_round(wd.permute(0, 2, 1).contiguous())
-            before = eng.lib.aero_launch_count()
+            eng._wh[wd.data_ptr()] = pack_kmajor_fp16(wd)
         try:
-            eng._gemm(out, wd, a1=mv(a1), a2=mv(a2), B=B, F_out=F_out, T=T, N=N, C1=C1, bias=mv(bias),
-                      stats=stats if sm else None, **{k: mv(v) for k, v in extra.items()}, **cfg)
-            if tag == "gpu":
+            eng._gemm(out, wd, a1=mv(a1, a_f16), a2=mv(a2, a_f16), B=B, F_out=F_out, T=T, N=N, C1=C1, bias=mv(bias),
+                      stats=stats if sm else None, **kw, **cfg)
+            if on_gpu:
                 torch.cuda.synchronize()
         finally:
-            if tag == "gpu":
+            if on_gpu:
                 eng.precision = 0
                 eng._wk.clear()
-        res[tag] = (out.cpu(), stats.cpu())
+                eng._wh.clear()
+        res[tag] = (out.float().cpu(), stats.cpu())
     assert torch.isfinite(res["gpu"][0]).all()
-    # products are exact; what is left is the tensor core's fp32 accumulation order/rounding, which grows with K
-    assert rel_l2(res["gpu"][0], res["cpu"][0]) < (5e-5 if K * nslab > 4096 else 5e-6)
+    err = rel_l2(res["gpu"][0], res["cpu"][0])
+    if o_f16:
+        assert err < 4e-4, err               # one FP16 rounding of the stored value (rms 2^-11/sqrt(3) relative to its binade)
+    else:
+        # products are exact; what is left is the fp32 accumulation order/rounding, which grows with K
+        assert err < (5e-5 if K * nslab > 4096 else 5e-6), err
     if sm:
         assert torch.allclose(res["gpu"][1], res["cpu"][1], rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("storage", ["tf32", "f16"])
+@pytest.mark.parametrize("name,cfg", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tapgemm_tcgen05(engines, name, cfg, storage):
+    gpu, emu = engines
+    _run_gemm_case(gpu, emu, cfg, storage, 2 if storage == "f16" else 1)
+
+
+@pytest.mark.parametrize("name,cfg", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
+def test_tapgemm_simt_fp16_storage(engines, name, cfg):
+    """The fp32 SIMT kernels (generic tile and the thin-N / thin-K / thin-transposed ones) reading and writing FP16 tensors."""
+    gpu, emu = engines
+    _run_gemm_case(gpu, emu, cfg, "f16", 0)
 
 
 def test_tcgen05_is_selected_for_the_big_convs(engines):
@@ -322,19 +353,56 @@ def test_lstm_layer_pair_tcgen05(engines, H, T, rows):
     assert e1 < 2e-3 and e2 < 2e-3
 
 
+@pytest.mark.parametrize("storage", ["tf32", "f16"])
 @pytest.mark.parametrize("B,Fq,T,Cc", [(2, 256, 37, 48), (1, 64, 131, 48), (3, 16, 50, 96), (2, 8, 77, 192)])
-def test_freq_mix_tcgen05_mn_major(engines, B, Fq, T, Cc):
-    """AERO_TAPS_MIX: contraction over the frequency rows with the activations as the MN-major UMMA operand."""
-    from aero_b200.engine import tf32_round
+def test_freq_mix_tcgen05_mn_major(engines, B, Fq, T, Cc, storage):
+    """AERO_TAPS_MIX: contraction over the frequency rows with the activations as the MN-major UMMA operand
+    (tf32: SWIZZLE_128B_BASE32B atoms; f16: plain SWIZZLE_128B atoms)."""
+    from aero_b200.engine import pack_kmajor_fp16, tf32_round
     gpu, _ = engines
-    x, wfc, gate = tf32_round(rnd(B, Fq, T, Cc, seed=1)), tf32_round(rnd(Fq, Fq, seed=2) / math.sqrt(Fq)), rnd(B, T, Cc, seed=3)
-    y = torch.full((B, Fq, T, Cc), float("nan"), device="cuda")
-    gpu._gemm(y, wfc.cuda(), a1=x.cuda(), mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc, N=Fq, C1=Fq,
+    f16 = storage == "f16"
+    q = (lambda t: t.half().float()) if f16 else tf32_round
+    x, wfc, gate = q(rnd(B, Fq, T, Cc, seed=1)), q(rnd(Fq, Fq, seed=2) / math.sqrt(Fq)), rnd(B, T, Cc, seed=3)
+    y = torch.full((B, Fq, T, Cc), float("nan"), device="cuda", dtype=torch.float16 if f16 else torch.float32)
+    wd = pack_kmajor_fp16(wfc.t()[None].contiguous())[0].cuda() if f16 else wfc.cuda()
+    gpu._gemm(y, wd, a1=x.half().cuda() if f16 else x.cuda(), mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc, N=Fq, C1=Fq,
               a1_s=(Fq * T * Cc, 0, T * Cc), o_s=(Fq * T * Cc, 0, T * Cc), colscale=gate.cuda(), cs_s=(T * Cc, 0))
     torch.cuda.synchronize()
     ref = torch.einsum("gf,bftc->bgtc", wfc.double(), x.double()) * gate[:, None].double()
     assert torch.isfinite(y).all()
-    assert rel_l2(y.cpu(), ref) < 5e-6
+    assert rel_l2(y.float().cpu(), ref) < (4e-4 if f16 else 5e-6)
+
+
+def test_fp16_outputs_of_the_other_kernels(engines):
+    """norm_act / LSTM recurrence / attention writing FP16: the fp32 result of the same call, rounded once."""
+    gpu, _ = engines
+    B, F_in, T, Cc = 2, 6, 77, 48
+    x = (rnd(B, F_in, T, Cc, seed=1) * 1.7 + 0.3).cuda()
+    xd = x.double().view(B * F_in, -1)
+    stats = torch.stack([xd.sum(1), (xd * xd).sum(1)], 1)
+    gamma, beta, scale = (1 + 0.2 * rnd(Cc, seed=2)).cuda(), (0.1 * rnd(Cc, seed=3)).cuda(), rnd(Cc // 2, seed=5).cuda()
+    resid = rnd(B, F_in, T, Cc // 2, seed=6).half()
+    ys = []
+    for dt in (torch.float32, torch.float16):
+        y = torch.zeros(B, F_in, T, Cc // 2, device="cuda", dtype=dt)
+        gpu._norm_act(x, stats, gamma, beta, y, B=B, F_in=F_in, T=T, C_=Cc, groups=1, scope=2, op=cabi.NA_GLU_SCALE_RES,
+                      scale=scale, residual=resid.cuda().to(dt))
+        ys.append(y.float().cpu())
+    assert rel_l2(ys[1], ys[0]) < 4e-4 and torch.equal(ys[1], ys[0].half().float())
+    H, Tt, rows = 48, 130, 2
+    ld = 3 * H + 16
+    qkvd = rnd(rows * Tt, ld, seed=1).cuda()
+    gpu.precision = 1
+    try:
+        outs_ = []
+        for dt in (torch.float32, torch.float16):
+            o = torch.zeros(rows * Tt, H, device="cuda", dtype=dt)
+            gpu._attn(qkvd, o, rows=rows, T=Tt, H=H, heads=4, ndecay=4, ld=ld)
+            outs_.append(o.float().cpu())
+    finally:
+        gpu.precision = 0
+    assert rel_l2(outs_[1], outs_[0]) < 4e-4
+
 
 
 @pytest.mark.parametrize("H,T,rows", [(48, 501, 3), (96, 251, 2), (48, 700, 1), (96, 33, 4), (48, 130, 2)])

@@ -80,19 +80,22 @@ def test_repeatable_and_buffer_reuse():
     assert rel_l2(m(a).cpu(), o3.cpu()) < 1e-6
 
 
+@pytest.mark.parametrize("precision", [2, 1])
 @pytest.mark.parametrize("case", CASES)
-def test_forward_tf32_tensor_core_path_within_tolerance(golden_dir, case):
-    """Default engine (precision=1): TF32 tcgen05 tap-GEMMs and LSTM recurrence, fp32 accumulate.
+def test_forward_tensor_core_paths_within_tolerance(golden_dir, case, precision):
+    """Tensor-core engines: precision 2 (default; FP16-stored activations, tcgen05 kind::f16, fp32 accumulate, fp32
+    GroupNorm inputs / gate pre-activations) and precision 1 (fp32 storage rounded to TF32, kind::tf32).
     north_star bar: 1e-3 relative."""
     g = np.load(os.path.join(golden_dir, case + ".npz"))
     m = build(str(g["exp"])).cuda()
-    assert m._engine().precision == 1
+    assert m._engine().precision == 2
+    m._engine().precision = precision
     mix = white_noise((int(g["B"]), m.in_channels, int(g["L"]))).cuda()
     out, zc = m(mix, return_spec=True)
     torch.cuda.synchronize()
     err = rel_l2(out.cpu(), g["out"])
     zc_r = torch.view_as_real(zc.contiguous()).cpu().reshape(-1)[torch.from_numpy(g["spec_idx"].astype(np.int64))]
-    print(f"{case} [tf32]: rel_l2 wave {err:.3e} spec {rel_l2(zc_r, g['spec_val']):.3e}")
+    print(f"{case} [precision {precision}]: rel_l2 wave {err:.3e} spec {rel_l2(zc_r, g['spec_val']):.3e}")
     assert torch.isfinite(out).all()
     assert err < TOL
 
