@@ -70,6 +70,28 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// (b, f, t) index of a pixel walking a [B][F][T] grid with a fixed stride: one decomposition up front, then carries only
+// (64-bit div/mod per pixel costs ~100 instructions and was the limiter of the HBM-bound elementwise / thin kernels).
+struct PixelWalk {
+    int t, f, b;          // current position
+    int dt, df, db;       // stride decomposed the same way
+    int T, F;
+    __device__ __forceinline__ void init(int64_t pix, int64_t step, int T_, int F_) {
+        T = T_; F = F_;
+        t = (int)(pix % T); const int64_t r = pix / T; f = (int)(r % F); b = (int)(r / F);
+        dt = (int)(step % T); const int64_t rs = step / T; df = (int)(rs % F); db = (int)(rs / F);
+    }
+    __device__ __forceinline__ void next() {
+        t += dt;
+        int cf = 0;
+        if (t >= T) { t -= T; cf = 1; }
+        f += df + cf;
+        int cb = 0;
+        if (f >= F) { f -= F; cb = 1; }
+        b += db + cb;
+    }
+};
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace aero

@@ -95,9 +95,11 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
     }
     const bool rnd = (p.flags & AERO_TG_ROUND_TF32) && sizeof(TO) == 4;
     const int64_t npix = (int64_t)(f_hi - f_lo) * p.T;                       // pixels of this segment (row-major f, t)
-    for (int64_t pix = (int64_t)blockIdx.y * ppp + dp; pix < npix; pix += (int64_t)gridDim.y * ppp) {
-        const int fl = f_lo + (int)(pix / p.T);                              // one division per pixel, not per element
-        const int t = (int)(pix - (int64_t)(fl - f_lo) * p.T);
+    PixelWalk pw;                                                            // (row, t) of the pixel; no per-pixel division
+    pw.init((int64_t)blockIdx.y * ppp + dp, (int64_t)gridDim.y * ppp, p.T, 1 << 30);
+    for (int64_t pix = (int64_t)blockIdx.y * ppp + dp; pix < npix; pix += (int64_t)gridDim.y * ppp, pw.next()) {
+        const int fl = f_lo + pw.f;
+        const int t = pw.t;
         const int fin = fl + p.f_off;
         const float* xp = x + (((int64_t)b * p.F_in + fin) * p.T + t) * p.C;
         const int64_t oidx = (((int64_t)b * p.F_out + fl) * p.T + t) * Cout + c;

@@ -20,6 +20,8 @@ struct TapGemmArgs {
     int ldw;          // weight row stride (N rounded up to 4)
     int vec_a;        // 16-byte loads of A are legal
     int vec_o;        // 16-byte stores legal
+    // tcgen05 path: exact division of tile indices (< 2^31) by n_tiles, tiles_t, F_out:  q = (n * mul) >> shr
+    uint32_t dv_mul[3], dv_shr[3];
 };
 int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st);
 int tapgemm_tc_launch(const TapGemmArgs& g, cudaStream_t st);

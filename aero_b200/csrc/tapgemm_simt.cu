@@ -238,10 +238,10 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
     }
     __syncthreads();
     const int64_t npix = (int64_t)p.B * p.F_out * p.T;
-    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
-        const int t = (int)(pix % p.T);
-        const int64_t rowi = pix / p.T;
-        const int fo = (int)(rowi % p.F_out), b = (int)(rowi / p.F_out);
+    PixelWalk pw;
+    pw.init((int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, p.T, p.F_out);
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x, pw.next()) {
+        const int t = pw.t, fo = pw.f, b = pw.b;
         float acc[kThinN];
 #pragma unroll
         for (int n = 0; n < kThinN; ++n) acc[n] = 0.f;
@@ -314,10 +314,10 @@ __global__ void __launch_bounds__(256) tapgemm_thin_k_kernel(const TapGemmArgs g
     const float4 bias = g.bias ? *reinterpret_cast<const float4*>(g.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
     const bool rnd = (p.flags & 1) && sizeof(TO) == 4;
     const int64_t npix = (int64_t)p.B * p.F_out * p.T;
-    for (int64_t pix = (int64_t)blockIdx.x * ppp + dp; pix < npix; pix += (int64_t)gridDim.x * ppp) {
-        const int t = (int)(pix % p.T);
-        const int64_t rowi = pix / p.T;
-        const int fo = (int)(rowi % p.F_out), b = (int)(rowi / p.F_out);
+    PixelWalk pw;
+    pw.init((int64_t)blockIdx.x * ppp + dp, (int64_t)gridDim.x * ppp, p.T, p.F_out);
+    for (int64_t pix = (int64_t)blockIdx.x * ppp + dp; pix < npix; pix += (int64_t)gridDim.x * ppp, pw.next()) {
+        const int t = pw.t, fo = pw.f, b = pw.b;
         const TA* a = static_cast<const TA*>(g.a1) + (int64_t)b * p.a1_sb + (int64_t)fo * p.a1_sf + (int64_t)t * p.a1_st;
         float4 acc = bias;
 #pragma unroll
@@ -350,10 +350,10 @@ __global__ void __launch_bounds__(256) tapgemm_thin_convt_kernel(const TapGemmAr
     }
     __syncthreads();
     const int64_t npix = (int64_t)p.B * n_a * p.T;
-    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
-        const int t = (int)(pix % p.T);
-        const int64_t rowi = pix / p.T;
-        const int a = a_lo + (int)(rowi % n_a), b = (int)(rowi / n_a);
+    PixelWalk pw;
+    pw.init((int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, p.T, n_a);
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x, pw.next()) {
+        const int t = pw.t, a = a_lo + pw.f, b = pw.b;
         float acc[kThinN];
 #pragma unroll
         for (int v = 0; v < kThinN; ++v) acc[v] = 0.f;

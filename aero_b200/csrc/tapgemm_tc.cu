@@ -70,25 +70,32 @@ __device__ __forceinline__ bool tap_geometry(const aero_tapgemm_params& p, int t
 struct TileCoord {
     int b, fo, t0, n0, n_iters;
 };
+// exact n / d for n < 2^31 (Granlund-Montgomery round-up multiplier, set up by the host): three instructions instead of ~25
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr) {
+    return (int)(((uint64_t)(uint32_t)n * mul) >> shr);
+}
+// number of taps whose input row exists (time-axis borders are TMA zero fill and always count)
+__device__ __forceinline__ int valid_taps(const aero_tapgemm_params& p, int fo, int ntaps) {
+    if (p.mode == AERO_TAPS_CONV) {
+        const int base = fo * p.stride_f - p.pad_f;                    // fi = base + jf
+        const int lo = max(0, -base), hi = min(p.kf - 1, p.F_in - 1 - base);
+        return max(0, hi - lo + 1) * p.kt;
+    }
+    const int a = (fo + p.f_out_offset) / p.stride_f;                  // fi = a - tap
+    const int lo = max(0, a - p.F_in + 1), hi = min(ntaps - 1, a);
+    return max(0, hi - lo + 1);
+}
 // tile order: the n-tiles of one pixel tile are adjacent, so CTAs working at the same time share the A operand in L2
 __device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, int n_tiles, int BN, int nch1, int nch2) {
     const aero_tapgemm_params& p = g.p;
     TileCoord c;
-    const int nt = tile % n_tiles, mt = tile / n_tiles;
-    const int tt = mt % g.tiles_t, row = mt / g.tiles_t;
-    c.fo = row % p.F_out;
-    c.b = row / p.F_out;
+    const int mt = fast_div(tile, g.dv_mul[0], g.dv_shr[0]), nt = tile - mt * n_tiles;
+    const int row = fast_div(mt, g.dv_mul[1], g.dv_shr[1]), tt = mt - row * g.tiles_t;
+    c.b = fast_div(row, g.dv_mul[2], g.dv_shr[2]);
+    c.fo = row - c.b * p.F_out;
     c.t0 = tt * kBM;
     c.n0 = nt * BN;
-    if (p.mode == AERO_TAPS_MIX) {
-        c.n_iters = nch1;
-    } else {
-        c.n_iters = 0;
-        for (int tap = 0; tap < g.ntaps; ++tap) {
-            TapIter it;
-            if (tap_geometry(p, tap, c.fo, it)) c.n_iters += nch1 + nch2;
-        }
-    }
+    c.n_iters = (p.mode == AERO_TAPS_MIX) ? nch1 : valid_taps(p, c.fo, g.ntaps) * (nch1 + nch2);
     return c;
 }
 
@@ -128,7 +135,7 @@ __device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], uint32
 
 template <int AMODE, bool RES, bool STATS, typename TO>
 __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmArgs& g, const TileCoord& tc, uint32_t tacc, int BN, int q,
-                                                   int ew, int lane, int Nout, int gw) {
+                                                   int ew, int lane, int Nout, int gw, int c_start, int c_step) {
     const aero_tapgemm_params& p = g.p;
     constexpr int CNT = (AMODE == 3) ? 8 : 16;          // staged output columns per 16 accumulator columns
     constexpr int LPR = CNT / 4;                         // lanes per row (one float4 each)
@@ -144,7 +151,7 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
     TO* const obase = static_cast<TO*>(g.out) + (int64_t)tc.b * p.o_sb + (int64_t)tc.fo * p.o_sf + (int64_t)row0 * p.o_st;
     const TO* const rbase = RES ? static_cast<const TO*>(g.residual) + (int64_t)tc.b * p.r_sb + (int64_t)tc.fo * p.r_sf + (int64_t)row0 * p.r_st : nullptr;
     const float* const adp = g.addend_fn ? g.addend_fn + (int64_t)tc.fo * Nout : nullptr;
-    for (int c0 = (ew >> 2) * 16; c0 < BN; c0 += 32) {   // the two warps of a lane quarter alternate 16-column chunks
+    for (int c0 = c_start; c0 < BN; c0 += c_step) {      // split mode: the two warps of a lane quarter alternate 16-column chunks
         const int nb = tc.n0 + c0;
         if (nb >= p.N) break;
         uint32_t r[16];
@@ -232,10 +239,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
     const int nch1 = (p.C1 + kBKc - 1) / kBKc, nch2 = (p.C2 + kBKc - 1) / kBKc;
     const bool mix = p.mode == AERO_TAPS_MIX;
     const uint32_t acc_cols = tmem_cols >> 1;          // columns per accumulator buffer
+    // Epilogue organisation.  Wide tiles (tensor-bound): all eight warps drain one accumulator, two per TMEM lane quarter.
+    // Narrow tiles (HBM-bound layers, BN <= 64): the per-tile latency chain dominates, so the warps form two groups of
+    // four and each group drains every other tile on its own accumulator buffer -- two tiles in flight per CTA.
+    const bool grouped = BN <= 64;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1); mbar_init(&sh->acc_empty[s], 32 * kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1); mbar_init(&sh->acc_empty[s], grouped ? 16 * kEpiWarps : 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int w = 0; w < kEpiWarps; ++w)
             for (int i = 0; i < 8; ++i) { sh->stats[w][i][0] = 0.f; sh->stats[w][i][1] = 0.f; }
@@ -350,9 +361,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
         const int Nout = p.glu ? p.N / 2 : p.N;
         const int gw = (p.stats_mode == 1) ? Nout / p.groups : Nout;
         const bool rnd = (p.flags & 1) && !F16O;
+        const int grp = ew >> 2;                       // grouped mode: which accumulator buffer / tile parity this warp serves
+        const int c_start = grouped ? 0 : grp * 16, c_step = grouped ? 16 : 32;
+        const int t_step = grouped ? 2 : 1;
         const bool fast = !mix && g.vec_o && !g.colscale && (p.stats_mode == 0 || gw % 4 == 0);
-        int local = 0;
-        for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
+        int local = grouped ? grp : 0;
+        for (int64_t tile64 = (int64_t)blockIdx.x + (int64_t)local * gridDim.x; tile64 < tiles_total; tile64 += (int64_t)t_step * gridDim.x, local += t_step) {
+            const int tile = (int)tile64;
             const TileCoord tc = tile_coord(g, tile, n_tiles, BN, nch1, nch2);
             const int b = tc.b, fo = tc.fo, t0 = tc.t0, n0 = tc.n0, n_iters = tc.n_iters;
             const int buf = local & 1;
@@ -375,7 +390,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 // transposed store: lane = pixel m (contiguous in memory), column = output row n
                 const float gate = (row_ok && g.colscale) ? g.colscale[(int64_t)b * p.cs_sb + t] : 1.f;
                 TO* ob = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + t;
-                for (int c0 = (ew >> 2) * 16; c0 < BN; c0 += 32) {
+                for (int c0 = c_start; c0 < BN; c0 += c_step) {
                     uint32_t r[16];
                     tmem_ld16(tacc + (uint32_t)c0, r);
                     if (row_ok) {
@@ -391,10 +406,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     }
                 }
             } else if (fast) {
-                epilogue_fast_tile<AMODE, RES, STATS, TO>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw);
+                epilogue_fast_tile<AMODE, RES, STATS, TO>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw, c_start, c_step);
             } else {
                 // generic (unaligned outputs / colscale) epilogue: lane = row, scattered stores; one warp per lane quarter
-                for (int c0 = 0; c0 < (ew < 4 ? BN : 0); c0 += 16) {
+                for (int c0 = 0; c0 < ((grouped || ew < 4) ? BN : 0); c0 += 16) {
                     uint32_t r[16];
                     if (n_iters > 0) {
                         tmem_ld16(tacc + (uint32_t)c0, r);
@@ -476,12 +491,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             tcgen05_fence_before();
             mbar_arrive(&sh->acc_empty[buf]);
             if (p.stats_mode != 0) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int e = threadIdx.x - 64;
+                // fixed-order reduction over the warps that drained this tile (all eight, or this group's four)
+                const int w_lo = grouped ? grp * 4 : 0, w_n = grouped ? 4 : kEpiWarps;
+                if (grouped) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                else asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int e = threadIdx.x - 64 - w_lo * 32;
                 if (e < 8) {
                     float a = 0.f, c = 0.f;
-#pragma unroll
-                    for (int w = 0; w < kEpiWarps; ++w) { a += sh->stats[w][e][0]; c += sh->stats[w][e][1]; }
+                    for (int w = w_lo; w < w_lo + w_n; ++w) { a += sh->stats[w][e][0]; c += sh->stats[w][e][1]; }
                     const int gi = g_lo + e;
                     const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
                     if (gi < ngroups && (a != 0.f || c != 0.f)) {
@@ -489,9 +506,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         atomicAdd(&g.stats[2 * slot], (double)a);
                         atomicAdd(&g.stats[2 * slot + 1], (double)c);
                     }
-                    for (int w = 0; w < kEpiWarps; ++w) { sh->stats[w][e][0] = 0.f; sh->stats[w][e][1] = 0.f; }
+                    for (int w = w_lo; w < w_lo + w_n; ++w) { sh->stats[w][e][0] = 0.f; sh->stats[w][e][1] = 0.f; }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (grouped) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                else asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
@@ -685,6 +703,16 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     g.tiles_t = cdiv(p.T, kBM);
     const int64_t tiles = (int64_t)p.B * p.F_out * g.tiles_t;
     if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
+    {
+        const uint32_t divs[3] = {(uint32_t)cdiv(p.N, BN), (uint32_t)g.tiles_t, (uint32_t)p.F_out};
+        for (int i = 0; i < 3; ++i) {
+            uint32_t s = 0;
+            while ((1ull << s) < divs[i]) ++s;                         // ceil(log2 d)
+            const uint64_t two = 1ull << (31 + s);
+            g.dv_mul[i] = (uint32_t)((two + divs[i] - 1) / divs[i]);   // ceil(2^(31+s) / d) <= 2^32 - 1 (d = 1: 2^31)
+            g.dv_shr[i] = 31 + s;
+        }
+    }
     uint32_t tmem_cols = 32;                       // two accumulator buffers (double-buffered epilogue)
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
     tmem_cols <<= 1;
@@ -703,7 +731,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     if (max_iters >= (f16a ? 12 : 24)) {
         kStages = (227 * 1024 - fixed) / stage_bytes;
     } else {
-        kStages = (72 * 1024) / stage_bytes;
+        kStages = (96 * 1024) / stage_bytes;
     }
     if (kStages > kMaxStages) kStages = kMaxStages;
     if (kStages < 2) kStages = 2;
