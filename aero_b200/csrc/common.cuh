@@ -38,7 +38,17 @@ __device__ __forceinline__ float round_tf32_rna(float x) {
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
-__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// two fp32 -> packed FP16 pair, round-to-nearest-even, saturating at +-65504 (one F2FP.SATFINITE)
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void stf(__half* p, float v) {
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    *reinterpret_cast<unsigned short*>(p) = h;
+}
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4(const __half* p) {            // 8-byte aligned
     const uint2 u = *reinterpret_cast<const uint2*>(p);
@@ -48,16 +58,18 @@ __device__ __forceinline__ float4 ld4(const __half* p) {            // 8-byte al
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(__half* p, float4 v) {           // 8-byte aligned
-    const __half2 a = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
-    const __half2 b = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
     uint2 u;
-    u.x = *reinterpret_cast<const uint32_t*>(&a);
-    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    u.x = pack_half2_sat(v.x, v.y);
+    u.y = pack_half2_sat(v.z, v.w);
     *reinterpret_cast<uint2*>(p) = u;
 }
 // value as it will be read back from storage of type T (statistics must see the stored value)
 __device__ __forceinline__ float stored(float v, const float*) { return v; }
-__device__ __forceinline__ float stored(float v, const __half*) { return __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f))); }
+__device__ __forceinline__ float stored(float v, const __half*) {
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return __half2float(__ushort_as_half(h));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

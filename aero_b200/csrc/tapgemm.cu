@@ -53,6 +53,8 @@ extern "C" int aero_tapgemm_fwd(const void* a1, const void* a2, const void* w, c
     g.vec_o = al16(out) && p.o_sb % 4 == 0 && p.o_sf % 4 == 0 && p.o_st % 4 == 0 && Nout % 4 == 0 &&
               (!residual || (al16(residual) && p.r_sb % 4 == 0 && p.r_sf % 4 == 0 && p.r_st % 4 == 0)) &&
               (!addend_fn || al16(addend_fn));
+    g.vec_o8 = g.vec_o && p.o_sb % 8 == 0 && p.o_sf % 8 == 0 && p.o_st % 8 == 0 && Nout % 8 == 0 &&
+               (!residual || (p.r_sb % 8 == 0 && p.r_sf % 8 == 0 && p.r_st % 8 == 0));
     AERO_REQUIRE(al16(w) && p.w_sb % 4 == 0, "aero_tapgemm_fwd: weights must be 16-byte aligned");
     AERO_REQUIRE(p.precision >= 0 && p.precision <= 2, "aero_tapgemm_fwd: precision=%d", p.precision);
     AERO_REQUIRE((p.precision != 1 || !(p.flags & AERO_TG_A_F16)) && (p.precision != 2 || (p.flags & AERO_TG_A_F16)),

@@ -20,8 +20,12 @@ struct TapGemmArgs {
     int ldw;          // weight row stride (N rounded up to 4)
     int vec_a;        // 16-byte loads of A are legal
     int vec_o;        // 16-byte stores legal
+    int vec_o8;       // FP16 outputs: rows are 16-byte aligned in units of 8 halves (direct lane-per-row epilogue)
     // tcgen05 path: exact division of tile indices (< 2^31) by n_tiles, tiles_t, F_out:  q = (n * mul) >> shr
     uint32_t dv_mul[3], dv_shr[3];
+    int direct_f16;   // FP16 outputs: same choice
+    int direct_f32;   // fp32 outputs: direct lane-per-row epilogue instead of the shared-memory transpose
+    int grouped_bn;   // tiles with BN <= this use the two-group epilogue
 };
 int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st);
 int tapgemm_tc_launch(const TapGemmArgs& g, cudaStream_t st);

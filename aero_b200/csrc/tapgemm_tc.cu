@@ -23,16 +23,28 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 #include <type_traits>
 
 #include "tapgemm.cuh"
 #include "tc_common.cuh"
 
+#ifdef AERO_TC_TRACE
+// tuning aid (tools/tc_trace.py builds a separate library with this flag): clock64 stamps of CTA 0's pipeline events
+__device__ long long g_tc_trace[256 * 8];
+#define AERO_TRACE(slot, local) do { if (blockIdx.x == 0 && (local) < 256) g_tc_trace[(local) * 8 + (slot)] = clock64(); } while (0)
+extern "C" int aero_debug_tc_trace(long long* host) {
+    return cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(g_tc_trace)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define AERO_TRACE(slot, local) do { } while (0)
+#endif
+
 namespace aero {
 
 constexpr int kBM = 128;
 template <bool F16A> struct OperandKind { static constexpr int kBK = F16A ? 64 : 32; };   // elements per 128-byte swizzle row
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, alternating 16-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kATileBytes = kBM * 128;   // 16 KB
@@ -104,22 +116,15 @@ __device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, 
 // staging tile.  Stage B: the warp walks the tile so that consecutive lanes hold consecutive float4s of one output row
 // (residual loads and stores are whole 32-byte sectors of one row), adds the row-wise terms, rounds, accumulates statistics.
 template <int AMODE>
-__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], uint32_t stg_row, const float* __restrict__ bias,
-                                                 int nb, int N) {    // stg_row: shared-space address of this lane's staging row
-    const bool full = nb + 16 <= N;
+__device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], uint32_t stg_row, uint32_t sbias) {
+    // stg_row: shared-space address of this lane's staging row; sbias: shared-space address of this chunk's 16 bias values
+    float4 bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = lds128(sbias + 16 * j);
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-        if (bias) {
-            if (full) {
-                const float4 bv = *reinterpret_cast<const float4*>(bias + nb + j);
-                v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (nb + j + u < N) v[u] += bias[nb + j + u];
-            }
-        }
+        float v[4] = {__uint_as_float(r[j]) + bv[j / 4].x, __uint_as_float(r[j + 1]) + bv[j / 4].y,
+                      __uint_as_float(r[j + 2]) + bv[j / 4].z, __uint_as_float(r[j + 3]) + bv[j / 4].w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (AMODE == 1) v[u] = gelu_exact(v[u]);
@@ -135,7 +140,7 @@ __device__ __forceinline__ void epilogue_stage_a(const uint32_t (&r)[16], uint32
 
 template <int AMODE, bool RES, bool STATS, typename TO>
 __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmArgs& g, const TileCoord& tc, uint32_t tacc, int BN, int q,
-                                                   int ew, int lane, int Nout, int gw, int c_start, int c_step) {
+                                                   int ew, int lane, int Nout, int gw, int c_start, int c_step, uint32_t sbias) {
     const aero_tapgemm_params& p = g.p;
     constexpr int CNT = (AMODE == 3) ? 8 : 16;          // staged output columns per 16 accumulator columns
     constexpr int LPR = CNT / 4;                         // lanes per row (one float4 each)
@@ -161,7 +166,7 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = 0u;
         }
-        epilogue_stage_a<AMODE>(r, stg + (uint32_t)lane * 80u, g.bias, nb, p.N);
+        epilogue_stage_a<AMODE>(r, stg + (uint32_t)lane * 80u, sbias + (uint32_t)nb * 4u);
         __syncwarp();
         const int no0 = (AMODE == 3) ? nb >> 1 : nb;
         const int nn = no0 + 4 * cq;
@@ -220,6 +225,125 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
     }
 }
 
+// Direct epilogue: a lane's 16 accumulator columns of its row are 32 (FP16) or 64 (fp32) contiguous bytes -- whole sectors --
+// so the row is written straight from registers with 16-byte stores and no shared-memory transpose.  Everything is unrolled
+// and independent (bias / residual / addend loads issue together), which is what the HBM-bound layers need: with one or two
+// warps per scheduler the epilogue is a latency chain, not a throughput problem.
+template <int AMODE, bool RES, bool STATS, typename TO>
+__device__ __forceinline__ void epilogue_direct(TcShared* sh, const TapGemmArgs& g, const TileCoord& tc, uint32_t tacc, int BN, int q, int ew,
+                                                int lane, int Nout, int gw, int c_start, int c_step, uint32_t sbias) {
+    const aero_tapgemm_params& p = g.p;
+    constexpr int CNT = (AMODE == 3) ? 8 : 16;          // output columns per 16 accumulator columns
+    constexpr bool F16 = sizeof(TO) == 2;
+    const int t = tc.t0 + q * 32 + lane;
+    const bool row_ok = t < p.T;
+    TO* const orow = static_cast<TO*>(g.out) + (int64_t)tc.b * p.o_sb + (int64_t)tc.fo * p.o_sf + (int64_t)t * p.o_st;
+    const TO* const rrow = RES ? static_cast<const TO*>(g.residual) + (int64_t)tc.b * p.r_sb + (int64_t)tc.fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+    const float* const adp = g.addend_fn ? g.addend_fn + (int64_t)tc.fo * Nout : nullptr;
+    float sa = 1.f, sb = 0.f;
+    const bool affine = g.samp_affine != nullptr;
+    if (affine) { sa = g.samp_affine[2 * tc.b]; sb = g.samp_affine[2 * tc.b + 1]; }
+    const bool rnd = (p.flags & 1) && !F16;
+    const int g_lo = ((AMODE == 3) ? tc.n0 >> 1 : tc.n0) / gw;
+    int cur_g = -1;                                      // statistics: running group (warp-uniform), flushed when it changes
+    float ssum = 0.f, ssq = 0.f;
+    for (int c0 = c_start; c0 < BN; c0 += c_step) {
+        const int nb = tc.n0 + c0;
+        if (nb >= p.N) break;
+        uint32_t r[16];
+        if (tc.n_iters > 0) {
+            tmem_ld16(tacc + (uint32_t)c0, r);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        {
+            float4 bv[4];                                // bias lives in shared memory (zero padded): broadcast reads, no L1 misses
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = lds128(sbias + (uint32_t)nb * 4u + 16u * j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w; }
+        }
+        float o[CNT];
+        if (AMODE == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = (AMODE == 1) ? gelu_exact(v[j]) : (AMODE == 2) ? fmaxf(v[j], 0.f) : v[j];
+        }
+        const int no0 = (AMODE == 3) ? nb >> 1 : nb;
+        const int n_ok = min(CNT, Nout - no0);           // valid output columns of this chunk (a multiple of 4; 8 for FP16: host check)
+        if (row_ok) {
+            if (adp) {
+#pragma unroll
+                for (int j = 0; j < CNT; j += 4)
+                    if (j < n_ok) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(adp + no0 + j));
+                        o[j] += a.x; o[j + 1] += a.y; o[j + 2] += a.z; o[j + 3] += a.w;
+                    }
+            }
+            if (RES) {
+#pragma unroll
+                for (int j = 0; j < CNT; j += 4)
+                    if (j < n_ok) {
+                        const float4 a = ld4(rrow + no0 + j);
+                        o[j] += a.x; o[j + 1] += a.y; o[j + 2] += a.z; o[j + 3] += a.w;
+                    }
+            }
+            if (affine) {
+#pragma unroll
+                for (int j = 0; j < CNT; ++j) o[j] = fmaf(o[j], sa, sb);
+            }
+            if (rnd) {
+#pragma unroll
+                for (int j = 0; j < CNT; ++j) o[j] = round_tf32_rna(o[j]);
+            }
+            if (F16) {
+#pragma unroll
+                for (int j = 0; j < CNT; j += 8)
+                    if (j < n_ok) {
+                        uint4 u;
+                        u.x = pack_half2_sat(o[j], o[j + 1]); u.y = pack_half2_sat(o[j + 2], o[j + 3]);
+                        u.z = pack_half2_sat(o[j + 4], o[j + 5]); u.w = pack_half2_sat(o[j + 6], o[j + 7]);
+                        *reinterpret_cast<uint4*>(orow + no0 + j) = u;
+                    }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CNT; j += 4)
+                    if (j < n_ok) *reinterpret_cast<float4*>(orow + no0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+        }
+        if (STATS) {
+            // group width is a multiple of 4 (host check), so every column quad lies in one group
+#pragma unroll
+            for (int j = 0; j < CNT; j += 4) {
+                if (j < n_ok) {
+                    const int gi = (no0 + j) / gw;
+                    if (gi != cur_g) {
+                        if (cur_g >= 0) {
+                            const float a = warp_sum(ssum), c = warp_sum(ssq);
+                            if (lane == 0) { sh->stats[ew][cur_g - g_lo][0] += a; sh->stats[ew][cur_g - g_lo][1] += c; }
+                        }
+                        cur_g = gi; ssum = 0.f; ssq = 0.f;
+                    }
+                    if (row_ok) {
+                        ssum += (o[j] + o[j + 1]) + (o[j + 2] + o[j + 3]);
+                        ssq += (o[j] * o[j] + o[j + 1] * o[j + 1]) + (o[j + 2] * o[j + 2] + o[j + 3] * o[j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    if (STATS && cur_g >= 0) {
+        const float a = warp_sum(ssum), c = warp_sum(ssq);
+        if (lane == 0) { sh->stats[ew][cur_g - g_lo][0] += a; sh->stats[ew][cur_g - g_lo][1] += c; }
+    }
+}
+
 // Persistent: CTA c processes tiles c, c + gridDim.x, ...  The TMA producer runs ahead across tile boundaries; the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 template <int AMODE, bool RES, bool STATS, bool F16A, bool F16O>
@@ -231,6 +355,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = kATileBytes + BN * 128;
     TcShared* sh = reinterpret_cast<TcShared*>(smem + kStages * stage_bytes);
+    float* const sbias_f = reinterpret_cast<float*>(sh + 1);       // bias (or zeros), padded to whole 16-column chunks of the last tile
+    const uint32_t sbias = smem_u32(sbias_f);
 
     using TO = typename std::conditional<F16O, __half, float>::type;
     constexpr int kBKc = OperandKind<F16A>::kBK;
@@ -242,8 +368,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
     // Epilogue organisation.  Wide tiles (tensor-bound): all eight warps drain one accumulator, two per TMEM lane quarter.
     // Narrow tiles (HBM-bound layers, BN <= 64): the per-tile latency chain dominates, so the warps form two groups of
     // four and each group drains every other tile on its own accumulator buffer -- two tiles in flight per CTA.
-    const bool grouped = BN <= 64;
+    const bool grouped = BN <= g.grouped_bn;
 
+    for (int i = threadIdx.x; i < n_tiles * BN; i += kThreads) sbias_f[i] = (g.bias && i < g.p.N) ? g.bias[i] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1); mbar_init(&sh->acc_empty[s], grouped ? 16 * kEpiWarps : 32 * kEpiWarps); }
@@ -268,8 +395,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (uint32_t)stage_bytes;
-            for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+            int ptl = 0;
+            for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++ptl) {
                 const TileCoord c = tile_coord(g, tile, n_tiles, BN, nch1, nch2);
+                AERO_TRACE(0, ptl);
                 if (mix) {
                     // A = activations [K rows][M contiguous].  tf32: four 32(m) x 32(k) boxes, f16: two 64(m) x 64(k) boxes
                     // form one MN-major 128(m) x kBK(k) operand tile of 16 KB
@@ -303,6 +432,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         }
                     }
                 }
+                AERO_TRACE(1, ptl);
             }
         }
     } else if (warp == 1) {
@@ -316,10 +446,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                 const int buf = local & 1;
                 mbar_wait(&sh->acc_empty[buf], (uint32_t)(((local >> 1) & 1) ^ 1));     // epilogue has drained this buffer
                 tcgen05_fence_after();
+                AERO_TRACE(2, local);
                 const uint32_t tacc = tmem_base + (uint32_t)buf * acc_cols;
                 for (int i = 0; i < c.n_iters; ++i) {
                     mbar_wait(&sh->full[stage], phase);
                     tcgen05_fence_after();
+                    if (i == 0) AERO_TRACE(3, local);
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint64_t db = make_desc_sw128(sa + kATileBytes);
                     if (mix && F16A) {
@@ -351,6 +483,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&sh->acc_full[buf]);
+                AERO_TRACE(4, local);
             }
         }
     } else {
@@ -374,8 +507,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             const uint32_t tacc = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16);
             const int t = t0 + m;
             const bool row_ok = t < p.T;
+            if (q == 0 && lane == 0) AERO_TRACE(5, local);
             mbar_wait(&sh->acc_full[buf], (uint32_t)((local >> 1) & 1));
             tcgen05_fence_after();
+            if (q == 0 && lane == 0) AERO_TRACE(6, local);
             float sa = 1.f, sb = 0.f;
             if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
             TO* op = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
@@ -405,8 +540,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         }
                     }
                 }
+            } else if (fast && (F16O ? (g.vec_o8 && (g.direct_f16 == 1 || (g.direct_f16 == 2 && AMODE == 3))) : g.direct_f32)) {
+                epilogue_direct<AMODE, RES, STATS, TO>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw, c_start, c_step, sbias);
             } else if (fast) {
-                epilogue_fast_tile<AMODE, RES, STATS, TO>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw, c_start, c_step);
+                epilogue_fast_tile<AMODE, RES, STATS, TO>(sh, g, tc, tacc, BN, q, ew, lane, Nout, gw, c_start, c_step, sbias);
             } else {
                 // generic (unaligned outputs / colscale) epilogue: lane = row, scattered stores; one warp per lane quarter
                 for (int c0 = 0; c0 < ((grouped || ew < 4) ? BN : 0); c0 += 16) {
@@ -425,7 +562,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                         const int n = nb + j;
                         float x = __uint_as_float(r[j]);
                         if (row_ok && n < p.N) {
-                            if (g.bias) x += g.bias[n];
+                            x += sbias_f[n];
                             if (csp) x *= csp[n];
                             if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
                             else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
@@ -490,6 +627,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             // accumulator buffer drained: hand it back to the MMA warp before the (cheap) statistics flush
             tcgen05_fence_before();
             mbar_arrive(&sh->acc_empty[buf]);
+            if (q == 0 && lane == 0) AERO_TRACE(7, local);
             if (p.stats_mode != 0) {
                 // fixed-order reduction over the warps that drained this tile (all eight, or this group's four)
                 const int w_lo = grouped ? grp * 4 : 0, w_n = grouped ? 4 : kEpiWarps;
@@ -701,6 +839,12 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
         if ((rc = encode_map(&mW, g.w, 3, dims, strides, box, false, esz)) != AERO_OK) return rc;
     }
     g.tiles_t = cdiv(p.T, kBM);
+    g.grouped_bn = 64;
+    g.direct_f32 = 0;
+    g.direct_f16 = 2;       // measured: the direct form wins for GLU outputs (one 16-byte store per lane), the transpose otherwise
+    if (const char* e = getenv("AERO_TC_DIRECT_F32")) g.direct_f32 = atoi(e);
+    if (const char* e = getenv("AERO_TC_DIRECT_F16")) g.direct_f16 = atoi(e);
+    if (const char* e = getenv("AERO_TC_GROUPED_BN")) g.grouped_bn = atoi(e);
     const int64_t tiles = (int64_t)p.B * p.F_out * g.tiles_t;
     if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
     {
@@ -726,16 +870,19 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     const int stage_bytes = kATileBytes + BN * 128;
     // pipeline depth: the producer runs ahead across tiles, so depth is set by bytes in flight, not by the K length.
     // Long K loops get as many stages as fit; short, HBM-bound layers keep ~64 KB in flight and leave room for 2-3 CTAs/SM.
-    const int fixed = (int)sizeof(TcShared) + 1024;
+    const int bias_bytes = cdiv(p.N, BN) * BN * 4;
+    const int fixed = (int)sizeof(TcShared) + bias_bytes + 1024;
     int kStages;
     if (max_iters >= (f16a ? 12 : 24)) {
         kStages = (227 * 1024 - fixed) / stage_bytes;
     } else {
         kStages = (96 * 1024) / stage_bytes;
     }
+    if (const char* e = getenv("AERO_TC_STAGES")) kStages = atoi(e);      // tuning knobs (tools/kprof.py); not used by the product
     if (kStages > kMaxStages) kStages = kMaxStages;
     if (kStages < 2) kStages = 2;
-    const size_t smem = (size_t)kStages * stage_bytes + sizeof(TcShared) + 1024;
+    while (kStages > 2 && (size_t)kStages * stage_bytes + fixed > 227 * 1024) --kStages;
+    const size_t smem = (size_t)kStages * stage_bytes + fixed;
     const int amode = p.glu ? 3 : p.act;                 // the engine never combines GLU with an activation
     if (p.glu && p.act != AERO_ACT_NONE) { set_error("aero_tapgemm_fwd(tcgen05): GLU with an activation is not supported"); return AERO_ERR_UNSUPPORTED; }
     const bool res = g.residual != nullptr, stats = p.stats_mode != 0;
@@ -760,6 +907,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > (int)(512 / tmem_cols)) per_sm = (int)(512 / tmem_cols);
     if (per_sm > 2) per_sm = 2;                      // 320 threads x ~96 registers: two CTAs per SM
+    if (const char* e = getenv("AERO_TC_PER_SM")) per_sm = atoi(e) < per_sm ? atoi(e) : per_sm;
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)num_sms * per_sm;
     dim3 grid((unsigned)(tiles_total < want ? tiles_total : want));

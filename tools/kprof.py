@@ -28,6 +28,9 @@ SHAPES = {
     "enc0_ftb2": dict(F_out=256, N=48, C1=48, C2=48, act=cabi.ACT_RELU),
     "enc0_conv": dict(F_out=64, F_in=256, N=48, C1=48, kf=8, stride_f=4, pad_f=2, act=cabi.ACT_GELU),
     "enc0_dc_c2": dict(F_out=64, N=96, C1=12, stats_mode=2),
+    "enc1_ftb2": dict(F_out=64, N=96, C1=96, C2=96, act=cabi.ACT_RELU),
+    "enc0_rw": dict(F_out=64, N=96, C1=48, glu=1),
+    "dec3_ct_in": dict(F_out=64, N=192, C1=96),
     "enc3_gin2": dict(F_out=1, N=768, C1=192, T=768 * 200 // 32),
 }
 
@@ -41,7 +44,7 @@ def run_lstm(args):
     m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
     eng = AeroEngine(m)
     eng.precision = args.precision
-    tc = args.precision == 1
+    tc = args.precision >= 1
     G = 2 * (2 if H <= 64 else 4) * 128 if tc else 8 * H
     gin = torch.randn(rows * n_win * steps, G, device="cuda")
     bias = torch.randn(G, device="cuda")
@@ -114,10 +117,11 @@ def run_stft(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48", "stft", "attn96", "attn48"])
-    ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--precision", type=int, default=2)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-stats", action="store_true")
+    ap.add_argument("--out-f32", action="store_true")
     args = ap.parse_args()
     torch.manual_seed(0)
     if args.shape.startswith("lstm"):
@@ -139,14 +143,20 @@ def main():
     mode = cfg.get("mode", cabi.TAPS_CONV)
     nslab = cfg.get("kf", 1) * cfg.get("kt", 1)
     K = C1 + C2
+    from aero_b200.engine import pack_kmajor_fp16
     w = tf32_round(pack_taps(torch.randn(N, K, nslab) / math.sqrt(K * nslab))).cuda()
     eng._wk[w.data_ptr()] = tf32_round(w.permute(0, 2, 1).contiguous())
-    a1 = tf32_round(torch.randn(B, F_in, Tt, C1)).cuda() if C1 else None
-    a2 = tf32_round(torch.randn(B, F_in, Tt, C2)).cuda() if C2 else None
+    eng._wh[w.data_ptr()] = pack_kmajor_fp16(w)
+    sm = cfg.get("stats_mode", 0)
+    f16 = args.precision == 2 and C1 % 8 == 0 and C2 % 8 == 0
+    adt = torch.float16 if f16 else torch.float32
+    odt = torch.float16 if (args.precision == 2 and not sm and not args.out_f32) else torch.float32
+    a1 = tf32_round(torch.randn(B, F_in, Tt, C1)).cuda().to(adt) if C1 else None
+    a2 = tf32_round(torch.randn(B, F_in, Tt, C2)).cuda().to(adt) if C2 else None
     bias = torch.randn(N).cuda()
     n_out = N // 2 if cfg.get("glu") else N
-    out = torch.empty(B, F_out, Tt, n_out, device="cuda")
-    sm = cfg.get("stats_mode", 0)
+    out = torch.empty(B, F_out, Tt, n_out, device="cuda", dtype=odt)
+    nbytes = sum(t.numel() * t.element_size() for t in (a1, a2, out) if t is not None)
     stats = torch.zeros(max(1, {0: 0, 1: B * cfg.get("groups", 1), 2: B * F_out}[sm]), 2, dtype=torch.float64, device="cuda")
     ntaps = nslab if mode == cabi.TAPS_CONV else cfg["kf"] // cfg["stride_f"]
     flops = 2.0 * B * F_out * Tt * N * K * ntaps
@@ -164,7 +174,7 @@ def main():
             ms.append(e0.elapsed_time(e1))
     best = min(ms)
     print(f"{args.shape}: precision {args.precision} B={B} {flops/1e9:.1f} GFLOP  best {best*1e3:.1f} us  median {sorted(ms)[len(ms)//2]*1e3:.1f} us"
-          f"  -> {flops/best/1e9:.1f} TFLOP/s (best)")
+          f"  -> {flops/best/1e9:.1f} TFLOP/s, {nbytes/best/1e6:.0f} GB/s of {nbytes/1e6:.0f} MB (best)")
 
 
 if __name__ == "__main__":
