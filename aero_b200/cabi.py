@@ -50,6 +50,11 @@ class LstmParams(C.Structure):
                 ("in_windowed", i32), ("out_windowed", i32), ("flags", i32), ("precision", i32)]
 
 
+class FtbLinParams(C.Structure):
+    _fields_ = [("B", i32), ("F", i32), ("T", i32), ("N", i32), ("J", i32), ("flags", i32),
+                ("z_sb", i64), ("z_sf", i64), ("zm_sb", i64), ("zm_sf", i64)]
+
+
 class AttnParams(C.Structure):
     _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32), ("flags", i32)]
 
@@ -70,8 +75,9 @@ SYMBOLS = {
     "aero_istft_fwd": (C.c_int, [vp, vp, vp, C.POINTER(IstftParams), vp]),
     "aero_tapgemm_fwd": (C.c_int, [vp] * 10 + [C.POINTER(TapGemmParams), vp]),
     "aero_tapgemm_tc_eligible": (C.c_int, [C.POINTER(TapGemmParams)]),
-    "aero_sample_norm_fwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i32, vp]),
+    "aero_sample_norm_fwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, i32, vp]),
     "aero_norm_act_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
+    "aero_ftb_lin_out_fwd": (C.c_int, [vp] * 7 + [C.POINTER(FtbLinParams), vp]),
     "aero_lstm_rec_fwd": (C.c_int, [vp, vp, vp, vp, C.POINTER(LstmParams), vp]),
     "aero_local_attn_fwd": (C.c_int, [vp, vp, C.POINTER(AttnParams), vp]),
     "aero_lsd_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),

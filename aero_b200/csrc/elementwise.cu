@@ -8,11 +8,11 @@ namespace aero {
 // reference aero.py:462-464: mean / unbiased std over (C,F,T); y = (x-mean)/(1e-5+std)
 __global__ void __launch_bounds__(256) sample_norm_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                           float* __restrict__ y, float* __restrict__ samp_affine,
-                                                          int64_t per_sample, int rnd) {
+                                                          int64_t count, int64_t per_sample, int rnd) {
     const int b = blockIdx.y;
     __shared__ float s_mean, s_inv;
     if (threadIdx.x == 0) {
-        const double n = (double)per_sample;
+        const double n = (double)count;                 // statistics cover `count` values; `per_sample` floats are transformed
         const double mean = stats[2 * b] / n;
         double var = (stats[2 * b + 1] - n * mean * mean) / (n - 1.0);
         if (var < 0) var = 0;
@@ -142,14 +142,15 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
 }  // namespace aero
 
 extern "C" int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* samp_affine, int32_t B,
-                                    int64_t per_sample, int32_t round_tf32, aero_stream_t stream) {
+                                    int64_t count, int64_t extent, int32_t round_tf32, aero_stream_t stream) {
     using namespace aero;
-    AERO_REQUIRE(x && stats && y && B >= 1 && per_sample >= 2, "aero_sample_norm_fwd: bad argument");
+    const int64_t per_sample = extent > 0 ? extent : count;
+    AERO_REQUIRE(x && stats && y && B >= 1 && count >= 2 && per_sample >= count, "aero_sample_norm_fwd: bad argument");
     AERO_REQUIRE((per_sample & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
                  "aero_sample_norm_fwd: per_sample must be a multiple of 4 and buffers 16-byte aligned");
     const int chunks = (int)((per_sample / 4 + 256 * 8 - 1) / (256 * 8));
     dim3 grid(chunks < 1 ? 1 : chunks, B);
-    sample_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, y, samp_affine, per_sample, round_tf32);
+    sample_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, y, samp_affine, count, per_sample, round_tf32);
     return check_launch("aero_sample_norm_fwd");
 }
 

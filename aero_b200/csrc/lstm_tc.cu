@@ -21,6 +21,16 @@
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
 
+#ifdef AERO_TC_TRACE
+__device__ long long g_lstm_trace[128 * 8];
+#define LSTM_TRACE(slot, step) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (step) < 128) g_lstm_trace[(step) * 8 + (slot)] = clock64(); } while (0)
+extern "C" int aero_debug_lstm_trace(long long* host) {
+    return cudaMemcpyFromSymbol(host, g_lstm_trace, sizeof(g_lstm_trace)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define LSTM_TRACE(slot, step) do { } while (0)
+#endif
+
 namespace aero {
 
 constexpr int kNT = 16;          // sequences per CTA (UMMA N)
@@ -122,6 +132,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             for (int s = 1; s < p.steps; ++s) {
                 mbar_wait(&sh->h_ready, (uint32_t)((s - 1) & 1));
                 tcgen05_fence_after();
+                LSTM_TRACE(0, s);
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
                     for (int kc = 0; kc < nK; ++kc) {
@@ -133,6 +144,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                     }
                 }
                 umma_commit(&sh->acc_ready);
+                LSTM_TRACE(1, s);
             }
         }
     } else {
@@ -190,20 +202,39 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
 #pragma unroll
         for (int i = 0; i < kNS; ++i) c_state[i] = 0.f;
 
+        // The input-projection gate pre-activations stream from HBM (hundreds of MB per layer): their ~1 us load latency
+        // must not sit on the per-step dependency chain, so step s+1's values are requested at the top of step s
+        // (coalesced: lane r is contiguous) and consumed a whole step later.
+        float gn[NM][kNS];
+#pragma unroll
+        for (int i = 0; i < kNS; ++i) {
+            const float* src = ((unsigned)(0 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) gn[m][i] = src[m * 128];
+            goff[i] += gstep;
+        }
         for (int s = 0; s < p.steps; ++s) {
-            // ---- prefetch the input-projection gate pre-activations (coalesced: lane r is contiguous)
             float gi[NM][kNS];
 #pragma unroll
             for (int i = 0; i < kNS; ++i) {
-                const float* src = ((unsigned)(s - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
-                for (int m = 0; m < NM; ++m) gi[m][i] = src[m * 128];
-                goff[i] += gstep;
+                for (int m = 0; m < NM; ++m) gi[m][i] = gn[m][i];
             }
+            if (s + 1 < p.steps) {
+#pragma unroll
+                for (int i = 0; i < kNS; ++i) {
+                    const float* src = ((unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) gn[m][i] = src[m * 128];
+                    goff[i] += gstep;
+                }
+            }
+            if (ew == 0 && lane == 0) LSTM_TRACE(2, s);
             if (s > 0) {
                 mbar_wait(&sh->acc_ready, (uint32_t)((s - 1) & 1));
                 tcgen05_fence_after();
             }
+            if (ew == 0 && lane == 0) LSTM_TRACE(3, s);
             float a[NM][kNS];
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
@@ -224,6 +255,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                     a[m][i] = fmaf(k_mul, fast_rcp(1.0f + fast_ex2(k_in * x)), k_add);
                 }
             }
+            if (ew == 0 && lane == 0) LSTM_TRACE(4, s);
 #pragma unroll
             for (int i = 0; i < kNS; ++i) {
                 float ig, fg, gg, og;
@@ -250,11 +282,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                 }
                 ooff[i] += ostep;
             }
+            if (ew == 0 && lane == 0) LSTM_TRACE(5, s);
             if (s + 1 < p.steps) {
                 fence_proxy_async_smem();                // generic-proxy stores of h -> visible to the tensor core
                 tcgen05_fence_before();
                 mbar_arrive(&sh->h_ready);
             }
+            if (ew == 0 && lane == 0) LSTM_TRACE(6, s);
         }
     }
     tcgen05_fence_before();

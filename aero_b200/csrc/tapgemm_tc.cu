@@ -742,7 +742,7 @@ bool tapgemm_tc_eligible(const aero_tapgemm_params& p) {
     const bool f16 = (p.flags & AERO_TG_A_F16) != 0;
     const int q = f16 ? 8 : 4;
     if (p.mode == AERO_TAPS_MIX)
-        return p.w_sb == 0 && p.C1 % q == 0 && p.C2 == 0 && p.T % q == 0 && p.a1_st % q == 0 && p.a1_sb % q == 0 && p.N >= 8 &&
+        return p.w_sb == 0 && p.C1 % q == 0 && p.C2 == 0 && p.a1_st % q == 0 && p.a1_sb % q == 0 && p.N >= 8 &&
                p.stats_mode == 0 && !p.glu && p.F_out == 1 && p.F_in == 1;
     if (p.w_sb != 0) return false;                                   // activations-as-weights (FTB frequency mix)
     if (p.N < 8) return false;                                       // thin outputs stay on the SIMT path

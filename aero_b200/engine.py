@@ -118,6 +118,7 @@ class AeroEngine:
         #    gate pre-activations -- TF32's 10-bit mantissa at half the HBM bytes and twice the tensor-core rate;
         # 1: fp32-stored activations rounded to TF32 / tcgen05 kind::tf32;  0: exact fp32 SIMT kernels everywhere.
         self.precision = 2
+        self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
         self.last_glu_fp32 = False  # keep the last decoder layer's GLU output (input of the final transposed conv) in fp32
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
         self._prof, self._prof_tags = None, set()
@@ -152,11 +153,12 @@ class AeroEngine:
         if x.dtype != torch.float32:
             raise TypeError(f"aero_b200 computes in fp32; got {x.dtype}")
 
-    def _buf(self, name, *shape, dtype=torch.float32):
+    def _buf(self, name, *shape, dtype=torch.float32, zero=False):
+        """Cached workspace.  zero=True: zero-filled when created (row padding that no kernel writes must stay finite)."""
         key = (name, shape, dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=dtype, device=self._device())
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self._device())
             self._bufs[key] = t
         return t
 
@@ -217,6 +219,23 @@ class AeroEngine:
                 W[p + ".ftbfc.w"] = sd[q + ".freq_fc.weight"].contiguous()
                 w, b = fold_bn(sd[q + ".conv2.0.weight"][:, :, 0, 0], sd[q + ".conv2.0.bias"], q + ".conv2.1")
                 W[p + ".ftb2.w"], W[p + ".ftb2.b"] = pack_taps(w[:, :, None]), b.contiguous()
+                if g.index == 0:
+                    # FTB through the linear pre_conv (include/aero_b200.h, aero_ftb_lin_out_fwd): x = Wp z + bp
+                    Wp, bp = sd[p + ".pre_conv.weight"][:, :, 0, 0].double(), sd[p + ".pre_conv.bias"].double()
+                    w1, b1 = fold_bn(sd[q + ".conv1.0.weight"][:, :, 0, 0], sd[q + ".conv1.0.bias"], q + ".conv1.1")
+                    w1, b1 = w1.double(), b1.double()
+                    W[p + ".ftb1p.w"] = pack_taps((w1 @ Wp).float()[:, :, None])
+                    W[p + ".ftb1p.b"] = (w1 @ bp + b1).float().contiguous()
+                    w2, b2 = fold_bn(sd[q + ".conv2.0.weight"][:, :, 0, 0], sd[q + ".conv2.0.bias"], q + ".conv2.1")
+                    w2, b2 = w2.double(), b2.double()
+                    Cq, J = Wp.shape
+                    w2a, w2b = w2[:, :Cq], w2[:, Cq:]                                   # cat([freq_fc out, x]) (modules.py:322)
+                    ext = torch.cat([Wp, bp[:, None]], 1)                              # [C, J+1]
+                    Q = (w2a.t()[:, :, None] * ext[:, None, :]).reshape(Cq, Cq * (J + 1))   # Q[c][n*(J+1)+j]
+                    W[p + ".ftbQ.wf32"] = pack_taps(Q.t().float()[:, :, None])         # exact-fp32 GEMM (tiny): no tensor-core twin
+                    W[p + ".ftbV"] = (w2b @ Wp).float().contiguous()
+                    W[p + ".ftbd"] = (w2b @ bp + b2).float().contiguous()
+                    W[p + ".ftbs"] = sd[q + ".freq_fc.weight"].double().sum(1).float().contiguous()
             W[p + ".conv.w"] = pack_taps(sd[p + ".conv.weight"][:, :, :, 0])
             W[p + ".conv.b"] = sd[p + ".conv.bias"].contiguous()
             wr, br = sd[p + ".rewrite.weight"][:, :, 0, 0], sd[p + ".rewrite.bias"]
@@ -395,9 +414,16 @@ class AeroEngine:
                             (cabi.TG_OUT_F16 if out.dtype == torch.float16 else 0))
         cabi.check(self.lib.aero_local_attn_fwd(_ptr(qkvd), _ptr(out), C.byref(p), self._stream()), self.lib)
 
-    def _sample_norm(self, x, stats, y, affine, B, per_sample):
-        cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample, 0,
-                                                 self._stream()), self.lib)
+    def _sample_norm(self, x, stats, y, affine, B, per_sample, extent=None, rnd=False):
+        cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample,
+                                                 extent or per_sample, 1 if rnd else 0, self._stream()), self.lib)
+
+    def _ftb_lin_out(self, z, zm, M, s, V, d, out, *, B, F, T, N, J, zrow):
+        flags = cabi.TG_OUT_F16 if out.dtype == torch.float16 else (cabi.TG_ROUND_TF32 if self.precision >= 1 else 0)
+        p = cabi.FtbLinParams(B, F, T, N, J, flags, F * zrow, zrow, F * zrow, zrow)
+        cabi.check(self.lib.aero_ftb_lin_out_fwd(_ptr(z), _ptr(zm), _ptr(M), _ptr(s), _ptr(V), _ptr(d), _ptr(out),
+                                                 C.byref(p), self._stream()), self.lib)
+        return out
 
     def stft_into(self, x, z, stats, *, n_fft, hop, win, channels, bins_out, strides):
         n_sig, length = x.shape[0], x.shape[1]
@@ -472,6 +498,30 @@ class AeroEngine:
                    bias=W[p + ".ftb2.b"], act=ACT_RELU, rnd=True)
         return out
 
+    def _pre_ftb(self, xn, xr, W, p, B, Fq, T, J, Cc, tag, zrow):
+        """Encoder layer 0: pre_conv (aero.py:112) + FTB (modules.py:304-325) evaluated through the linearity of pre_conv
+        (include/aero_b200.h, aero_ftb_lin_out_fwd): the C-channel tensors pre_conv(z), freq_fc(..), cat(..) never exist.
+        xn: normalised spectrogram [B, Fq, zrow] (rows padded to 16 bytes); xr: its TF32-rounded copy for the tensor cores."""
+        r = 5
+        R = self._buf(tag + ".R", B, T, Fq * r, dtype=self._adt(Fq * r))
+        self._gemm(R, W[p + ".ftb1p.w"], a1=xn, B=B, F_out=Fq, T=T, N=r, C1=J, a1_s=(Fq * zrow, zrow, J),
+                   bias=W[p + ".ftb1p.b"], act=ACT_RELU, o_s=(T * Fq * r, r, Fq * r), rnd=True)
+        G = self._buf(tag + ".G", B, T, Cc)
+        self._gemm(G, W[p + ".ftb1d.w"], a1=R, B=B, F_out=1, T=T, N=Cc, C1=Fq * r, kt=9, pad_t=4,
+                   bias=W[p + ".ftb1d.b"], act=ACT_RELU, a1_s=(T * Fq * r, 0, Fq * r), o_s=(T * Cc, 0, Cc))
+        Zm = self._buf(tag + ".Zm", B, Fq, zrow, zero=True)
+        if xr is not None and Fq % 4 == 0 and Fq >= 8:
+            self._gemm(Zm, W[p + ".ftbfc.w@k"], a1=xr, mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * J, N=Fq, C1=Fq,
+                       a1_s=(Fq * zrow, 0, zrow), o_s=(Fq * zrow, 0, zrow), tag=p + ".ftbfc")
+        else:
+            self._gemm(Zm, xn, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * J, C1=Fq, a1_s=(0, 0, Fq),
+                       w_sb=Fq * zrow, o_s=(Fq * zrow, 0, zrow), tag=p + ".ftbfc")
+        M = self._buf(tag + ".M", B * T, Cc * (J + 1))
+        self._gemm_flat(M, G, W[p + ".ftbQ.wf32"], B * T, Cc, Cc * (J + 1))
+        out = self._buf(tag + ".out", B, Fq, T, Cc, dtype=self._adt(Cc))
+        return self._ftb_lin_out(xn, Zm, M, W[p + ".ftbs"], W[p + ".ftbV"], W[p + ".ftbd"], out, B=B, F=Fq, T=T, N=Cc,
+                                 J=J, zrow=zrow)
+
     def _blstm(self, h, W, o, rows, T, H, tag):
         """reference modules.py:32-65: framing, 2-layer BiLSTM, Linear, central-crop reassembly, skip."""
         if T > _LSTM_MAX_STEPS:
@@ -533,18 +583,26 @@ class AeroEngine:
                            op=NA_GLU_SCALE_RES, scale=W[o + ".ls"], residual=y, rnd=True)
         return y
 
-    def _encode(self, x, W, g, B, T):
+    def _encode(self, x, W, g, B, T, xr=None):
         """reference aero.py:108-135 (+ the frequency-embedding add aero.py:475-480 for layer 0)."""
         kw = self.geom.kw
         p = f"encoder.{g.index}"
         tag = f"e{g.index}"
         Fi, Fo, Cc = g.f_in, g.f_out, g.ch
         cin = g.enc_cin
+        fused = False
         if g.index == 0:
-            pre = self._buf(tag + ".pre", B, Fi, T, Cc, dtype=self._adt(Cc))
-            self._gemm_flat(pre, x, W[p + ".pre.w"], B * Fi * T, cin, Cc, bias=W[p + ".pre.b"], rnd=True)
-            x, cin = pre, Cc
-        if g.ftb:
+            zrow = x.shape[-1]                   # spectrogram rows [B, Fi, zrow]: T*cin floats padded to 16 bytes
+            fused = g.ftb and self.fuse_pre_ftb and cin in (2, 4) and Cc % 8 == 0 and Cc <= 128
+            if fused:
+                x = self._pre_ftb(x, xr, W, p, B, Fi, T, cin, Cc, tag + ".ftb", zrow)
+            else:
+                pre = self._buf(tag + ".pre", B, Fi, T, Cc, dtype=self._adt(Cc))
+                self._gemm(pre, W[p + ".pre.w"], a1=x, B=B, F_out=Fi, T=T, N=Cc, C1=cin, a1_s=(Fi * zrow, zrow, cin),
+                           bias=W[p + ".pre.b"], rnd=True)
+                x = pre
+            cin = Cc
+        if g.ftb and not fused:
             x = self._ftb(x, W, p, B, Fi, T, cin, tag + ".ftb")
         y = self._buf(tag + ".conv", B, Fo, T, Cc, dtype=self._adt(Cc))
         if g.norm:
@@ -681,17 +739,24 @@ class AeroEngine:
         C2 = 2 * Cin
 
         # STFT straight into channels-last [B, F, T, 2*Cin]; channel 2c+{0,1} = {re,im} (aero.py:430-434)
-        z = self._buf("z", B, Fq, T, C2)
+        # (rows of T*C2 floats padded to 16 bytes so that TMA can address them: the pad is zero and never read as data)
+        zrow = _pad4(T * C2)
+        z = self._buf("z", B, Fq, zrow, zero=True)
         st_in = self._stats.take(B)
         self.stft_into(x.view(B * Cin, Lp), z, st_in, n_fft=g.nfft, hop=g.hop_in, win=g.win_in, channels=Cin,
-                       bins_out=Fq, strides=(Fq * T * C2, 2, T * C2, C2))
-        xn = self._buf("xn", B, Fq, T, C2)
+                       bins_out=Fq, strides=(Fq * zrow, 2, zrow, C2))
+        xn = self._buf("xn", B, Fq, zrow)
         affine = self._buf("affine", B, 2)
-        self._sample_norm(z, st_in, xn, affine, B, Fq * T * C2)
+        self._sample_norm(z, st_in, xn, affine, B, Fq * T * C2, extent=Fq * zrow)
+        xr = None
+        l0 = g.layers[0]
+        if self.precision >= 1 and l0.ftb and self.fuse_pre_ftb:
+            xr = self._buf("xnr", B, Fq, zrow)        # TF32-rounded copy: the tensor-core operand of the frequency mix
+            self._sample_norm(z, st_in, xr, affine, B, Fq * T * C2, extent=Fq * zrow, rnd=True)
         h = xn
         saved = []
         for lg in g.layers:
-            h = self._encode(h, W, lg, B, T)
+            h = self._encode(h, W, lg, B, T, xr=xr if lg.index == 0 else None)
             saved.append(h)
         h = None
         for j, lg in enumerate(reversed(g.layers)):
@@ -710,5 +775,5 @@ class AeroEngine:
         zc = torch.view_as_complex(h.clone().view(B, Fq, T, Cout, 2)).permute(0, 3, 1, 2)
         if not return_lr_spec:
             return y, zc
-        zl = torch.view_as_complex(z.clone().view(B, Fq, T, Cin, 2)).permute(0, 3, 1, 2)
+        zl = torch.view_as_complex(z[:, :, :T * C2].reshape(B, Fq, T, Cin, 2)).permute(0, 3, 1, 2)
         return y, zc, zl

@@ -149,12 +149,13 @@ int aero_tapgemm_tc_eligible(const aero_tapgemm_params* p);
  * Normalisation / activation passes (HBM-bound elementwise kernels)
  *
  * aero_sample_norm_fwd: per-sample standardisation of the input spectrogram (reference
- *   aero.py:462-464): mean / unbiased std over `per_sample` floats from stats[b] = {sum, sumsq};
- *   y = (x - mean) / (1e-5 + std); also writes samp_affine[b] = {std, mean} for the output
+ *   aero.py:462-464): mean / unbiased std over `count` values from stats[b] = {sum, sumsq};
+ *   y = (x - mean) / (1e-5 + std) applied to `extent` (>= count; 0 means count) contiguous floats per sample -- rows may
+ *   carry alignment padding that the statistics did not see; also writes samp_affine[b] = {std, mean} for the output
  *   de-normalisation (aero.py:497-498).
  */
 int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* samp_affine,
-                         int32_t B, int64_t per_sample, int32_t round_tf32, aero_stream_t stream);
+                         int32_t B, int64_t count, int64_t extent, int32_t round_tf32, aero_stream_t stream);
 
 /* aero_norm_act_fwd: y = op(GroupNorm(x))   (replaces nn.GroupNorm + F.gelu / F.glu / Snake /
  *   LayerScale + residual: aero.py:127,133,198,206-214; modules.py:189,210,232-244; snake.py:67)
@@ -176,6 +177,24 @@ typedef struct {
 int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
                       const float* snake_a, const float* scale, const void* residual, void* y,
                       const aero_norm_act_params* p, aero_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FTB output conv through a linear input (encoder layer 0: `pre_conv` aero.py:89,112 followed by FTB modules.py:304-325).
+ * x = pre_conv(z) is linear in the J = 2*C_in spectrogram channels, and so is everything FTB does before its last ReLU:
+ *   out[b,f,t,n] = relu( sum_{j<J} M[b,t][n][j] * zm[b,f,t,j] + M[b,t][n][J] * s[f] + sum_{j<J} V[n][j] * z[b,f,t,j] + d[n] )
+ * with zm = freq_fc applied to z (AERO_TAPS_MIX), s[f] = sum_f' Wfc[f][f'], M[b,t] = gate[b,t,:] . Q,
+ *   Q[c][n*(J+1)+j] = W2a[n][c] * (j < J ? Wpre[c][j] : bpre[c]),  V = W2b Wpre,  d = W2b bpre + b2
+ * (W2 = [W2a | W2b] the BatchNorm-folded FTB conv2 acting on cat([freq_fc out, x]), modules.py:322-324).
+ * z, zm : fp32, element (b,f,t,j) at base + b*sb + f*sf + t*J + j;  M : fp32 [B*T][N*(J+1)];  out : [B][F][T][N] fp32 / FP16.
+ * The C-channel tensors pre_conv(z), freq_fc(..) and their concatenation are never materialised.
+ */
+typedef struct {
+    int32_t B, F, T, N, J;
+    int32_t flags;                    /* AERO_TG_OUT_F16 / AERO_TG_ROUND_TF32 */
+    int64_t z_sb, z_sf, zm_sb, zm_sf;
+} aero_ftb_lin_params;
+int aero_ftb_lin_out_fwd(const float* z, const float* zm, const float* M, const float* s, const float* V, const float* d,
+                         void* out, const aero_ftb_lin_params* p, aero_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Recurrent half of one bidirectional LSTM layer (replaces the cuDNN RNN behind nn.LSTM,

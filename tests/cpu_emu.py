@@ -31,6 +31,7 @@ class EmuEngine(AeroEngine):
         self._stats = None
         self.precision = 0
         self.last_glu_fp32 = False
+        self.fuse_pre_ftb = True
         self._seen = {}
         self._wh = {}
         self._prof, self._prof_tags = None, set()
@@ -213,7 +214,7 @@ class EmuEngine(AeroEngine):
         out.reshape(-1)[:r.numel()].copy_(r.float().reshape(-1))
 
     # ---- aero_sample_norm_fwd
-    def _sample_norm(self, x, stats, y, affine, B, per_sample):
+    def _sample_norm(self, x, stats, y, affine, B, per_sample, extent=None, rnd=False):
         self.calls.append(("sample_norm",))
         n = float(per_sample)
         mean = stats[:B, 0] / n
@@ -223,6 +224,17 @@ class EmuEngine(AeroEngine):
         y.reshape(B, -1).copy_(((xv - mean[:, None]) / (1e-5 + sd[:, None])).float())
         affine[:, 0] = sd.float()
         affine[:, 1] = mean.float()
+
+    # ---- aero_ftb_lin_out_fwd
+    def _ftb_lin_out(self, z, zm, M, s, V, d, out, *, B, F, T, N, J, zrow):
+        self.calls.append(("ftb_lin_out",))
+        zv = z.reshape(B, F, zrow)[:, :, :T * J].reshape(B, F, T, J).double()
+        zmv = zm.reshape(B, F, zrow)[:, :, :T * J].reshape(B, F, T, J).double()
+        Mv = M.reshape(B, T, N, J + 1).double()
+        x = torch.einsum("btnj,bftj->bftn", Mv[..., :J], zmv) + Mv[..., J][:, None] * s.double()[None, :, None, None]
+        x = x + torch.einsum("nj,bftj->bftn", V.double(), zv) + d.double()
+        out.copy_(x.clamp_min(0).float())
+        return out
 
     # ---- aero_stft_fwd / aero_istft_fwd
     def stft_into(self, x, z, stats, *, n_fft, hop, win, channels, bins_out, strides):

@@ -50,6 +50,7 @@ def test_struct_sizes_match_header(lib):
     assert ctypes.sizeof(cabi.NormActParams) == 11 * 4
     assert ctypes.sizeof(cabi.LstmParams) == 10 * 4
     assert ctypes.sizeof(cabi.AttnParams) == 7 * 4
+    assert ctypes.sizeof(cabi.FtbLinParams) == 6 * 4 + 4 * 8
 
 
 def test_oracle_is_not_imported_by_the_product():

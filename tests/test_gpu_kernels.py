@@ -188,6 +188,37 @@ def test_sample_norm(engines):
     assert rel_l2(outs[1][0], ref) < 1e-5
 
 
+@pytest.mark.parametrize("J,N,dt", [(2, 48, torch.float16), (2, 48, torch.float32), (4, 64, torch.float16)])
+def test_ftb_through_linear_input(engines, J, N, dt):
+    """aero_ftb_lin_out_fwd against the fp64 statement of its formula (padded spectrogram rows, ragged T)."""
+    gpu, emu = engines
+    B, F, T = 2, 9, 77
+    zrow = (T * J + 3) & ~3
+    z, zm = rnd(B, F, zrow, seed=1), rnd(B, F, zrow, seed=2)
+    M, s_, V, d = rnd(B * T, N * (J + 1), seed=3), rnd(F, seed=4), rnd(N, J, seed=5), rnd(N, seed=6)
+    ref = torch.zeros(B, F, T, N)
+    emu._ftb_lin_out(z, zm, M, s_, V, d, ref, B=B, F=F, T=T, N=N, J=J, zrow=zrow)
+    out = torch.full((B, F, T, N), float("nan"), device="cuda", dtype=dt)
+    gpu._ftb_lin_out(z.cuda(), zm.cuda(), M.cuda(), s_.cuda(), V.cuda(), d.cuda(), out, B=B, F=F, T=T, N=N, J=J, zrow=zrow)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out.float().cpu(), ref) < (4e-4 if dt == torch.float16 else 2e-6)
+
+
+def test_sample_norm_with_row_padding(engines):
+    """statistics over `count` values, transform applied to the padded extent (include/aero_b200.h)."""
+    gpu, _ = engines
+    B, rows, n, pad = 2, 5, 1002, 1004
+    x = torch.zeros(B, rows, pad)
+    x[:, :, :n] = rnd(B, rows, n, seed=1) * 2.0 + 0.5
+    xd = x[:, :, :n].double().reshape(B, -1)
+    stats = torch.stack([xd.sum(1), (xd * xd).sum(1)], 1)
+    y, aff = torch.zeros(B, rows, pad, device="cuda"), torch.zeros(B, 2, device="cuda")
+    gpu._sample_norm(x.cuda(), stats.cuda(), y, aff, B, rows * n, extent=rows * pad)
+    ref = (xd - xd.mean(1, keepdim=True)) / (1e-5 + xd.std(1, keepdim=True))
+    assert rel_l2(y.cpu()[:, :, :n].reshape(B, -1), ref.float()) < 1e-5
+
+
 def test_stft_istft_golden_and_roundtrip(golden_dir):
     """spectro / ispectro drop-ins against the reference's own outputs; round trip <= 1e-5 (north_star)."""
     from aero_b200 import ispectro, spectro

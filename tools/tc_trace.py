@@ -31,6 +31,18 @@ if __name__ == "__main__":
     sys.argv = [sys.argv[0], sys.argv[1], "--iters", "1"] + sys.argv[2:]
     kp.main()
     lib = cabi.load()
+    if sys.argv[1].startswith("lstm"):
+        buf = (C.c_longlong * (128 * 8))()
+        lib.aero_debug_lstm_trace.argtypes = [C.c_void_p]
+        assert lib.aero_debug_lstm_trace(buf) == 0
+        rows = [[buf[i * 8 + j] for j in range(8)] for i in range(128)]
+        names = ["mma:h_ready", "mma:commit", "upd:top", "upd:acc", "upd:act", "upd:h_stored", "upd:arrived"]
+        t0 = rows[1][0]
+        print("step " + " ".join(f"{n:>12s}" for n in names) + "   (cycles; update warp 0 lane 0)")
+        for i in range(1, int(os.environ.get("ROWS", 24))):
+            print(f"{i:4d} " + " ".join(f"{v - t0:12d}" if v else " " * 12 for v in rows[i][:7]))
+        print(f"steady state: {(rows[100][0] - rows[20][0]) / 80:.0f} cycles per step")
+        sys.exit(0)
     buf = (C.c_longlong * (256 * 8))()
     lib.aero_debug_tc_trace.argtypes = [C.c_void_p]
     assert lib.aero_debug_tc_trace(buf) == 0
