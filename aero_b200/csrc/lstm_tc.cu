@@ -139,8 +139,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                         const uint64_t da = make_desc_sw128(a0 + (uint32_t)((m * nK + kc) * 16384));
                         const uint64_t db = make_desc_sw128(b0 + (uint32_t)(kc * 2048));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(tmem_base + (uint32_t)(m * kNT), da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);   // K = 16 fp16 = 32 B
+                        for (int k = 0; k < 4; ++k)                  // K = 16 fp16 = 32 B per UMMA.  (Skipping the all-zero K padding
+                            umma_f16(tmem_base + (uint32_t)(m * kNT), da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);   // was measured slower: the guards break the back-to-back issue.)
                     }
                 }
                 umma_commit(&sh->acc_ready);
@@ -202,30 +202,44 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
 #pragma unroll
         for (int i = 0; i < kNS; ++i) c_state[i] = 0.f;
 
-        // The input-projection gate pre-activations stream from HBM (hundreds of MB per layer): their ~1 us load latency
-        // must not sit on the per-step dependency chain, so step s+1's values are requested at the top of step s
-        // (coalesced: lane r is contiguous) and consumed a whole step later.
-        float gn[NM][kNS];
+        // The input-projection gate pre-activations stream from HBM (hundreds of MB per layer); their ~1 us load latency must
+        // not sit on the per-step dependency chain.  GPT == 1 (one CTA per SM, registers to spare): step s+1's values are
+        // requested at the top of step s and consumed a whole step later.  GPT == 2 (two CTAs per SM, register-tight): the
+        // loads stay at the top of their own step, but step s+1's lines are pulled into L2 a step ahead.
+        constexpr bool kRegPrefetch = (GPT == 1);
+        float gn[kRegPrefetch ? NM : 1][kRegPrefetch ? kNS : 1];
+        if (kRegPrefetch) {
 #pragma unroll
-        for (int i = 0; i < kNS; ++i) {
-            const float* src = ((unsigned)(0 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+            for (int i = 0; i < kNS; ++i) {
+                const float* src = ((unsigned)(0 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
-            for (int m = 0; m < NM; ++m) gn[m][i] = src[m * 128];
-            goff[i] += gstep;
+                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * 128];
+                goff[i] += gstep;
+            }
         }
         for (int s = 0; s < p.steps; ++s) {
             float gi[NM][kNS];
-#pragma unroll
-            for (int i = 0; i < kNS; ++i) {
-#pragma unroll
-                for (int m = 0; m < NM; ++m) gi[m][i] = gn[m][i];
-            }
-            if (s + 1 < p.steps) {
+            if (kRegPrefetch) {
 #pragma unroll
                 for (int i = 0; i < kNS; ++i) {
-                    const float* src = ((unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) gn[m][i] = src[m * 128];
+                    for (int m = 0; m < NM; ++m) gi[m][i] = gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0];
+                }
+                if (s + 1 < p.steps) {
+#pragma unroll
+                    for (int i = 0; i < kNS; ++i) {
+                        const float* src = ((unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+#pragma unroll
+                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * 128];
+                        goff[i] += gstep;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kNS; ++i) {
+                    const float* src = ((unsigned)(s - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) gi[m][i] = src[m * 128];
                     goff[i] += gstep;
                 }
             }

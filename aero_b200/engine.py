@@ -224,7 +224,7 @@ class AeroEngine:
                     Wp, bp = sd[p + ".pre_conv.weight"][:, :, 0, 0].double(), sd[p + ".pre_conv.bias"].double()
                     w1, b1 = fold_bn(sd[q + ".conv1.0.weight"][:, :, 0, 0], sd[q + ".conv1.0.bias"], q + ".conv1.1")
                     w1, b1 = w1.double(), b1.double()
-                    W[p + ".ftb1p.w"] = pack_taps((w1 @ Wp).float()[:, :, None])
+                    W[p + ".ftb1p.w"] = (w1 @ Wp).float().contiguous()                  # [r, J]
                     W[p + ".ftb1p.b"] = (w1 @ bp + b1).float().contiguous()
                     w2, b2 = fold_bn(sd[q + ".conv2.0.weight"][:, :, 0, 0], sd[q + ".conv2.0.bias"], q + ".conv2.1")
                     w2, b2 = w2.double(), b2.double()
@@ -418,6 +418,13 @@ class AeroEngine:
         cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample,
                                                  extent or per_sample, 1 if rnd else 0, self._stream()), self.lib)
 
+    def _ftb_lin_squeeze(self, z, W1p, b1p, R, *, B, F, T, J, r, zrow):
+        flags = cabi.TG_OUT_F16 if R.dtype == torch.float16 else (cabi.TG_ROUND_TF32 if self.precision >= 1 else 0)
+        p = cabi.FtbLinParams(B, F, T, 0, J, flags, F * zrow, zrow, 0, 0)
+        cabi.check(self.lib.aero_ftb_lin_squeeze_fwd(_ptr(z), _ptr(W1p), _ptr(b1p), _ptr(R), r, C.byref(p), self._stream()),
+                   self.lib)
+        return R
+
     def _ftb_lin_out(self, z, zm, M, s, V, d, out, *, B, F, T, N, J, zrow):
         flags = cabi.TG_OUT_F16 if out.dtype == torch.float16 else (cabi.TG_ROUND_TF32 if self.precision >= 1 else 0)
         p = cabi.FtbLinParams(B, F, T, N, J, flags, F * zrow, zrow, F * zrow, zrow)
@@ -504,8 +511,7 @@ class AeroEngine:
         xn: normalised spectrogram [B, Fq, zrow] (rows padded to 16 bytes); xr: its TF32-rounded copy for the tensor cores."""
         r = 5
         R = self._buf(tag + ".R", B, T, Fq * r, dtype=self._adt(Fq * r))
-        self._gemm(R, W[p + ".ftb1p.w"], a1=xn, B=B, F_out=Fq, T=T, N=r, C1=J, a1_s=(Fq * zrow, zrow, J),
-                   bias=W[p + ".ftb1p.b"], act=ACT_RELU, o_s=(T * Fq * r, r, Fq * r), rnd=True)
+        self._ftb_lin_squeeze(xn, W[p + ".ftb1p.w"], W[p + ".ftb1p.b"], R, B=B, F=Fq, T=T, J=J, r=r, zrow=zrow)
         G = self._buf(tag + ".G", B, T, Cc)
         self._gemm(G, W[p + ".ftb1d.w"], a1=R, B=B, F_out=1, T=T, N=Cc, C1=Fq * r, kt=9, pad_t=4,
                    bias=W[p + ".ftb1d.b"], act=ACT_RELU, a1_s=(T * Fq * r, 0, Fq * r), o_s=(T * Cc, 0, Cc))
@@ -593,7 +599,7 @@ class AeroEngine:
         fused = False
         if g.index == 0:
             zrow = x.shape[-1]                   # spectrogram rows [B, Fi, zrow]: T*cin floats padded to 16 bytes
-            fused = g.ftb and self.fuse_pre_ftb and cin in (2, 4) and Cc % 8 == 0 and Cc <= 128
+            fused = g.ftb and self.fuse_pre_ftb and cin in (2, 4) and Cc % 8 == 0 and Cc <= 64
             if fused:
                 x = self._pre_ftb(x, xr, W, p, B, Fi, T, cin, Cc, tag + ".ftb", zrow)
             else:

@@ -195,6 +195,11 @@ typedef struct {
 } aero_ftb_lin_params;
 int aero_ftb_lin_out_fwd(const float* z, const float* zm, const float* M, const float* s, const float* V, const float* d,
                          void* out, const aero_ftb_lin_params* p, aero_stream_t stream);
+/* FTB squeeze (modules.py:286-291,308-309: 1x1 conv C -> r, BatchNorm, ReLU, regrouped to [B][T][F*r]) through the same
+ * linearity:  R[b][t][f*r + n] = relu( sum_j W1p[n][j] * z[b,f,t,j] + b1p[n] ),  W1p = W1 Wpre [r][J], b1p = W1 bpre + b1, r <= 8.
+ * R is fp32 or FP16 (flags); p->N is unused. */
+int aero_ftb_lin_squeeze_fwd(const float* z, const float* W1p, const float* b1p, void* R, int32_t r,
+                             const aero_ftb_lin_params* p, aero_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Recurrent half of one bidirectional LSTM layer (replaces the cuDNN RNN behind nn.LSTM,

@@ -225,6 +225,14 @@ class EmuEngine(AeroEngine):
         affine[:, 0] = sd.float()
         affine[:, 1] = mean.float()
 
+    # ---- aero_ftb_lin_squeeze_fwd
+    def _ftb_lin_squeeze(self, z, W1p, b1p, R, *, B, F, T, J, r, zrow):
+        self.calls.append(("ftb_lin_squeeze",))
+        zv = z.reshape(B, F, zrow)[:, :, :T * J].reshape(B, F, T, J).double()
+        x = (torch.einsum("nj,bftj->btfn", W1p.double(), zv) + b1p.double()).clamp_min(0)
+        R.copy_(x.reshape(B, T, F * r).float())
+        return R
+
     # ---- aero_ftb_lin_out_fwd
     def _ftb_lin_out(self, z, zm, M, s, V, d, out, *, B, F, T, N, J, zrow):
         self.calls.append(("ftb_lin_out",))

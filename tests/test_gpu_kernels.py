@@ -188,7 +188,7 @@ def test_sample_norm(engines):
     assert rel_l2(outs[1][0], ref) < 1e-5
 
 
-@pytest.mark.parametrize("J,N,dt", [(2, 48, torch.float16), (2, 48, torch.float32), (4, 64, torch.float16)])
+@pytest.mark.parametrize("J,N,dt", [(2, 48, torch.float16), (2, 48, torch.float32), (4, 64, torch.float16), (2, 24, torch.float16)])
 def test_ftb_through_linear_input(engines, J, N, dt):
     """aero_ftb_lin_out_fwd against the fp64 statement of its formula (padded spectrogram rows, ragged T)."""
     gpu, emu = engines
@@ -203,6 +203,20 @@ def test_ftb_through_linear_input(engines, J, N, dt):
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     assert rel_l2(out.float().cpu(), ref) < (4e-4 if dt == torch.float16 else 2e-6)
+
+
+@pytest.mark.parametrize("J,dt", [(2, torch.float16), (2, torch.float32), (4, torch.float16)])
+def test_ftb_squeeze_through_linear_input(engines, J, dt):
+    gpu, emu = engines
+    B, F, T, r = 2, 70, 45, 5
+    zrow = (T * J + 3) & ~3
+    z, W1p, b1p = rnd(B, F, zrow, seed=1), rnd(r, J, seed=2), rnd(r, seed=3)
+    ref = torch.zeros(B, T, F * r)
+    emu._ftb_lin_squeeze(z, W1p, b1p, ref, B=B, F=F, T=T, J=J, r=r, zrow=zrow)
+    R = torch.full((B, T, F * r), float("nan"), device="cuda", dtype=dt)
+    gpu._ftb_lin_squeeze(z.cuda(), W1p.cuda(), b1p.cuda(), R, B=B, F=F, T=T, J=J, r=r, zrow=zrow)
+    torch.cuda.synchronize()
+    assert torch.isfinite(R).all() and rel_l2(R.float().cpu(), ref) < (4e-4 if dt == torch.float16 else 2e-6)
 
 
 def test_sample_norm_with_row_padding(engines):
