@@ -63,6 +63,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
         : "memory");
 }
 
+// tcgen05.mma kind::f16 with the two shared-memory descriptors given as (low word, common high word) and a compile-time
+// accumulate flag: nothing but the low-word add is left on the issuing thread's dependency chain
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+
 template <int NSQ>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NSQ]);
 template <>
@@ -124,23 +138,39 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                     tma_load_2d(sA + (m * nK + kc) * 16384, &mapW, &sh->w_full, kc * 64, (dir * NM + m) * 128);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // The whole warp walks the step loop and one elected lane issues: with `elect.sync` the compiler knows the tcgen05
+        // instructions are issued by a single converged lane and does not wrap each of them in its own election loop.
+        {
             // UMMA instruction descriptor: D=F32 (1<<4), A=B=F16 (format 0), K-major, N=16, M=128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            // The issuing thread is on the per-step critical path (a single thread pays ~6 cycles per dependent instruction):
+            // every descriptor is step-invariant, so build them once; only the low word changes along K (+2 per 32 bytes).
+            uint32_t da_lo[NM][2], db_lo[2];
+            const uint32_t d_hi = (uint32_t)(make_desc_sw128(0) >> 32);
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                db_lo[kc] = (uint32_t)make_desc_sw128(b0 + (uint32_t)(kc * 2048));
+#pragma unroll
+                for (int m = 0; m < NM; ++m) da_lo[m][kc] = (uint32_t)make_desc_sw128(a0 + (uint32_t)((m * nK + kc) * 16384));
+            }
             mbar_wait(&sh->w_full, 0);
             for (int s = 1; s < p.steps; ++s) {
                 mbar_wait(&sh->h_ready, (uint32_t)((s - 1) & 1));
                 tcgen05_fence_after();
+                if (!elect_one()) continue;
                 LSTM_TRACE(0, s);
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
-                    for (int kc = 0; kc < nK; ++kc) {
-                        const uint64_t da = make_desc_sw128(a0 + (uint32_t)((m * nK + kc) * 16384));
-                        const uint64_t db = make_desc_sw128(b0 + (uint32_t)(kc * 2048));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)                  // K = 16 fp16 = 32 B per UMMA.  (Skipping the all-zero K padding
-                            umma_f16(tmem_base + (uint32_t)(m * kNT), da + 2 * k, db + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);   // was measured slower: the guards break the back-to-back issue.)
+                    for (int kc = 0; kc < 2; ++kc) {
+                        if (kc < nK) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {              // K = 16 fp16 = 32 B per UMMA
+                                if (kc == 0 && k == 0) umma_f16_lohi<false>(tmem_base + (uint32_t)(m * kNT), da_lo[m][kc], db_lo[kc], d_hi, idesc);
+                                else umma_f16_lohi<true>(tmem_base + (uint32_t)(m * kNT), da_lo[m][kc] + 2 * k, db_lo[kc] + 2 * k, d_hi, idesc);
+                            }
+                        }
                     }
                 }
                 umma_commit(&sh->acc_ready);
@@ -164,43 +194,52 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         // A step s reads the input projection iff (unsigned)(s - g_lo) < g_len (else the frame is zero padding: bias only)
         // and writes its output iff (unsigned)(s - w_lo) < w_len (window crop of modules.py:53-59 and the T limit).
         // For GPT=2 lane<16 updates even local sequences, lane>=16 odd ones.
-        int goff[kNS], ooff[kNS];
-        int g_lo[kNS], g_len[kNS], w_lo[kNS], w_len[kNS];
-        uint32_t baddr[kNS];
+        // A lane reads gate pre-activations for all kNS sequences of its warp, but finishes (cell state, h, stores) only
+        // kMS = kNS / GPT of them: sequence i = ii*GPT + sub (GPT == 2: the partner lane xor 16 finishes the others).
+        constexpr int kMS = kNS / GPT;
+        int goff[kNS], g_lo[kNS], g_len[kNS];
+        int ooff[kMS], w_lo[kMS], w_len[kMS];
+        uint32_t baddr[kMS];
         const int jq = (cell & 63) >> 3;
         const uint32_t bbase = smem_u32(sB) + (uint32_t)((cell >> 6) * 2048 + ((cell & 7) << 1));
 #pragma unroll
         for (int i = 0; i < kNS; ++i) {
             const int n = wp * kNS + i;
             const int sq = min(seq0 + n, n_seq - 1);
-            const bool exists = seq0 + n < n_seq;
             const int row = sq / p.n_win, k = sq - row * p.n_win;
             const int f0 = k * p.win_stride;                               // first frame of the window
-            const int frame_start = f0 + pos0;
-            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + frame_start)) * ldg + dir * (NM * 128) + r;
-            ooff[i] = (p.out_windowed ? (sq * p.steps + pos0) : (row * p.T + frame_start)) * 2 * H + dir * H + cell;
-            // valid positions of this window: input frames < T; kept output positions [lo, hi) intersected with frames < T
+            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + f0 + pos0)) * ldg + dir * (NM * 128) + r;
+            // valid input positions of this window: frames < T.  position -> step: dir 0: s = pos; dir 1: s = steps-1-pos
             const int in_hi = p.in_windowed ? p.steps : max(0, min(p.steps, p.T - f0));
+            g_lo[i] = dir ? p.steps - in_hi : 0;
+            g_len[i] = in_hi;
+        }
+#pragma unroll
+        for (int ii = 0; ii < kMS; ++ii) {
+            const int n = wp * kNS + ii * GPT + sub;
+            const int sq = min(seq0 + n, n_seq - 1);
+            const bool exists = seq0 + n < n_seq;
+            const int row = sq / p.n_win, k = sq - row * p.n_win;
+            const int f0 = k * p.win_stride;
+            ooff[ii] = (p.out_windowed ? (sq * p.steps + pos0) : (row * p.T + f0 + pos0)) * 2 * H + dir * H + cell;
+            // kept output positions [lo, hi) (window crop of modules.py:53-59) intersected with frames < T
             int lo = 0, hi = p.steps;
             if (!p.out_windowed) {
                 lo = (k == 0) ? 0 : half;
                 hi = min((k == p.n_win - 1) ? p.steps : p.steps - half, p.T - f0);
             }
             if (!exists || !cell_ok) hi = lo;
-            // position -> step: dir 0: s = pos; dir 1: s = steps-1-pos
-            g_lo[i] = dir ? p.steps - in_hi : 0;
-            g_len[i] = in_hi;
-            w_lo[i] = dir ? p.steps - hi : lo;
-            w_len[i] = max(0, hi - lo);
+            w_lo[ii] = dir ? p.steps - hi : lo;
+            w_len[ii] = max(0, hi - lo);
             // swizzled B-operand address of (sequence n, k = cell), fp16: tile kc = cell/64, row n (128 B), chunk (j/8)^(n%8)
-            baddr[i] = bbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4));
+            baddr[ii] = bbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4));
         }
         const float* bptr = bias_pad + dir * (NM * 128) + r;
         const int gstep = dpos * ldg, ostep = dpos * 2 * H;
 
-        float c_state[kNS];
+        float c_state[kMS];
 #pragma unroll
-        for (int i = 0; i < kNS; ++i) c_state[i] = 0.f;
+        for (int i = 0; i < kMS; ++i) c_state[i] = 0.f;
 
         // The input-projection gate pre-activations stream from HBM (hundreds of MB per layer); their ~1 us load latency must
         // not sit on the per-step dependency chain.  GPT == 1 (one CTA per SM, registers to spare): step s+1's values are
@@ -271,30 +310,30 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             }
             if (ew == 0 && lane == 0) LSTM_TRACE(4, s);
 #pragma unroll
-            for (int i = 0; i < kNS; ++i) {
+            for (int ii = 0; ii < kMS; ++ii) {
                 float ig, fg, gg, og;
-                bool mine = true;
                 if (GPT == 1) {
-                    ig = a[0][i]; fg = a[1 % NM][i]; gg = a[2 % NM][i]; og = a[3 % NM][i];
+                    ig = a[0][ii]; fg = a[1 % NM][ii]; gg = a[2 % NM][ii]; og = a[3 % NM][ii];
                 } else {
-                    const float p0 = __shfl_xor_sync(0xffffffffu, a[0][i], 16);
-                    const float p1 = __shfl_xor_sync(0xffffffffu, a[1 % NM][i], 16);
-                    if (sub == 0) { ig = a[0][i]; gg = a[1 % NM][i]; fg = p0; og = p1; }
-                    else          { fg = a[0][i]; og = a[1 % NM][i]; ig = p0; gg = p1; }
-                    mine = (i & 1) == sub;
+                    // this lane finishes sequence 2*ii + sub and hands its two gates of sequence 2*ii + (1 - sub) to the partner
+                    const int e = (2 * ii) % kNS, o = (2 * ii + 1) % kNS;
+                    const float own0 = sub ? a[0][o] : a[0][e], own1 = sub ? a[1 % NM][o] : a[1 % NM][e];
+                    const float snd0 = sub ? a[0][e] : a[0][o], snd1 = sub ? a[1 % NM][e] : a[1 % NM][o];
+                    const float p0 = __shfl_xor_sync(0xffffffffu, snd0, 16);
+                    const float p1 = __shfl_xor_sync(0xffffffffu, snd1, 16);
+                    if (sub == 0) { ig = own0; gg = own1; fg = p0; og = p1; }
+                    else          { fg = own0; og = own1; ig = p0; gg = p1; }
                 }
-                if (mine) {
-                    const float c = fmaf(fg, c_state[i], ig * gg);
-                    c_state[i] = c;
-                    const float th = fmaf(2.0f, fast_rcp(1.0f + fast_ex2(-2.885390081777927f * c)), -1.0f);
-                    const float h = round_tf32_rna(og * th);
-                    if (cell_ok) {
-                        const unsigned short hh = __half_as_ushort(__float2half_rn(h));
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(baddr[i]), "h"(hh) : "memory");
-                    }
-                    if ((unsigned)(s - w_lo[i]) < (unsigned)w_len[i]) stf(hout + ooff[i], h);
+                const float c = fmaf(fg, c_state[ii], ig * gg);
+                c_state[ii] = c;
+                const float th = fmaf(2.0f, fast_rcp(1.0f + fast_ex2(-2.885390081777927f * c)), -1.0f);
+                const float h = round_tf32_rna(og * th);
+                if (cell_ok) {
+                    const unsigned short hh = __half_as_ushort(__float2half_rn(h));
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(baddr[ii]), "h"(hh) : "memory");
                 }
-                ooff[i] += ostep;
+                if ((unsigned)(s - w_lo[ii]) < (unsigned)w_len[ii]) stf(hout + ooff[ii], h);
+                ooff[ii] += ostep;
             }
             if (ew == 0 && lane == 0) LSTM_TRACE(5, s);
             if (s + 1 < p.steps) {

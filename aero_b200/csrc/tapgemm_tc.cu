@@ -436,8 +436,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (the warp walks the pipeline, one elected lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -452,6 +452,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                     mbar_wait(&sh->full[stage], phase);
                     tcgen05_fence_after();
                     if (i == 0) AERO_TRACE(3, local);
+                    if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint64_t db = make_desc_sw128(sa + kATileBytes);
                     if (mix && F16A) {
@@ -480,9 +481,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                             umma<F16A>(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&sh->empty[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&sh->acc_full[buf]);
+                if (elect_one()) umma_commit(&sh->acc_full[buf]);
+                __syncwarp();
                 AERO_TRACE(4, local);
             }
         }
