@@ -17,11 +17,8 @@ constexpr int kAQ = 64;      // queries per CTA
 constexpr int kAKT = 128;    // keys per smem tile
 constexpr float kLog2e = 1.4426950408889634f;
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return u;
-}
+// round-to-nearest TF32 bit pattern in two integer instructions (ptxas expands cvt.rna.tf32.f32 into ~5)
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -115,12 +112,18 @@ __global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __rest
                     sc[u][1] = fmaf(-fabsf(d_lo + 1.f), slope_lo, sc[u][1]);
                     sc[u][2] = fmaf(-fabsf(d_hi), slope_hi, sc[u][2]);
                     sc[u][3] = fmaf(-fabsf(d_hi + 1.f), slope_hi, sc[u][3]);
-                    if (t_a == s_lo) sc[u][0] = kDiag;
-                    if (t_a + 1 == s_lo) sc[u][1] = kDiag;
-                    if (t_a == s_hi) sc[u][2] = kDiag;
-                    if (t_a + 1 == s_hi) sc[u][3] = kDiag;
-                    if (t_a >= p.T) { sc[u][0] = -1e30f; sc[u][2] = -1e30f; }          // padding keys of the last block
-                    if (t_a + 1 >= p.T) { sc[u][1] = -1e30f; sc[u][3] = -1e30f; }
+                    // the diagonal and the padding keys touch one or two key blocks per warp: keep them off the common path
+                    const int kb0 = k0 + kb * 8;                                       // (warp-uniform)
+                    if (kb0 < q0 + 16 && kb0 + 8 > q0) {
+                        if (t_a == s_lo) sc[u][0] = kDiag;
+                        if (t_a + 1 == s_lo) sc[u][1] = kDiag;
+                        if (t_a == s_hi) sc[u][2] = kDiag;
+                        if (t_a + 1 == s_hi) sc[u][3] = kDiag;
+                    }
+                    if (kb0 + 8 > p.T) {                                               // padding keys of the last block
+                        if (t_a >= p.T) { sc[u][0] = -1e30f; sc[u][2] = -1e30f; }
+                        if (t_a + 1 >= p.T) { sc[u][1] = -1e30f; sc[u][3] = -1e30f; }
+                    }
                     cm_lo = fmaxf(cm_lo, fmaxf(sc[u][0], sc[u][1]));
                     cm_hi = fmaxf(cm_hi, fmaxf(sc[u][2], sc[u][3]));
                 } else {

@@ -95,24 +95,15 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
     }
     const bool rnd = (p.flags & AERO_TG_ROUND_TF32) && sizeof(TO) == 4;
     const int64_t npix = (int64_t)(f_hi - f_lo) * p.T;                       // pixels of this segment (row-major f, t)
-    PixelWalk pw;                                                            // (row, t) of the pixel; no per-pixel division
-    pw.init((int64_t)blockIdx.y * ppp + dp, (int64_t)gridDim.y * ppp, p.T, 1 << 30);
-    for (int64_t pix = (int64_t)blockIdx.y * ppp + dp; pix < npix; pix += (int64_t)gridDim.y * ppp, pw.next()) {
-        const int fl = f_lo + pw.f;
-        const int t = pw.t;
-        const int fin = fl + p.f_off;
-        const float* xp = x + (((int64_t)b * p.F_in + fin) * p.T + t) * p.C;
-        const int64_t oidx = (((int64_t)b * p.F_out + fl) * p.T + t) * Cout + c;
-        const float4 v = *reinterpret_cast<const float4*>(xp + c);
+    // one pixel: normalise, activate, store (loads are issued by the caller so that two pixels' worth are in flight)
+    auto finish = [&](const float4 v, const float4 v2, const float4 rs, int fin, int64_t oidx) {
         float a[4] = {fmaf(v.x, k0.x, o0.x), fmaf(v.y, k0.y, o0.y), fmaf(v.z, k0.z, o0.z), fmaf(v.w, k0.w, o0.w)};
         float o[4];
         if (GLU) {
-            const float4 v2 = *reinterpret_cast<const float4*>(xp + c + Cout);
             const float gt[4] = {fmaf(v2.x, k1.x, o1.x), fmaf(v2.y, k1.y, o1.y), fmaf(v2.z, k1.z, o1.z), fmaf(v2.w, k1.w, o1.w)};
 #pragma unroll
             for (int u = 0; u < 4; ++u) o[u] = a[u] * sigmoid_f(gt[u]);
             if (OP == AERO_NA_GLU_SCALE_RES) {
-                const float4 rs = ld4(residual + oidx);
                 o[0] = fmaf(sc.x, o[0], rs.x); o[1] = fmaf(sc.y, o[1], rs.y);
                 o[2] = fmaf(sc.z, o[2], rs.z); o[3] = fmaf(sc.w, o[3], rs.w);
             }
@@ -136,6 +127,37 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
             for (int u = 0; u < 4; ++u) o[u] = round_tf32_rna(o[u]);
         }
         st4(y + oidx, make_float4(o[0], o[1], o[2], o[3]));
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t step = (int64_t)gridDim.y * ppp;
+    PixelWalk pw;                                                            // (row, t) of the pixel; no per-pixel division
+    pw.init((int64_t)blockIdx.y * ppp + dp, step, p.T, 1 << 30);
+    int64_t pix = (int64_t)blockIdx.y * ppp + dp;
+    for (; pix + step < npix; pix += 2 * step) {                             // two pixels per iteration
+        const int fl0 = f_lo + pw.f, t0 = pw.t;
+        pw.next();
+        const int fl1 = f_lo + pw.f, t1 = pw.t;
+        pw.next();
+        const float* xp0 = x + (((int64_t)b * p.F_in + fl0 + p.f_off) * p.T + t0) * p.C + c;
+        const float* xp1 = x + (((int64_t)b * p.F_in + fl1 + p.f_off) * p.T + t1) * p.C + c;
+        const int64_t oi0 = (((int64_t)b * p.F_out + fl0) * p.T + t0) * Cout + c;
+        const int64_t oi1 = (((int64_t)b * p.F_out + fl1) * p.T + t1) * Cout + c;
+        const float4 va = *reinterpret_cast<const float4*>(xp0), vb = *reinterpret_cast<const float4*>(xp1);
+        const float4 va2 = GLU ? *reinterpret_cast<const float4*>(xp0 + Cout) : zero4;
+        const float4 vb2 = GLU ? *reinterpret_cast<const float4*>(xp1 + Cout) : zero4;
+        const float4 ra = (OP == AERO_NA_GLU_SCALE_RES) ? ld4(residual + oi0) : zero4;
+        const float4 rb = (OP == AERO_NA_GLU_SCALE_RES) ? ld4(residual + oi1) : zero4;
+        finish(va, va2, ra, fl0 + p.f_off, oi0);
+        finish(vb, vb2, rb, fl1 + p.f_off, oi1);
+    }
+    if (pix < npix) {
+        const int fl0 = f_lo + pw.f, t0 = pw.t;
+        const float* xp0 = x + (((int64_t)b * p.F_in + fl0 + p.f_off) * p.T + t0) * p.C + c;
+        const int64_t oi0 = (((int64_t)b * p.F_out + fl0) * p.T + t0) * Cout + c;
+        const float4 va = *reinterpret_cast<const float4*>(xp0);
+        const float4 va2 = GLU ? *reinterpret_cast<const float4*>(xp0 + Cout) : zero4;
+        const float4 ra = (OP == AERO_NA_GLU_SCALE_RES) ? ld4(residual + oi0) : zero4;
+        finish(va, va2, ra, fl0 + p.f_off, oi0);
     }
 }
 

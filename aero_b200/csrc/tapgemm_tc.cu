@@ -633,25 +633,22 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
             mbar_arrive(&sh->acc_empty[buf]);
             if (q == 0 && lane == 0) AERO_TRACE(7, local);
             if (p.stats_mode != 0) {
-                // fixed-order reduction over the warps that drained this tile (all eight, or this group's four)
-                const int w_lo = grouped ? grp * 4 : 0, w_n = grouped ? 4 : kEpiWarps;
-                if (grouped) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                else asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int e = threadIdx.x - 64 - w_lo * 32;
-                if (e < 8) {
-                    float a = 0.f, c = 0.f;
-                    for (int w = w_lo; w < w_lo + w_n; ++w) { a += sh->stats[w][e][0]; c += sh->stats[w][e][1]; }
-                    const int gi = g_lo + e;
+                // every warp publishes its own partial sums (fp64 atomics: the order across warps / CTAs only moves the last
+                // bits of a double): no CTA-wide barrier on the per-tile path
+                __syncwarp();
+                if (lane < 8) {
+                    const float a = sh->stats[ew][lane][0], c = sh->stats[ew][lane][1];
+                    const int gi = g_lo + lane;
                     const int ngroups = (p.stats_mode == 1) ? p.groups : 1;
                     if (gi < ngroups && (a != 0.f || c != 0.f)) {
                         const int64_t slot = (p.stats_mode == 1) ? ((int64_t)b * p.groups + gi) : ((int64_t)b * p.F_out + fo);
                         atomicAdd(&g.stats[2 * slot], (double)a);
                         atomicAdd(&g.stats[2 * slot + 1], (double)c);
                     }
-                    for (int w = w_lo; w < w_lo + w_n; ++w) { sh->stats[w][e][0] = 0.f; sh->stats[w][e][1] = 0.f; }
+                    sh->stats[ew][lane][0] = 0.f;
+                    sh->stats[ew][lane][1] = 0.f;
                 }
-                if (grouped) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                else asm volatile("bar.sync 1, 256;" ::: "memory");
+                __syncwarp();
             }
         }
     }
