@@ -840,7 +840,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
         if ((rc = encode_map(&mW, g.w, 3, dims, strides, box, false, esz)) != AERO_OK) return rc;
     }
     g.tiles_t = cdiv(p.T, kBM);
-    g.grouped_bn = 64;
+    g.grouped_bn = 128;
     g.direct_f32 = 0;
     g.direct_f16 = 2;       // measured: the direct form wins for GLU outputs (one 16-byte store per lane), the transpose otherwise
     if (const char* e = getenv("AERO_TC_DIRECT_F32")) g.direct_f32 = atoi(e);

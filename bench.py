@@ -41,7 +41,8 @@ GFLOP_PER_CLIP_REQUIRED = 102.9
 # `ncu --set full` capture summarised in profiles/ (algorithmic bytes of that launch: 514 MB); None until captured
 TRAFFIC_NCU = {1: {"kernel": "tapgemm_tc_kernel<0,0,1,tf32> decoder.0.rw B=32", "bytes_per_launch": 473.8e6, "algorithmic_bytes": 513.7e6,
                    "tensor_pipe_pct": 80.8, "source": "profiles/r1_dec0rw_tc_ncu.md"},
-               2: None}
+               2: {"kernel": "tapgemm_tc_kernel<0,0,1,f16,f32> decoder.0.rw B=32", "bytes_per_launch": 401.7e6, "algorithmic_bytes": 453.9e6,
+                   "tensor_pipe_pct": 82.2, "source": "profiles/r1_dec0rw_f16_ncu.md"}}
 
 
 def peaks():
