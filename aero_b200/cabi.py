@@ -62,7 +62,7 @@ class AttnParams(C.Structure):
 ABI_VERSION = 2
 TAPS_CONV, TAPS_CONVT, TAPS_MIX = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-TG_ROUND_TF32, TG_A_F16, TG_OUT_F16 = 1, 2, 4      # storage-type flags (AERO_TG_*)
+TG_ROUND_TF32, TG_A_F16, TG_OUT_F16, TG_REVERSE = 1, 2, 4, 8      # storage-type flags (AERO_TG_*)
 NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES = 0, 1, 2, 3, 4
 
 # every symbol include/aero_b200.h declares (tests/test_cabi.py checks the library exports them all)

@@ -2,7 +2,8 @@
 // Used when aero_attn_params.flags has AERO_TG_ROUND_TF32 (the engine's tensor-core mode); attention.cu is the exact-fp32 twin.
 //
 // One CTA = one (row, head) and 64 queries (4 warps x 16).  K and V of that (row, head) stream through shared memory in
-// tiles of 128 keys, rounded to TF32 once while staging.  Per block of 8 keys a warp issues
+// double-buffered tiles of 64 keys filled by cp.async (16-byte chunks, zero fill past T) while the previous tile is being
+// consumed; the producing GEMM rounds q/k/v to TF32, so no conversion is needed on the way.  Per block of 8 keys a warp issues
 //   S[16 q x 8 keys]  = Q[16 x d] K^T        (d/8 mma, Q fragments live in registers, pre-scaled by log2(e)/sqrt(d))
 //   O[16 q x d]      += P[16 x 8] V[8 x d]   (d/8 mma)
 // The C-fragment of S is reused directly as the A-fragment of P by permuting the key order inside the block
@@ -14,7 +15,7 @@
 namespace aero {
 
 constexpr int kAQ = 64;      // queries per CTA
-constexpr int kAKT = 128;    // keys per smem tile
+constexpr int kAKT = 64;     // keys per smem tile (two buffers)
 constexpr float kLog2e = 1.4426950408889634f;
 
 // round-to-nearest TF32 bit pattern in two integer instructions (ptxas expands cvt.rna.tf32.f32 into ~5)
@@ -36,8 +37,11 @@ __global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __rest
     constexpr int DP = (D + 7) / 8 * 8;                  // 16 or 24
     constexpr int KS = DP / 8;                           // k-steps of QK^T == n-tiles of PV
     constexpr int PITCH = DP + 4;                        // 20 / 28: conflict-free fragment loads
-    __shared__ __align__(16) uint32_t Ks[kAKT * PITCH];
-    __shared__ __align__(16) uint32_t Vs[kAKT * PITCH];
+    __shared__ __align__(16) uint32_t Ksm[2][kAKT * PITCH];
+    __shared__ __align__(16) uint32_t Vsm[2][kAKT * PITCH];
+    constexpr int CH = D / 4;                            // 16-byte chunks per key row (D = 12 / 24)
+    for (int i = threadIdx.x; i < 2 * kAKT * PITCH; i += 128) { (&Ksm[0][0])[i] = 0u; (&Vsm[0][0])[i] = 0u; }   // padding columns stay zero
+    __syncthreads();
 
     const int row = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,22 +78,28 @@ __global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __rest
     float m_lo = -1e30f, m_hi = -1e30f, l_lo = 0.f, l_hi = 0.f;
     constexpr float kDiag = -100.0f * kLog2e;
 
-    for (int k0 = 0; k0 < p.T; k0 += kAKT) {
-        const int nk = min(kAKT, p.T - k0);
-        __syncthreads();
-        // stage K and V of this tile (TF32-rounded; keys beyond T and dims beyond D are zero)
-        for (int i = threadIdx.x; i < kAKT * DP; i += 128) {
-            const int t = i / DP, c = i - t * DP;
-            float kv = 0.f, vv = 0.f;
-            if (t < nk && c < D) {
-                const float* src = base + (int64_t)(k0 + t) * p.ld + h * D + c;
-                kv = src[p.H];
-                vv = src[2 * p.H];
-            }
-            Ks[t * PITCH + c] = to_tf32(kv);
-            Vs[t * PITCH + c] = to_tf32(vv);
+    // asynchronous fill of one tile: key rows beyond T are zero-filled (src-size 0)
+    auto fill = [&](int k0, int buf) {
+        for (int i = threadIdx.x; i < kAKT * CH * 2; i += 128) {
+            const int which = i / (kAKT * CH), j = i - which * (kAKT * CH);
+            const int t = j / CH, c4 = j - t * CH;
+            const bool ok = k0 + t < p.T;
+            const float* src = base + (int64_t)min(k0 + t, p.T - 1) * p.ld + (which + 1) * p.H + h * D + 4 * c4;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared((which ? &Vsm[buf][0] : &Ksm[buf][0]) + t * PITCH + 4 * c4);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fill(0, 0);
+    int it = 0;
+    for (int k0 = 0; k0 < p.T; k0 += kAKT, ++it) {
+        const int nk = min(kAKT, p.T - k0);
+        if (k0 + kAKT < p.T) fill(k0 + kAKT, (it + 1) & 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
+        const uint32_t* Ks = &Ksm[it & 1][0];
+        const uint32_t* Vs = &Vsm[it & 1][0];
         const int nblk = (nk + 7) >> 3;
         for (int cb = 0; cb < nblk; cb += 4) {               // chunk of up to 4 key blocks = 32 keys
             float sc[4][4];
@@ -159,6 +169,7 @@ __global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __rest
                 }
             }
         }
+        __syncthreads();                                 // this buffer is refilled by the prefetch issued one iteration from now
     }
     // row sums across the quad, normalise, store (C fragment: cols nt*8 + 2 tig, +1)
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
@@ -184,7 +195,7 @@ __global__ void __launch_bounds__(128) local_attn_mma_kernel(const float* __rest
 
 int local_attn_mma_launch(const float* qkvd, void* out, const aero_attn_params& p, cudaStream_t st, bool* taken) {
     const int d = p.H / p.heads;
-    *taken = (d == 12 || d == 24);
+    *taken = (d == 12 || d == 24) && p.ld % 4 == 0 && p.H % 4 == 0 && (reinterpret_cast<uintptr_t>(qkvd) & 15) == 0;   // 16-byte cp.async chunks
     if (!*taken) return AERO_OK;
     dim3 grid(cdiv(p.T, kAQ), p.heads, p.rows);
     if (p.flags & AERO_TG_OUT_F16) {

@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
                                                        const TO* residual, TO* y,
                                                        const aero_norm_act_params p) {
     constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
-    const int seg = blockIdx.x;                       // scope 1: b ; scope 2: b*F_in + f
+    // grid = (chunks, segments): the chunks of one segment are scheduled together; AERO_TG_REVERSE walks both from the end
+    const bool rev = p.flags & AERO_TG_REVERSE;
+    const int seg = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;      // scope 1: b ; scope 2: b*F_in + f
+    const int chunk = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
     __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
     if (threadIdx.x < p.groups) {
         const double n = (p.scope == 1) ? (double)p.F_in * p.T * (p.C / p.groups) : (double)p.T * p.C;
@@ -129,10 +132,10 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
         st4(y + oidx, make_float4(o[0], o[1], o[2], o[3]));
     };
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t step = (int64_t)gridDim.y * ppp;
+    const int64_t step = (int64_t)gridDim.x * ppp;
     PixelWalk pw;                                                            // (row, t) of the pixel; no per-pixel division
-    pw.init((int64_t)blockIdx.y * ppp + dp, step, p.T, 1 << 30);
-    int64_t pix = (int64_t)blockIdx.y * ppp + dp;
+    pw.init((int64_t)chunk * ppp + dp, step, p.T, 1 << 30);
+    int64_t pix = (int64_t)chunk * ppp + dp;
     for (; pix + step < npix; pix += 2 * step) {                             // two pixels per iteration
         const int fl0 = f_lo + pw.f, t0 = pw.t;
         pw.next();
@@ -199,8 +202,8 @@ extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const floa
     // ~8 pixels per thread; keep at least a few CTAs per SM in flight across all segments
     int chunks = (int)((npix + (int64_t)ppp * 8 - 1) / ((int64_t)ppp * 8));
     if (chunks < 1) chunks = 1;
-    if (chunks > 65535) chunks = 65535;
-    dim3 grid(nseg, chunks);
+    AERO_REQUIRE(nseg <= 65535, "aero_norm_act_fwd: at most 65535 segments (got %d)", nseg);
+    dim3 grid(chunks, nseg);
     cudaStream_t st = (cudaStream_t)stream;
     const bool o16 = p->flags & AERO_TG_OUT_F16;
 #define AERO_NA_LAUNCH(OP)                                                                                                  \

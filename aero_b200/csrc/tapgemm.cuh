@@ -25,6 +25,7 @@ struct TapGemmArgs {
     uint32_t dv_mul[3], dv_shr[3];
     int direct_f16;   // FP16 outputs: same choice
     int direct_f32;   // fp32 outputs: direct lane-per-row epilogue instead of the shared-memory transpose
+    int last_tile;    // tiles_total - 1 (reverse walk)
     int grouped_bn;   // tiles with BN <= this use the two-group epilogue
 };
 int tapgemm_simt_launch(const TapGemmArgs& g, cudaStream_t st);

@@ -101,6 +101,7 @@ __device__ __forceinline__ int valid_taps(const aero_tapgemm_params& p, int fo, 
 __device__ __forceinline__ TileCoord tile_coord(const TapGemmArgs& g, int tile, int n_tiles, int BN, int nch1, int nch2) {
     const aero_tapgemm_params& p = g.p;
     TileCoord c;
+    if (p.flags & AERO_TG_REVERSE) tile = g.last_tile - tile;       // walk from the end: see AERO_TG_REVERSE
     const int mt = fast_div(tile, g.dv_mul[0], g.dv_shr[0]), nt = tile - mt * n_tiles;
     const int row = fast_div(mt, g.dv_mul[1], g.dv_shr[1]), tt = mt - row * g.tiles_t;
     c.b = fast_div(row, g.dv_mul[2], g.dv_shr[2]);
@@ -911,6 +912,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     if (const char* e = getenv("AERO_TC_PER_SM")) per_sm = atoi(e) < per_sm ? atoi(e) : per_sm;
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)num_sms * per_sm;
+    g.last_tile = (int)tiles_total - 1;
     dim3 grid((unsigned)(tiles_total < want ? tiles_total : want));
     kern<<<grid, kThreads, smem, st>>>(mA1, mA2, mW, g, BN, idesc, tmem_cols, kStages, n_tiles, (int)tiles_total);
     return check_launch("aero_tapgemm_fwd(tcgen05)");

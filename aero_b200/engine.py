@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -118,6 +119,8 @@ class AeroEngine:
         #    gate pre-activations -- TF32's 10-bit mantissa at half the HBM bytes and twice the tensor-core rate;
         # 1: fp32-stored activations rounded to TF32 / tcgen05 kind::tf32;  0: exact fp32 SIMT kernels everywhere.
         self.precision = 2
+        self.snake = os.environ.get("AERO_SNAKE", "0") == "1"   # (measured: no gain, off) alternate the walk direction of consecutive tap-GEMM / norm_act launches (L2 reuse)
+        self._flip = False
         self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
         self.last_glu_fp32 = False  # keep the last decoder layer's GLU output (input of the final transposed conv) in fp32
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
@@ -345,7 +348,7 @@ class AeroEngine:
         if residual is not None and residual.dtype != out.dtype:
             raise TypeError("aero_b200: residual and output of a tap-GEMM must share a storage type")
         flags = (cabi.TG_ROUND_TF32 if (rnd and self.precision >= 1 and not o16) else 0) | (cabi.TG_A_F16 if a16 else 0) | \
-                (cabi.TG_OUT_F16 if o16 else 0)
+                (cabi.TG_OUT_F16 if o16 else 0) | (cabi.TG_REVERSE if self._next_dir() else 0)
         p = cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
                                act, glu, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 0, flags)
         if mode == cabi.TAPS_MIX:
@@ -367,6 +370,14 @@ class AeroEngine:
             ntaps = kf * kt if mode == TAPS_CONV else kf // stride_f
             self._prof.append((tag, e0, e1, 2.0 * B * F_out * T * N * (C1 + C2) * ntaps))
         return out
+
+    def _next_dir(self):
+        """Walk direction of the next tap-GEMM / norm_act launch: alternating, so that a consumer starts where its producer
+        just finished (that part of the tensor is still in L2)."""
+        if not self.snake:
+            return False
+        self._flip = not self._flip
+        return self._flip
 
     def start_profile(self, tags):
         """Time the tap-GEMM launches whose tag is in `tags` with CUDA events on the launch stream."""
@@ -394,7 +405,7 @@ class AeroEngine:
             raise TypeError("aero_b200: norm_act reads fp32 and its residual shares the output's storage type")
         p = cabi.NormActParams(B, F_in, F_in if F_out is None else F_out, f_off, T, C_, groups, scope, op, 1e-5,
                                (cabi.TG_ROUND_TF32 if (rnd and self.precision >= 1 and not o16) else 0) |
-                               (cabi.TG_OUT_F16 if o16 else 0))
+                               (cabi.TG_OUT_F16 if o16 else 0) | (cabi.TG_REVERSE if self._next_dir() else 0))
         rc = self.lib.aero_norm_act_fwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(snake_a), _ptr(scale),
                                         _ptr(residual), _ptr(y), C.byref(p), self._stream())
         cabi.check(rc, self.lib)
@@ -555,7 +566,8 @@ class AeroEngine:
         """reference modules.py:94-127."""
         ld = 3 * H + _ATTN_HEADS * _ATTN_NDECAY
         qkvd = self._buf(tag + ".qkvd", rows * T, ld)
-        self._gemm_flat(qkvd, h, W[o + ".qkvd.w"], rows * T, H, ld, bias=W[o + ".qkvd.b"])
+        # (fp32 output rounded to TF32 by the epilogue: the attention kernel feeds q/k/v to mma.sync without converting)
+        self._gemm_flat(qkvd, h, W[o + ".qkvd.w"], rows * T, H, ld, bias=W[o + ".qkvd.b"], rnd=True)
         r = self._buf(tag + ".attn", rows * T, H, dtype=self._adt(H))
         self._attn(qkvd, r, rows=rows, T=T, H=H, heads=_ATTN_HEADS, ndecay=_ATTN_NDECAY, ld=ld)
         self._gemm_flat(h, r, W[o + ".proj.w"], rows * T, H, H, bias=W[o + ".proj.b"], residual=h, rnd=True)

@@ -136,7 +136,10 @@ typedef struct {
 enum {
     AERO_TG_ROUND_TF32 = 1,           /* fp32 outputs: round stored values to TF32 (round-to-nearest) for a kind::tf32 consumer */
     AERO_TG_A_F16 = 2,                /* a1 / a2 are FP16 */
-    AERO_TG_OUT_F16 = 4               /* out and residual are FP16 */
+    AERO_TG_OUT_F16 = 4,              /* out and residual are FP16 */
+    AERO_TG_REVERSE = 8               /* tap-GEMM (tcgen05 path) / norm_act: walk tiles / rows from the end.  Results are identical;
+                                         a kernel launched right after its producer then starts on the data the producer wrote last,
+                                         which is still in the 126 MB L2 (the host alternates the direction from launch to launch) */
 };
 int aero_tapgemm_fwd(const void* a1, const void* a2, const void* w, const float* bias,
                      const float* addend_fn, const float* colscale, const void* residual,

@@ -32,6 +32,8 @@ class EmuEngine(AeroEngine):
         self.precision = 0
         self.last_glu_fp32 = False
         self.fuse_pre_ftb = True
+        self.snake = False
+        self._flip = False
         self._seen = {}
         self._wh = {}
         self._prof, self._prof_tags = None, set()
