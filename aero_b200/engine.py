@@ -121,6 +121,7 @@ class AeroEngine:
         self.precision = 2
         self.snake = os.environ.get("AERO_SNAKE", "0") == "1"   # (measured: no gain, off) alternate the walk direction of consecutive tap-GEMM / norm_act launches (L2 reuse)
         self._flip = False
+        self.lstm_tc = True         # tcgen05 LSTM recurrence (re-ordered gate layout) when precision >= 1
         self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
         self.last_glu_fp32 = False  # keep the last decoder layer's GLU output (input of the final transposed conv) in fp32
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
@@ -547,7 +548,7 @@ class AeroEngine:
         else:
             steps, stride, n_win = T, 0, 1
         n_seq = rows * n_win
-        tc = self.precision >= 1 and H % 4 == 0 and 32 < H <= 96
+        tc = self.lstm_tc and self.precision >= 1 and H % 4 == 0 and 32 < H <= 96
         L0, L1, G = ("lstm0r", "lstm1r", 2 * (2 if H <= 64 else 4) * 128) if tc else ("lstm0", "lstm1", 8 * H)
         gin1 = self._buf(tag + ".gin1", rows * T, G)
         self._gemm_flat(gin1, h, W[f"{o}.{L0}.ih.w"], rows * T, H, G, bias=W[f"{o}.{L0}.b"])

@@ -32,6 +32,7 @@ class EmuEngine(AeroEngine):
         self.precision = 0
         self.last_glu_fp32 = False
         self.fuse_pre_ftb = True
+        self.lstm_tc = False          # the emulation states the recurrence in PyTorch's gate layout
         self.snake = False
         self._flip = False
         self._seen = {}
@@ -55,6 +56,14 @@ class EmuEngine(AeroEngine):
               f_off=0, bias=None, act=cabi.ACT_NONE, glu=0, stats=None, stats_mode=0, groups=1, addend=None,
               colscale=None, cs_s=(0, 0), residual=None, r_s=None, samp_affine=None, w_sb=0, tag=None, rnd=False):
         self.calls.append(("tapgemm", N, C1 + C2))
+        if mode == cabi.TAPS_MIX:
+            # out[b][n][m] = colscale[b][m] * sum_k a1[b][k][m] * W[n][k]   (w: K-major twin, rows possibly padded)
+            Av = torch.as_strided(a1.reshape(-1), (B, C1, T), (a1_s[0], a1_s[2], 1)).double()
+            v = torch.einsum("nk,bkm->bnm", w.reshape(N, -1)[:, :C1].double(), Av)
+            if colscale is not None:
+                v = v * torch.as_strided(colscale.reshape(-1), (B, 1, T), (cs_s[0], 0, 1)).double()
+            torch.as_strided(out.reshape(-1), (B, N, T), (o_s[0], o_s[2], 1)).copy_(v.float())
+            return out
         F_in = F_out if F_in is None else F_in
         T_in = T if T_in is None else T_in
         n_out = N // 2 if glu else N

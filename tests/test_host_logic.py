@@ -47,6 +47,25 @@ def test_engine_windowed_lstm_and_stereo_match_oracle():
     assert {"stft", "istft", "tapgemm", "norm_act", "lstm", "attn", "sample_norm"} <= kinds
 
 
+@pytest.mark.parametrize("precision", [2, 1])
+def test_storage_type_plumbing_of_the_tensor_core_engines(precision):
+    """engine.precision 2 / 1 on the CPU emulation: the real host logic picks FP16 / fp32 buffers, K-major weight twins, the
+    MN-major frequency mix and the fused layer-0 path; the emulation stores through those dtypes, so the FP16 activation
+    rounding is real (the arithmetic is exact): the error budget of the default engine, measured without a GPU."""
+    m = make("aero_4-16_512_256")
+    eng = m._engine_obj
+    eng.precision = precision
+    mix = white_noise((2, 1, 4100))
+    with torch.no_grad():
+        ref = O.aero_forward(m.state_dict(), m.geom, mix)
+    out = m(mix)
+    err = rel_l2(out, ref)
+    dts = {t.dtype for t in eng._bufs.values()}
+    print(f"precision {precision}: rel_l2 {err:.2e}, buffer dtypes {sorted(str(d) for d in dts)}")
+    assert (torch.float16 in dts) == (precision == 2)
+    assert err < (1e-3 if precision == 2 else 2e-5)
+
+
 def test_spec_roundtrip_api_shapes():
     m = make("aero_4-16_512_64")
     x = white_noise((2, 1, 4000))
