@@ -110,7 +110,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
     const int seq0 = blockIdx.x * kNT;
     const int n_seq = p.rows * p.n_win;
     const int H = p.H;
-    const int ldg = 2 * NM * 128;                        // floats per gin row (both directions, padded)
+    const int ldg = 8 * H;                               // floats per gin row: [dir][i,f,g,o][H], PyTorch's own order
 
     if (threadIdx.x == 0) {
         mbar_init(&sh->w_full, 1);
@@ -196,6 +196,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         // For GPT=2 lane<16 updates even local sequences, lane>=16 odd ones.
         // A lane reads gate pre-activations for all kNS sequences of its warp, but finishes (cell state, h, stores) only
         // kMS = kNS / GPT of them: sequence i = ii*GPT + sub (GPT == 2: the partner lane xor 16 finishes the others).
+        // gate pre-activation column of this lane in tile 0 (tile m adds m * GPT * H): gate = m*GPT + sub, this lane's cell
+        // (clamped for the padding lanes of the last cells: their values are never used)
+        const int gcol = dir * 4 * H + sub * H + min(cell, H - 1);
+        const int gtile = GPT * H;
         constexpr int kMS = kNS / GPT;
         int goff[kNS], g_lo[kNS], g_len[kNS];
         int ooff[kMS], w_lo[kMS], w_len[kMS];
@@ -208,7 +212,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             const int sq = min(seq0 + n, n_seq - 1);
             const int row = sq / p.n_win, k = sq - row * p.n_win;
             const int f0 = k * p.win_stride;                               // first frame of the window
-            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + f0 + pos0)) * ldg + dir * (NM * 128) + r;
+            goff[i] = (p.in_windowed ? (sq * p.steps + pos0) : (row * p.T + f0 + pos0)) * ldg + gcol;
             // valid input positions of this window: frames < T.  position -> step: dir 0: s = pos; dir 1: s = steps-1-pos
             const int in_hi = p.in_windowed ? p.steps : max(0, min(p.steps, p.T - f0));
             g_lo[i] = dir ? p.steps - in_hi : 0;
@@ -234,7 +238,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             // swizzled B-operand address of (sequence n, k = cell), fp16: tile kc = cell/64, row n (128 B), chunk (j/8)^(n%8)
             baddr[ii] = bbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4));
         }
-        const float* bptr = bias_pad + dir * (NM * 128) + r;
+        const float* bptr = bias_pad + gcol;
         const int gstep = dpos * ldg, ostep = dpos * 2 * H;
 
         float c_state[kMS];
@@ -252,7 +256,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             for (int i = 0; i < kNS; ++i) {
                 const float* src = ((unsigned)(0 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
-                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * 128];
+                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * gtile];
                 goff[i] += gstep;
             }
         }
@@ -269,7 +273,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                     for (int i = 0; i < kNS; ++i) {
                         const float* src = ((unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
-                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * 128];
+                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * gtile];
                         goff[i] += gstep;
                     }
                 }
@@ -278,7 +282,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                 for (int i = 0; i < kNS; ++i) {
                     const float* src = ((unsigned)(s - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) gi[m][i] = src[m * 128];
+                    for (int m = 0; m < NM; ++m) gi[m][i] = src[m * gtile];
                     goff[i] += gstep;
                 }
             }
@@ -381,7 +385,7 @@ int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, v
     }
     const int n_seq = p.rows * p.n_win;
     const int64_t max_rows = (int64_t)n_seq * p.steps > (int64_t)p.rows * p.T ? (int64_t)n_seq * p.steps : (int64_t)p.rows * p.T;
-    if ((max_rows + p.steps) * (2 * nM * 128) >= (1ll << 31)) {
+    if ((max_rows + p.steps) * (8ll * H) >= (1ll << 31)) {
         set_error("aero_lstm_rec_fwd(tcgen05): problem too large for 32-bit offsets (%lld rows)", (long long)max_rows);
         return AERO_ERR_UNSUPPORTED;
     }

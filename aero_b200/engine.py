@@ -277,13 +277,7 @@ class AeroEngine:
                         for l in range(2):
                             def reord(t):
                                 return torch.where(ok.view(-1, *([1] * (t.dim() - 1))), t[src], torch.zeros_like(t[src]))
-                            wih, whh, bb = [], [], []
-                            for sfx in ("", "_reverse"):
-                                wih.append(reord(sd[f"{q}.lstm.lstm.weight_ih_l{l}{sfx}"]))
-                                whh.append(reord(sd[f"{q}.lstm.lstm.weight_hh_l{l}{sfx}"]))
-                                bb.append(reord(sd[f"{q}.lstm.lstm.bias_ih_l{l}{sfx}"] + sd[f"{q}.lstm.lstm.bias_hh_l{l}{sfx}"]))
-                            W[f"{o}.lstm{l}r.ih.w"] = pack_taps(torch.cat(wih, 0)[:, :, None])
-                            W[f"{o}.lstm{l}r.b"] = torch.cat(bb).contiguous()
+                            whh = [reord(sd[f"{q}.lstm.lstm.weight_hh_l{l}{sfx}"]) for sfx in ("", "_reverse")]
                             W[f"{o}.lstm{l}r.whh"] = lstm_whh_fp16(torch.cat(whh, 0))
                         W[o + ".lin.w"] = pack_taps(sd[q + ".lstm.linear.weight"][:, :, None])
                         W[o + ".lin.b"] = sd[q + ".lstm.linear.bias"].contiguous()
@@ -549,16 +543,19 @@ class AeroEngine:
             steps, stride, n_win = T, 0, 1
         n_seq = rows * n_win
         tc = self.lstm_tc and self.precision >= 1 and H % 4 == 0 and 32 < H <= 96
-        L0, L1, G = ("lstm0r", "lstm1r", 2 * (2 if H <= 64 else 4) * 128) if tc else ("lstm0", "lstm1", 8 * H)
+        # the input projections use PyTorch's own [dir][i,f,g,o][H] column order on both paths; only W_hh is re-ordered
+        # (tile / lane order, FP16) for the tcgen05 recurrence
+        G = 8 * H
+        whh0, whh1 = (W[f"{o}.lstm0r.whh"], W[f"{o}.lstm1r.whh"]) if tc else (W[f"{o}.lstm0.whh"], W[f"{o}.lstm1.whh"])
         gin1 = self._buf(tag + ".gin1", rows * T, G)
-        self._gemm_flat(gin1, h, W[f"{o}.{L0}.ih.w"], rows * T, H, G, bias=W[f"{o}.{L0}.b"])
+        self._gemm_flat(gin1, h, W[f"{o}.lstm0.ih.w"], rows * T, H, G, bias=W[f"{o}.lstm0.b"])
         h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H, dtype=self._adt(2 * H))
-        self._lstm_rec(gin1, W[f"{o}.{L0}.b"], W[f"{o}.{L0}.whh"], h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+        self._lstm_rec(gin1, W[f"{o}.lstm0.b"], whh0, h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
                        stride=stride, in_windowed=0, out_windowed=1, tc=tc)
         gin2 = self._buf(tag + ".gin2", n_seq * steps, G)
-        self._gemm_flat(gin2, h1, W[f"{o}.{L1}.ih.w"], n_seq * steps, 2 * H, G, bias=W[f"{o}.{L1}.b"])
+        self._gemm_flat(gin2, h1, W[f"{o}.lstm1.ih.w"], n_seq * steps, 2 * H, G, bias=W[f"{o}.lstm1.b"])
         h2 = self._buf(tag + ".h2", rows * T, 2 * H, dtype=self._adt(2 * H))
-        self._lstm_rec(gin2, W[f"{o}.{L1}.b"], W[f"{o}.{L1}.whh"], h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
+        self._lstm_rec(gin2, W[f"{o}.lstm1.b"], whh1, h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
                        stride=stride, in_windowed=1, out_windowed=0, tc=tc)
         self._gemm_flat(h, h2, W[o + ".lin.w"], rows * T, 2 * H, H, bias=W[o + ".lin.b"], residual=h, rnd=True)
         return h

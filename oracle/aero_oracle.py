@@ -194,19 +194,19 @@ def local_state(x, sd, prefix, heads=4, ndecay=4, explicit=False):
     k = proj("key").view(N, heads, -1, T)
     v = proj("content").view(N, heads, -1, T)
     dq = torch.sigmoid(proj("query_decay").view(N, heads, ndecay, T)) / 2
-    idx = torch.arange(T, dtype=x.dtype)
+    idx = torch.arange(T, dtype=x.dtype, device=x.device)
     dist = (idx[:, None] - idx[None, :]).abs()                    # [t(key), s(query)]
     if not explicit:
         dots = torch.einsum("bhct,bhcs->bhts", k, q) / k.shape[2] ** 0.5
-        decays = torch.arange(1, ndecay + 1, dtype=x.dtype)
+        decays = torch.arange(1, ndecay + 1, dtype=x.dtype, device=x.device)
         kern = -decays.view(-1, 1, 1) * dist / ndecay ** 0.5
         dots = dots + torch.einsum("fts,bhfs->bhts", kern, dq)
-        dots.masked_fill_(torch.eye(T, dtype=torch.bool), -100)
+        dots.masked_fill_(torch.eye(T, dtype=torch.bool, device=x.device), -100)
         w = torch.softmax(dots, dim=2)
         r = torch.einsum("bhts,bhct->bhcs", w, v)
     else:
         # closed form: the decay term is -|t-s| * slope[s], slope = sum_f f*dq_f / sqrt(ndecay)
-        f = torch.arange(1, ndecay + 1, dtype=x.dtype).view(1, 1, -1, 1)
+        f = torch.arange(1, ndecay + 1, dtype=x.dtype, device=x.device).view(1, 1, -1, 1)
         slope = (f * dq).sum(2) / ndecay ** 0.5                   # [N, h, s]
         d = k.shape[2]
         r = torch.empty_like(v)

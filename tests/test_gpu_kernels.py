@@ -375,20 +375,16 @@ def test_lstm_layer_pair_tcgen05(engines, H, T, rows):
 
     src, ok = lstm_gate_reorder(H)
 
-    def cols(t):      # [..., 2*4H] PyTorch order -> [..., 2*nM*128] re-ordered, zero padded
-        parts = [torch.where(ok, t[..., d * 4 * H:(d + 1) * 4 * H][..., src], torch.zeros(())) for d in range(2)]
-        return torch.cat(parts, -1).contiguous()
-
     def rows_(w):     # [2, 4H, H] -> [2*nM*128, H]
         return lstm_whh_fp16(torch.cat([torch.where(ok[:, None], w[d][src], torch.zeros(())) for d in range(2)], 0))
 
     gpu.precision = 1
     try:
         h1 = torch.zeros(n_seq * steps, 2 * H, device="cuda")
-        gpu._lstm_rec(cols(gin1).cuda(), cols(b1).cuda(), rows_(whh1).cuda(), h1, rows=rows, T=T, H=H, n_win=n_win,
+        gpu._lstm_rec(gin1.cuda(), b1.cuda(), rows_(whh1).cuda(), h1, rows=rows, T=T, H=H, n_win=n_win,
                       steps=steps, stride=stride, in_windowed=0, out_windowed=1, tc=True)
         h2 = torch.zeros(rows * T, 2 * H, device="cuda")
-        gpu._lstm_rec(cols(gin2).cuda(), cols(b1).cuda(), rows_(whh2).cuda(), h2, rows=rows, T=T, H=H, n_win=n_win,
+        gpu._lstm_rec(gin2.cuda(), b1.cuda(), rows_(whh2).cuda(), h2, rows=rows, T=T, H=H, n_win=n_win,
                       steps=steps, stride=stride, in_windowed=1, out_windowed=0, tc=True)
         torch.cuda.synchronize()
     finally:

@@ -45,7 +45,7 @@ def run_lstm(args):
     eng = AeroEngine(m)
     eng.precision = args.precision
     tc = args.precision >= 1
-    G = 2 * (2 if H <= 64 else 4) * 128 if tc else 8 * H
+    G = 8 * H
     gin = torch.randn(rows * n_win * steps, G, device="cuda")
     bias = torch.randn(G, device="cuda")
     whh = torch.randn(2, 4 * H, H) / math.sqrt(H)
