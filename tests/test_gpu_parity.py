@@ -185,6 +185,8 @@ def test_faster_than_pytorch_eager_on_the_same_gpu():
         pytest.skip(f"oracle does not run on this GPU: {str(e)[:200]}")
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for _ in range(3):                       # (the third call of a shape captures its CUDA graph: keep that out of the timing)
+        m(x)
     ms_ours = timed(lambda: m(x), n=5)
     print(f"B=32 x 2 s forward: PyTorch eager on this GPU {ms_eager_fp32:.1f} ms (fp32) / {ms_eager_tf32:.1f} ms (TF32 allowed); "
           f"aero_b200 {ms_ours:.2f} ms -> {ms_eager_tf32 / ms_ours:.1f}x")
