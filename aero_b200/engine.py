@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import os
 
 import torch
 
@@ -119,7 +118,9 @@ class AeroEngine:
         #    gate pre-activations -- TF32's 10-bit mantissa at half the HBM bytes and twice the tensor-core rate;
         # 1: fp32-stored activations rounded to TF32 / tcgen05 kind::tf32;  0: exact fp32 SIMT kernels everywhere.
         self.precision = 2
-        self.snake = os.environ.get("AERO_SNAKE", "0") == "1"   # (measured: no gain, off) alternate the walk direction of consecutive tap-GEMM / norm_act launches (L2 reuse)
+        # alternate the walk direction of consecutive tap-GEMM / norm_act launches (AERO_TG_REVERSE) so that a consumer starts
+        # on what its producer wrote last; measured on B200: no gain for this model (12.19 ms either way), so off
+        self.snake = False
         self._flip = False
         self.lstm_tc = True         # tcgen05 LSTM recurrence (re-ordered gate layout) when precision >= 1
         self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
