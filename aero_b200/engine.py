@@ -695,7 +695,7 @@ class AeroEngine:
         """Public entry (behind Aero.forward).  With ``use_graph`` the ~110 launches of one forward are captured once per
         input shape into a CUDA graph and replayed: identical kernels and results, no per-launch host cost (this is what
         matters at batch 1, where the eager path is host-bound)."""
-        if not self.use_graph or return_spec or self._prof is not None:
+        if not self.use_graph or return_spec or self._prof is not None or mix.shape[0] == 0:
             return self._forward(mix, return_spec, return_lr_spec)
         self._require(mix)
         key = (tuple(mix.shape), tuple(p._version for p in self.model.parameters()), self.precision, self.fp32_tags)
@@ -738,6 +738,18 @@ class AeroEngine:
         kw = g.kw
         if mix.dim() != 3 or mix.shape[1] != kw["in_channels"]:
             raise ValueError(f"expected input [B, {kw['in_channels']}, L], got {tuple(mix.shape)}")
+        if mix.shape[0] == 0:
+            # an empty batch maps to an empty batch (clips are independent); nothing to launch
+            hop = g.hop_in
+            Lp = mix.shape[2] + (-mix.shape[2]) % hop
+            Tn, Fq0 = 1 + Lp // hop, g.nfft // 2
+            y0 = mix.new_zeros(0, kw["out_channels"], min(int(mix.shape[2] * g.scale), g.hop_out * (Tn - 1)))
+            if not return_spec:
+                return y0
+            zc0 = torch.zeros(0, kw["out_channels"], Fq0, Tn, dtype=torch.complex64, device=mix.device)
+            if not return_lr_spec:
+                return y0, zc0
+            return y0, zc0, torch.zeros(0, kw["in_channels"], Fq0, Tn, dtype=torch.complex64, device=mix.device)
         W = self._weights()
         B_ = mix.shape[0]
         need = B_ + sum((2 * B_ * kw["norm_groups"] if lg.norm else 0) * 2 +

@@ -259,6 +259,16 @@ int aero_local_attn_fwd(const float* qkvd, void* out, const aero_attn_params* p,
 int aero_lsd_fwd(const float* z_ref, const float* z_est, double* out_sum, int32_t B, int32_t bins, int32_t frames,
                  int32_t n_fft, aero_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-resolution STFT loss, forward value (reference src/models/stft_loss.py:11-27,30-63,96-138).
+ * z_est, z_ref : planar complex spectrograms [B][bins][frames] (float2) of the estimate and the target as written by
+ * aero_stft_fwd (normalised) at ONE resolution; with mag = sqrt(max(n_fft |z|^2, 1e-7)):
+ *   sums[0] += sum (mag_ref - mag_est)^2;  sums[1] += sum mag_ref^2;  sums[2] += sum |log mag_ref - log mag_est|
+ * -> spectral convergence = sqrt(sums[0]/sums[1]), log-magnitude L1 = sums[2] / (B*bins*frames).  The caller zeroes `sums`.
+ */
+int aero_stft_loss_fwd(const float* z_est, const float* z_ref, double* sums, int32_t B, int32_t bins, int32_t frames,
+                       int32_t n_fft, aero_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -358,3 +358,22 @@ def aero_forward(sd, geom, mix, return_spec=False, return_lr_spec=False, explici
     if return_spec:
         return (out, zc, z) if return_lr_spec else (out, zc)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-resolution STFT loss, forward value
+def mrstft_loss(x, y, fft_sizes=(1024, 2048, 512), hop_sizes=(120, 240, 50), win_lengths=(600, 1200, 240),
+                factor_sc=0.1, factor_mag=0.1):
+    """reference src/models/stft_loss.py:96-138 (`MultiResolutionSTFTLoss.forward`): per resolution, magnitudes
+    sqrt(clamp(re^2 + im^2, 1e-7)) of the un-normalised centred STFT (`:11-27`), spectral convergence
+    ||mag_y - mag_x||_F / ||mag_y||_F (`:30-45`) and L1 of the log magnitudes (`:48-63`); both averaged over the
+    resolutions and scaled.  x = estimate, y = target, [B, T]."""
+    sc, mag = 0.0, 0.0
+    for n_fft, hop, win in zip(fft_sizes, hop_sizes, win_lengths):
+        w = torch.hann_window(win, dtype=x.dtype, device=x.device)
+        mx = torch.stft(x, n_fft, hop, win, w, return_complex=True).abs().square().clamp_min(1e-7).sqrt()
+        my = torch.stft(y, n_fft, hop, win, w, return_complex=True).abs().square().clamp_min(1e-7).sqrt()
+        sc = sc + torch.linalg.norm(my - mx) / torch.linalg.norm(my)
+        mag = mag + (my.log() - mx.log()).abs().mean()
+    k = len(fft_sizes)
+    return factor_sc * sc / k, factor_mag * mag / k

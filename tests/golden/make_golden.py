@@ -106,6 +106,42 @@ def main():
         blob[f"{i}/y"] = y.numpy()
         print("stft case", i, tuple(z.shape), tuple(y.shape))
     np.savez_compressed(os.path.join(HERE, "stft_cases.npz"), **blob)
+    make_mrstft(ref)
+
+
+MRSTFT_CASES = [  # batch, length, seed offset, scale of the estimate's perturbation
+    (2, 32000, 0, 0.3),
+    (3, 9000, 1, 1.0),
+]
+
+
+def make_mrstft(ref):
+    """Multi-resolution STFT loss (reference src/models/stft_loss.py:96-138) on seeded signals.  The reference's `stft()`
+    (`:22`) calls torch.stft without return_complex and raises on torch >= 2: the module is used unmodified except that
+    its `torch.stft` is wrapped to return the real view it expects (the one-line shim of SURVEY.md appendix C)."""
+    mod = ref["stft_loss"]
+
+    class _TorchShim:
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def stft(x, fft_size, hop_size, win_length, window):
+            return torch.view_as_real(torch.stft(x, fft_size, hop_size, win_length, window, return_complex=True))
+    mod.torch = _TorchShim()
+    loss = mod.MultiResolutionSTFTLoss()
+    blob = {}
+    for i, (B, L, so, eps) in enumerate(MRSTFT_CASES):
+        y = white_noise((B, L), seed=SEED + 100 + so)
+        x = y + eps * white_noise((B, L), seed=SEED + 200 + so)
+        if i == 1:
+            x[:, :2000] = 0.0                                   # exercise the 1e-7 clamp
+        sc, mag = loss(x, y)
+        blob[f"{i}/params"] = np.array([B, L, so], dtype=np.int64)
+        blob[f"{i}/eps"] = np.array(eps)
+        blob[f"{i}/sc"], blob[f"{i}/mag"] = np.array(float(sc)), np.array(float(mag))
+        print("mrstft case", i, float(sc), float(mag))
+    np.savez_compressed(os.path.join(HERE, "mrstft_cases.npz"), **blob)
 
 
 if __name__ == "__main__":

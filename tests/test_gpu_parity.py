@@ -191,3 +191,31 @@ def test_faster_than_pytorch_eager_on_the_same_gpu():
     print(f"B=32 x 2 s forward: PyTorch eager on this GPU {ms_eager_fp32:.1f} ms (fp32) / {ms_eager_tf32:.1f} ms (TF32 allowed); "
           f"aero_b200 {ms_ours:.2f} ms -> {ms_eager_tf32 / ms_ours:.1f}x")
     assert ms_ours < ms_eager_tf32
+
+
+def test_empty_batch_and_too_short_clip():
+    """edge cases of the boundary: an empty batch maps to an empty batch; a clip shorter than the reflect padding raises
+    (as torch.stft does in the reference) instead of reading out of bounds."""
+    m = build("aero_4-16_512_256").cuda()
+    out, zc, zl = m(torch.zeros(0, 1, 8000, device="cuda"), return_spec=True, return_lr_spec=True)
+    assert out.shape == (0, 1, 32000) and zc.shape[:3] == (0, 1, 256) and zl.shape[:3] == (0, 1, 256)
+    with pytest.raises(Exception, match="reflect padding"):
+        m(white_noise((1, 1, 200)).cuda())
+
+
+def test_mrstft_loss_matches_reference_golden(golden_dir):
+    """aero_b200.losses.MultiResolutionSTFTLoss (aero_stft_fwd + aero_stft_loss_fwd) against
+    the values of the reference's module on the same seeded signals."""
+    from aero_b200.losses import MultiResolutionSTFTLoss
+    from test_oracle import _mrstft_inputs
+    g = np.load(os.path.join(golden_dir, "mrstft_cases.npz"))
+    loss = MultiResolutionSTFTLoss()
+    i = 0
+    while f"{i}/params" in g.files:
+        x, y = _mrstft_inputs(g, i)
+        sc, mag = loss(x.cuda(), y.cuda())
+        print(f"mrstft case {i}: sc {float(sc):.6f} (ref {float(g[f'{i}/sc']):.6f}) mag {float(mag):.6f} (ref {float(g[f'{i}/mag']):.6f})")
+        assert abs(float(sc) - float(g[f"{i}/sc"])) < 2e-5 * float(g[f"{i}/sc"])
+        assert abs(float(mag) - float(g[f"{i}/mag"])) < 1e-4 * float(g[f"{i}/mag"])
+        i += 1
+    assert i >= 2

@@ -114,3 +114,27 @@ def test_oracle_vs_live_reference_blocks():
             assert rel_l2(a, b) < 1e-5
         mix = white_noise((1, 1, 5000))
         assert rel_l2(O.aero_forward(sd, mine.geom, mix), rmodel(mix)) < 1e-5
+
+
+def _mrstft_inputs(g, i):
+    B, L, so = (int(v) for v in g[f"{i}/params"])
+    eps = float(g[f"{i}/eps"])
+    y = white_noise((B, L), seed=SEED + 100 + so)
+    x = y + eps * white_noise((B, L), seed=SEED + 200 + so)
+    if i == 1:
+        x[:, :2000] = 0.0
+    return x, y
+
+
+def test_mrstft_loss_oracle_matches_reference_golden(golden_dir):
+    """the loss restatement against values produced by the reference's own module
+    (tests/golden/make_golden.py::make_mrstft)."""
+    g = np.load(os.path.join(golden_dir, "mrstft_cases.npz"))
+    i = 0
+    while f"{i}/params" in g.files:
+        x, y = _mrstft_inputs(g, i)
+        sc, mag = O.mrstft_loss(x, y)
+        assert abs(float(sc) - float(g[f"{i}/sc"])) <= 1e-6 * abs(float(g[f"{i}/sc"])) + 1e-9
+        assert abs(float(mag) - float(g[f"{i}/mag"])) <= 1e-6 * abs(float(g[f"{i}/mag"])) + 1e-9
+        i += 1
+    assert i >= 2

@@ -79,7 +79,7 @@ def import_reference():
     path_saved = list(sys.path)
     sys.path[:] = [ref_root] + [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
     try:
-        mods = {n: importlib.import_module("src.models." + n) for n in ("aero", "spec", "modules")}
+        mods = {n: importlib.import_module("src.models." + n) for n in ("aero", "spec", "modules", "stft_loss")}
     finally:
         sys.path[:] = path_saved
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
