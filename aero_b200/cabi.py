@@ -79,6 +79,7 @@ SYMBOLS = {
     "aero_norm_act_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
     "aero_ftb_lin_out_fwd": (C.c_int, [vp] * 7 + [C.POINTER(FtbLinParams), vp]),
     "aero_ftb_lin_squeeze_fwd": (C.c_int, [vp, vp, vp, vp, i32, C.POINTER(FtbLinParams), vp]),
+    "aero_freq_mix_small_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i32, vp]),
     "aero_lstm_rec_fwd": (C.c_int, [vp, vp, vp, vp, C.POINTER(LstmParams), vp]),
     "aero_local_attn_fwd": (C.c_int, [vp, vp, C.POINTER(AttnParams), vp]),
     "aero_lsd_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),

@@ -177,3 +177,67 @@ extern "C" int aero_ftb_lin_squeeze_fwd(const float* z, const float* W1p, const 
 #undef AERO_SQ
     return check_launch("aero_ftb_lin_squeeze_fwd");
 }
+
+// ------------------------------------------------------------------------------------------------
+// FTB frequency mix for the deep layers (F = 8 / 16 rows): out[b][g][m] = gate[b][m] * sum_f W[g][f] * x[b][f][m].
+// With so few rows the tensor-core tile (128 pixels x F) is all per-tile overhead (measured 170 us for 98 MB at F = 8);
+// here a thread keeps the F inputs of 4 consecutive positions in registers and produces the F outputs: one read and one
+// write of the tensor at copy bandwidth.
+namespace aero {
+
+template <int F, typename TA, typename TO>
+__global__ void __launch_bounds__(256) freq_mix_small_kernel(const TA* __restrict__ x, const float* __restrict__ W,
+                                                             const float* __restrict__ gate, TO* __restrict__ out,
+                                                             const int64_t M, const int flags) {
+    __shared__ float ws[F * F];
+    for (int i = threadIdx.x; i < F * F; i += 256) ws[i] = W[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const bool rnd = sizeof(TO) == 4 && (flags & AERO_TG_ROUND_TF32);
+    const TA* xb = x + (int64_t)b * F * M;
+    TO* ob = out + (int64_t)b * F * M;
+    for (int64_t m = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; m < M; m += (int64_t)gridDim.x * 256 * 4) {
+        float4 v[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = ld4(xb + (int64_t)f * M + m);
+        const float4 gt = gate ? *reinterpret_cast<const float4*>(gate + (int64_t)b * M + m) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int g = 0; g < F; ++g) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float w = ws[g * F + f];
+                a.x = fmaf(w, v[f].x, a.x); a.y = fmaf(w, v[f].y, a.y); a.z = fmaf(w, v[f].z, a.z); a.w = fmaf(w, v[f].w, a.w);
+            }
+            a.x *= gt.x; a.y *= gt.y; a.z *= gt.z; a.w *= gt.w;
+            if (rnd) { a.x = round_tf32_rna(a.x); a.y = round_tf32_rna(a.y); a.z = round_tf32_rna(a.z); a.w = round_tf32_rna(a.w); }
+            st4(ob + (int64_t)g * M + m, a);
+        }
+    }
+}
+
+template <int F>
+static int freq_mix_small_go(const void* x, const float* W, const float* gate, void* out, int B, int64_t M, int flags, cudaStream_t st) {
+    int blocks = (int)((M / 4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dim3 grid(blocks < 1 ? 1 : blocks, B);
+    const bool a16 = flags & AERO_TG_A_F16, o16 = flags & AERO_TG_OUT_F16;
+    if (a16 && o16) freq_mix_small_kernel<F, __half, __half><<<grid, 256, 0, st>>>((const __half*)x, W, gate, (__half*)out, M, flags);
+    else if (!a16 && !o16) freq_mix_small_kernel<F, float, float><<<grid, 256, 0, st>>>((const float*)x, W, gate, (float*)out, M, flags);
+    else { set_error("aero_freq_mix_small_fwd: input and output must share a storage type"); return AERO_ERR_UNSUPPORTED; }
+    return check_launch("aero_freq_mix_small_fwd");
+}
+
+}  // namespace aero
+
+extern "C" int aero_freq_mix_small_fwd(const void* x, const float* W, const float* gate, void* out, int32_t B, int32_t F, int64_t M,
+                                       int32_t flags, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && W && out && B >= 1 && B <= 65535 && M >= 4, "aero_freq_mix_small_fwd: bad argument");
+    AERO_REQUIRE(M % 4 == 0 && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)gate) & 15) == 0, "aero_freq_mix_small_fwd: M %% 4 and 16-byte alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F == 8) return freq_mix_small_go<8>(x, W, gate, out, B, M, flags, st);
+    if (F == 16) return freq_mix_small_go<16>(x, W, gate, out, B, M, flags, st);
+    set_error("aero_freq_mix_small_fwd: F=%d (8 or 16)", F);
+    return AERO_ERR_UNSUPPORTED;
+}

@@ -425,6 +425,12 @@ class AeroEngine:
         cabi.check(self.lib.aero_sample_norm_fwd(_ptr(x), _ptr(stats), _ptr(y), _ptr(affine), B, per_sample,
                                                  extent or per_sample, 1 if rnd else 0, self._stream()), self.lib)
 
+    def _freq_mix_small(self, x, Wfc, gate, out, *, B, F, M):
+        flags = (cabi.TG_A_F16 | cabi.TG_OUT_F16) if x.dtype == torch.float16 else (cabi.TG_ROUND_TF32 if self.precision >= 1 else 0)
+        cabi.check(self.lib.aero_freq_mix_small_fwd(_ptr(x), _ptr(Wfc), _ptr(gate), _ptr(out), B, F, M, flags, self._stream()),
+                   self.lib)
+        return out
+
     def _ftb_lin_squeeze(self, z, W1p, b1p, R, *, B, F, T, J, r, zrow):
         flags = cabi.TG_OUT_F16 if R.dtype == torch.float16 else (cabi.TG_ROUND_TF32 if self.precision >= 1 else 0)
         p = cabi.FtbLinParams(B, F, T, 0, J, flags, F * zrow, zrow, 0, 0)
@@ -496,7 +502,10 @@ class AeroEngine:
         Y = self._buf(tag + ".Y", B, Fq, T, Cc, dtype=x.dtype)
         x16 = x.dtype == torch.float16
         q = 8 if x16 else 4
-        if self.precision >= 1 and Fq % q == 0 and Fq >= 8 and (T * Cc) % q == 0 and \
+        if self.precision >= 1 and Fq in (8, 16) and (T * Cc) % 4 == 0:
+            # deep layers: too few rows for tensor-core tiles -- one pass at copy bandwidth (csrc/ftb_lin.cu)
+            self._freq_mix_small(x, W[p + ".ftbfc.w"], G, Y, B=B, F=Fq, M=T * Cc)
+        elif self.precision >= 1 and Fq % q == 0 and Fq >= 8 and (T * Cc) % q == 0 and \
                 not (self.fp32_tags and (p + ".ftbfc").startswith(self.fp32_tags)):
             # frequency mixing on the tensor cores: contraction over the row axis, activations as the MN-major operand
             self._gemm(Y, W[p + (".ftbfc.w@h" if x16 else ".ftbfc.w@k")], a1=x, mode=cabi.TAPS_MIX, B=B, F_out=1, T=T * Cc,
@@ -530,7 +539,7 @@ class AeroEngine:
             self._gemm(Zm, xn, a1=W[p + ".ftbfc.w"], B=B, F_out=1, T=Fq, T_in=Fq, N=T * J, C1=Fq, a1_s=(0, 0, Fq),
                        w_sb=Fq * zrow, o_s=(Fq * zrow, 0, zrow), tag=p + ".ftbfc")
         M = self._buf(tag + ".M", B * T, Cc * (J + 1))
-        self._gemm_flat(M, G, W[p + ".ftbQ.wf32"], B * T, Cc, Cc * (J + 1))
+        self._gemm_flat(M, G, W[p + ".ftbQ.wf32"], B * T, Cc, Cc * (J + 1), tag=p + ".ftbQ")
         out = self._buf(tag + ".out", B, Fq, T, Cc, dtype=self._adt(Cc))
         return self._ftb_lin_out(xn, Zm, M, W[p + ".ftbs"], W[p + ".ftbV"], W[p + ".ftbd"], out, B=B, F=Fq, T=T, N=Cc,
                                  J=J, zrow=zrow)

@@ -204,6 +204,13 @@ int aero_ftb_lin_out_fwd(const float* z, const float* zm, const float* M, const 
 int aero_ftb_lin_squeeze_fwd(const float* z, const float* W1p, const float* b1p, void* R, int32_t r,
                              const aero_ftb_lin_params* p, aero_stream_t stream);
 
+/* FTB frequency mix (`freq_fc`, modules.py:296,317-320) for the deep layers where only F = 8 / 16 frequency rows are left:
+ *   out[b][g][m] = gate[b][m] * sum_f W[g][f] * x[b][f][m],  m < M = T*C contiguous positions (M a multiple of 4), W fp32 [F][F],
+ * gate fp32 [B][M] or NULL; x and out are both fp32 or both FP16 (AERO_TG_A_F16 | AERO_TG_OUT_F16).  Same result as
+ * AERO_TAPS_MIX, without tensor-core tiles (they are all overhead at this F). */
+int aero_freq_mix_small_fwd(const void* x, const float* W, const float* gate, void* out, int32_t B, int32_t F, int64_t M,
+                            int32_t flags, aero_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Recurrent half of one bidirectional LSTM layer (replaces the cuDNN RNN behind nn.LSTM,
  * reference modules.py:28,46, together with the overlapping-window framing modules.py:36-44,

@@ -236,6 +236,13 @@ class EmuEngine(AeroEngine):
         affine[:, 0] = sd.float()
         affine[:, 1] = mean.float()
 
+    # ---- aero_freq_mix_small_fwd
+    def _freq_mix_small(self, x, Wfc, gate, out, *, B, F, M):
+        self.calls.append(("freq_mix_small", F))
+        v = torch.einsum("gf,bfm->bgm", Wfc.double(), x.reshape(B, F, M).double()) * gate.reshape(B, 1, M).double()
+        out.copy_(v.reshape(out.shape).float())
+        return out
+
     # ---- aero_ftb_lin_squeeze_fwd
     def _ftb_lin_squeeze(self, z, W1p, b1p, R, *, B, F, T, J, r, zrow):
         self.calls.append(("ftb_lin_squeeze",))

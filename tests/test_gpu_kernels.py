@@ -414,6 +414,23 @@ def test_freq_mix_tcgen05_mn_major(engines, B, Fq, T, Cc, storage):
     assert rel_l2(y.float().cpu(), ref) < (4e-4 if f16 else 5e-6)
 
 
+@pytest.mark.parametrize("F,dt", [(8, torch.float16), (16, torch.float16), (8, torch.float32), (16, torch.float32)])
+def test_freq_mix_small(engines, F, dt):
+    """aero_freq_mix_small_fwd (deep FTB layers) against the einsum statement; ragged M."""
+    gpu, _ = engines
+    B, T, Cc = 3, 77, 36
+    M = T * Cc
+    x = rnd(B, F, T, Cc, seed=1)
+    x = x.half().float() if dt == torch.float16 else x
+    wfc, gate = rnd(F, F, seed=2) / math.sqrt(F), rnd(B, T, Cc, seed=3)
+    ref = torch.einsum("gf,bftc->bgtc", wfc.double(), x.double()) * gate[:, None].double()
+    y = torch.full((B, F, T, Cc), float("nan"), device="cuda", dtype=dt)
+    gpu._freq_mix_small(x.cuda().to(dt), wfc.cuda(), gate.cuda(), y, B=B, F=F, M=M)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert rel_l2(y.float().cpu(), ref) < (4e-4 if dt == torch.float16 else 2e-6)
+
+
 def test_fp16_outputs_of_the_other_kernels(engines):
     """norm_act / LSTM recurrence / attention writing FP16: the fp32 result of the same call, rounded once."""
     gpu, _ = engines
