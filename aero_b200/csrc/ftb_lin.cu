@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) freq_mix_small_kernel(const TA* __restric
 #pragma unroll
         for (int f = 0; f < F; ++f) v[f] = ld4(xb + (int64_t)f * M + m);
         const float4 gt = gate ? *reinterpret_cast<const float4*>(gate + (int64_t)b * M + m) : make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
+#pragma unroll 1                      // (unrolled, the compiler keeps all F*F weights in registers: 255 registers and spills at F = 16)
         for (int g = 0; g < F; ++g) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
