@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.period = index, [], False, 0.02
+        self.index, self.rows, self.stop_flag, self.period, self.paused = index, [], False, 0.02, False
 
     def run(self):
         try:                                   # NVML in-process: millisecond polls, no fork on the launching host
@@ -68,6 +68,9 @@ class ClockSampler(threading.Thread):
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             bits = [(0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5)]      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
             while not self.stop_flag:
+                if self.paused:
+                    time.sleep(0.01)
+                    continue
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -84,6 +87,9 @@ class ClockSampler(threading.Thread):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
+            if self.paused:
+                time.sleep(0.01)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -257,9 +263,9 @@ def main():
     prof = eng.stop_profile()
     ms_dev = ev0.elapsed_time(ev1) / args.steps
 
-    # ---- end to end through the public API with host buffers (NVML queries contend with CUDA API calls for driver locks:
-    #      poll slowly while every step synchronises)
-    sampler.period = 0.1
+    # ---- end to end through the public API with host buffers.  NVML queries contend with CUDA API calls for driver locks
+    #      (measured: +3-4 ms per synchronised step): the clocks were sampled during the device-timed region above, stop here.
+    sampler.paused = True
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
