@@ -124,7 +124,6 @@ class AeroEngine:
         self._flip = False
         self.lstm_tc = True         # tcgen05 LSTM recurrence (re-ordered gate layout) when precision >= 1
         self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
-        self.last_glu_fp32 = False  # keep the last decoder layer's GLU output (input of the final transposed conv) in fp32
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
         self._prof, self._prof_tags = None, set()
         self._wk, self._wh, self._wname = {}, {}, {}
@@ -664,8 +663,7 @@ class AeroEngine:
         tag = f"d{j}"
         Fq, Cc = g.f_out, g.ch
         c1 = 0 if x is None else Cc
-        y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc,
-                      dtype=torch.float32 if (last and self.last_glu_fp32) else self._adt(2 * Cc))
+        y = self._buf(tag + ".glu", B, Fq, T, 2 * Cc, dtype=self._adt(2 * Cc))
         common = dict(a1=x, a2=skip, B=B, F_out=Fq, T=T, N=4 * Cc, C1=c1, C2=Cc, kf=3, kt=3, pad_f=1, pad_t=1,
                       bias=W[p + ".rw.b"])
         if g.norm:

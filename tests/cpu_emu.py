@@ -30,7 +30,6 @@ class EmuEngine(AeroEngine):
         self._windows = {}
         self._stats = None
         self.precision = 0
-        self.last_glu_fp32 = False
         self.fuse_pre_ftb = True
         self.lstm_tc = False          # the emulation states the recurrence in PyTorch's gate layout
         self.snake = False

@@ -37,7 +37,7 @@ class DryEngine(AeroEngine):
         self._packed = self._packed_key = None
         self._bufs, self._windows, self._stats = {}, {}, None
         self.precision, self.fp32_tags = 2, ()
-        self.snake, self._flip, self.lstm_tc, self.fuse_pre_ftb, self.last_glu_fp32 = False, False, True, True, False
+        self.snake, self._flip, self.lstm_tc, self.fuse_pre_ftb = False, False, True, True
         self._prof, self._prof_tags = None, set()
         self._wk, self._wh, self._wname = {}, {}, {}
         self.use_graph, self._graphs, self._seen = False, {}, {}
