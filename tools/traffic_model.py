@@ -85,6 +85,10 @@ class DryEngine(AeroEngine):
     def _sample_norm(self, x, stats, y, affine, B, per_sample, extent=None, rnd=False):
         self.log.append(("sample_norm", 0.0, 4.0 * B * (extent or per_sample), 4.0 * B * (extent or per_sample), 0))
 
+    def _freq_mix_small(self, x, Wfc, gate, out, *, B, F, M):
+        self.log.append((f"freq_mix_small F={F}", 2.0 * B * F * F * M, nbytes(x) + nbytes(gate), nbytes(out), 0))
+        return out
+
     def _ftb_lin_squeeze(self, z, W1p, b1p, R, **kw):
         self.log.append(("ftb_lin_squeeze", 0.0, nbytes(z), nbytes(R), 0))
         return R
