@@ -1,14 +1,13 @@
-// Tap-GEMM on the 5th-generation tensor cores (sm_100a): TMA -> shared memory -> tcgen05.mma
-// (kind::tf32, fp32 accumulate in TMEM) -> tcgen05.ld epilogue.  Implicit GEMM, im2col-free:
-// every tap of a convolution is a shifted TMA box of the channels-last activation tensor; image
-// borders, channel tails and the K tail are TMA out-of-bounds zero fill.
+// Tap-GEMM on the 5th-generation tensor cores (sm_100a): TMA -> shared memory -> tcgen05.mma (kind::f16 / kind::tf32, fp32
+// accumulate in TMEM) -> tcgen05.ld epilogue.  Implicit GEMM, im2col-free: every tap of a convolution is a shifted TMA box
+// of the channels-last activation tensor; image borders, channel tails and the K tail are TMA out-of-bounds zero fill.
 //
-//   A tile : 128 pixels (consecutive t of one (b, f) row) x 32 channels  = 128 rows x 128 B, SWIZZLE_128B
-//   B tile : BN output columns x 32 channels (weights stored K-major [slab][N][K]) = BN rows x 128 B
-//   D      : 128 lanes x BN fp32 columns of TMEM
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).  STAGES-deep mbarrier ring between
-// producer and MMA; tcgen05.commit frees a stage / publishes the accumulator.
+//   A tile : 128 pixels (consecutive t of one (b, f) row) x 128 bytes of channels = 128 rows, SWIZZLE_128B
+//   B tile : BN output columns x 128 bytes of channels (weights stored K-major [slab][N][K]) = BN rows
+//   D      : 128 lanes x BN fp32 columns of TMEM, two buffers (the epilogue of tile i overlaps the main loop of tile i+1)
+// Persistent CTAs (one or two per SM) of 320 threads: warp 0 = TMA producer (runs ahead across tiles), warp 1 = TMEM allocator +
+// MMA issue by one elected lane, warps 2..9 = epilogue.  STAGES-deep mbarrier ring between producer and MMA; tcgen05.commit
+// frees a stage / publishes an accumulator buffer.
 //
 // Operand kinds: kind::tf32 (fp32 storage, 32 channels per 128-byte row, UMMA_K = 8) or kind::f16 (FP16 storage, 64 channels
 // per row, UMMA_K = 16): the shared-memory image is identical in bytes (128 rows x 128 B per k-block, four UMMAs of 32 B along
