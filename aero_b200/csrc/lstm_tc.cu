@@ -13,11 +13,11 @@
 //   operands are FP16 (kind::f16, K = 16 per UMMA): h is in (-1, 1) and W_hh is O(1), so FP16's 10-bit mantissa gives
 //       the same rounding as TF32 at half the shared-memory traffic and half the instruction count; accumulation is fp32;
 //   D = (4/GPT) x 16 fp32 columns of TMEM, read back with tcgen05.ld by the same threads.
-// The input-projection gate pre-activations (computed by the tap-GEMM in the same re-ordered column
-// order, so a warp reads 128 contiguous bytes per sequence) are prefetched while the MMA runs.
-// One elected thread issues the MMAs; two mbarriers ping-pong between "h ready" and "accumulators
-// ready".  c stays in registers for the whole sequence.  8 cell-update warps: two per TMEM lane
-// quarter, each owning 8 of the 16 sequences.
+// The input-projection gate pre-activations keep PyTorch's [dir][i,f,g,o][H] column order (a warp reads the contiguous
+// cells of one gate per sequence); with one CTA per SM (GPT = 1) they are requested a whole step ahead.
+// One elected lane issues the MMAs back to back from step-invariant descriptors; two mbarriers ping-pong between
+// "h ready" and "accumulators ready".  c stays in registers for the whole sequence.  8 (GPT = 2) or 16 (GPT = 1)
+// cell-update warps; in the two-gates-per-tile layout a lane finishes only its own half of the warp's sequences.
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
 
