@@ -66,6 +66,21 @@ def test_storage_type_plumbing_of_the_tensor_core_engines(precision):
     assert err < (1e-3 if precision == 2 else 2e-5)
 
 
+@pytest.mark.parametrize("exp,C,L", [("aero_12-48_512_128", 1, 3000), ("aero_8-24_512_64", 1, 2100), ("aero_11-44_512_64", 2, 2300),
+                                     ("aero_4-16_512_128", 1, 2050)])
+def test_default_engine_plumbing_on_every_shipped_geometry(exp, C, L):
+    """precision 2 on the CPU emulation for the other experiment files (odd hops, stereo, ragged lengths): buffer dtypes, row
+    padding, frequency-mix variants and the fused layer 0 must line up for every geometry the YAMLs describe."""
+    m = make(exp)
+    m._engine_obj.precision = 2
+    mix = white_noise((1, C, L))
+    with torch.no_grad():
+        ref = O.aero_forward(m.state_dict(), m.geom, mix)
+    out = m(mix)
+    assert out.shape == ref.shape
+    assert rel_l2(out, ref) < 1e-3
+
+
 def test_spec_roundtrip_api_shapes():
     m = make("aero_4-16_512_64")
     x = white_noise((2, 1, 4000))
