@@ -809,7 +809,20 @@ static KernelFn pick_kernel(int amode, bool res, bool stats) {
 #undef AERO_TC_K
 }
 
+// tuning knobs (tools/kprof.py), read from the environment ONCE when the library first launches this kernel: the launch
+// path itself never calls getenv.  -1 = not set.
+struct TcKnobs {
+    int direct_f32 = -1, direct_f16 = -1, grouped_bn = -1, stages = -1, per_sm = -1;
+    TcKnobs() {
+        auto rd = [](const char* name, int& v) { if (const char* e = getenv(name)) v = atoi(e); };
+        rd("AERO_TC_DIRECT_F32", direct_f32); rd("AERO_TC_DIRECT_F16", direct_f16); rd("AERO_TC_GROUPED_BN", grouped_bn);
+        rd("AERO_TC_STAGES", stages); rd("AERO_TC_PER_SM", per_sm);
+    }
+};
+static const TcKnobs& knobs() { static const TcKnobs k; return k; }
+
 int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
+    const TcKnobs& kn = knobs();
     TapGemmArgs g = g0;
     const aero_tapgemm_params& p = g.p;
     const bool f16a = p.precision == 2, f16o = (p.flags & AERO_TG_OUT_F16) != 0;
@@ -843,9 +856,9 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     g.grouped_bn = 128;
     g.direct_f32 = 0;
     g.direct_f16 = 2;       // measured: the direct form wins for GLU outputs (one 16-byte store per lane), the transpose otherwise
-    if (const char* e = getenv("AERO_TC_DIRECT_F32")) g.direct_f32 = atoi(e);
-    if (const char* e = getenv("AERO_TC_DIRECT_F16")) g.direct_f16 = atoi(e);
-    if (const char* e = getenv("AERO_TC_GROUPED_BN")) g.grouped_bn = atoi(e);
+    if (kn.direct_f32 >= 0) g.direct_f32 = kn.direct_f32;
+    if (kn.direct_f16 >= 0) g.direct_f16 = kn.direct_f16;
+    if (kn.grouped_bn >= 0) g.grouped_bn = kn.grouped_bn;
     const int64_t tiles = (int64_t)p.B * p.F_out * g.tiles_t;
     if (tiles > 2147483647LL) { set_error("aero_tapgemm_fwd: too many tiles"); return AERO_ERR_INVALID; }
     {
@@ -879,7 +892,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     } else {
         kStages = (96 * 1024) / stage_bytes;
     }
-    if (const char* e = getenv("AERO_TC_STAGES")) kStages = atoi(e);      // tuning knobs (tools/kprof.py); not used by the product
+    if (kn.stages >= 0) kStages = kn.stages;
     if (kStages > kMaxStages) kStages = kMaxStages;
     if (kStages < 2) kStages = 2;
     while (kStages > 2 && (size_t)kStages * stage_bytes + fixed > 227 * 1024) --kStages;
@@ -908,7 +921,7 @@ int tapgemm_tc_launch(const TapGemmArgs& g0, cudaStream_t st) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > (int)(512 / tmem_cols)) per_sm = (int)(512 / tmem_cols);
     if (per_sm > 2) per_sm = 2;                      // 320 threads x ~96 registers: two CTAs per SM
-    if (const char* e = getenv("AERO_TC_PER_SM")) per_sm = atoi(e) < per_sm ? atoi(e) : per_sm;
+    if (kn.per_sm >= 0 && kn.per_sm < per_sm) per_sm = kn.per_sm;
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)num_sms * per_sm;
     g.last_tile = (int)tiles_total - 1;

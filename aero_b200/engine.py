@@ -106,12 +106,22 @@ class _Stats:
 
 class AeroEngine:
     def __init__(self, model):
+        self._init_state(model, cabi.load())
+
+    def _init_state(self, model, lib):
+        """All engine state (also used by the test / tooling subclasses that replace the kernel wrappers)."""
         self.model = model
         self.geom = model.geom
-        self.lib = cabi.load()
+        self.lib = lib
         self._packed = None
         self._packed_key = None
+        # workspaces live in "shape sets" (one per (input shape, precision)); only the most recently used few are kept,
+        # so a loop over variable-length files (reference test.py / evaluate.py) cannot grow device memory without bound.
+        # A CUDA graph holds raw pointers into its shape set: evicting a set drops its graph too.
+        self._bufsets = {}
         self._bufs = {}
+        self.max_shape_sets = 4
+        self._plist = None
         self._windows = {}
         self._stats = None
         # 2 (default): FP16-stored activations / tcgen05 kind::f16 operands, fp32 accumulate, fp32 GroupNorm inputs and
@@ -136,15 +146,43 @@ class AeroEngine:
     # ------------------------------------------------------------------ plumbing
     def invalidate(self):
         self._packed = None
+        self._bufsets = {}
         self._bufs = {}
         self._graphs = {}
         self._seen = {}
+        self._plist = None
+
+    def _select_shape_set(self, key):
+        """Make `key`'s workspace set current (LRU order = dict insertion order)."""
+        cur = self._bufsets.pop(key, None)
+        if cur is None:
+            cur = {}
+            while len(self._bufsets) >= self.max_shape_sets:
+                old = next(iter(self._bufsets))
+                del self._bufsets[old]
+                for gk in [gk for gk in self._graphs if gk[0] == old[0] and gk[2] == old[1]]:
+                    del self._graphs[gk]
+        self._bufsets[key] = cur
+        self._bufs = cur
+
+    def _weights_version(self):
+        """Cheap change detector for the model's tensors: in-place updates (optimizer steps, load_state_dict) bump
+        `_version`, which only ever grows, so the sum changes whenever any tensor does.  The tensor list is cached;
+        `Aero._apply` / `load_state_dict` (device moves, re-materialised parameters) call invalidate()."""
+        if self._plist is None:
+            self._plist = list(self.model.parameters()) + list(self.model.buffers())
+        return sum(t._version for t in self._plist)
 
     def _device(self):
         return next(self.model.parameters()).device
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+
+    def _on_device(self):
+        """Context that makes the model's device current: every launch, event and allocation below it targets the
+        device the weights live on, whatever the caller's current device is (the reference nn.Module works that way)."""
+        return torch.cuda.device(self._device())
 
     def _require(self, x):
         dev = self._device()
@@ -185,7 +223,7 @@ class AeroEngine:
         return w
 
     def _weights(self):
-        key = tuple(p._version for p in self.model.parameters()) + tuple(b._version for b in self.model.buffers())
+        key = self._weights_version()
         if self._packed is None or key != self._packed_key:
             self._packed = self._pack()
             self._packed_key = key
@@ -253,7 +291,7 @@ class AeroEngine:
             if g.index == 0 and kw["freq_emb"]:
                 W["emb"] = (sd["freq_emb.embedding.weight"] * (kw["emb_scale"] * kw["freq_emb"])).contiguous()
             if g.dconv:
-                for d in range(kw["dconv_depth"]):
+                for d in range(abs(kw["dconv_depth"])):
                     q = f"{p}.dconv.layers.{d}"
                     o = f"{p}.dc{d}"
                     W[o + ".c1.w"], W[o + ".c1.b"] = pack_taps(sd[q + ".conv1.0.weight"]), sd[q + ".conv1.0.bias"].contiguous()
@@ -462,6 +500,10 @@ class AeroEngine:
     def spec(self, x, scale=False):
         """reference aero.py:409-421 -> complex [..., nfft/2, frames]."""
         self._require(x)
+        with self._on_device():
+            return self._spec(x, scale)
+
+    def _spec(self, x, scale):
         g = self.geom
         *lead, length = x.shape
         hop = g.hop_in
@@ -483,6 +525,11 @@ class AeroEngine:
         *lead, bins, frames = zc.shape
         z = torch.view_as_real(zc.reshape(-1, bins, frames).contiguous())
         self._require(z)
+        with self._on_device():
+            return self._ispec(z, lead, bins, frames)
+
+    def _ispec(self, z, lead, bins, frames):
+        g = self.geom
         y = torch.empty(z.shape[0], g.hop_out * (frames - 1), dtype=torch.float32, device=z.device)
         self.istft_into(z, y, n_fft=g.nfft, hop=g.hop_out, win=g.win_out, channels=1, frames=frames, bins_in=bins,
                         strides=(bins * frames * 2, 0, frames * 2, 2))
@@ -586,9 +633,9 @@ class AeroEngine:
         Fq, Cc = g.f_out, g.ch
         hid = int(Cc / kw["dconv_comp"])
         rows = B * Fq
-        for d in range(kw["dconv_depth"]):
+        for d in range(abs(kw["dconv_depth"])):
             o = f"encoder.{g.index}.dc{d}"
-            dil = 2 ** d
+            dil = 2 ** d if kw["dconv_depth"] > 0 else 1      # negative depth = no dilation (reference modules.py:176-177,201)
             st1 = self._stats.take(rows)
             h = self._buf(f"{tag}.h", B, Fq, T, hid, dtype=self._adt(hid))
             h_raw = self._raw(h, f"{tag}.h32")
@@ -702,45 +749,53 @@ class AeroEngine:
         """Public entry (behind Aero.forward).  With ``use_graph`` the ~110 launches of one forward are captured once per
         input shape into a CUDA graph and replayed: identical kernels and results, no per-launch host cost (this is what
         matters at batch 1, where the eager path is host-bound)."""
-        if not self.use_graph or return_spec or self._prof is not None or mix.shape[0] == 0:
-            return self._forward(mix, return_spec, return_lr_spec)
         self._require(mix)
-        key = (tuple(mix.shape), tuple(p._version for p in self.model.parameters()), self.precision, self.fp32_tags)
-        entry = self._graphs.get(key)
-        if entry is None and self.use_graph == "auto":
-            n = self._seen.get(key, 0)
-            if n < 2:
-                if len(self._seen) >= 64:
-                    self._seen.clear()
-                self._seen[key] = n + 1
+        self._check_mode()
+        with self._on_device():
+            if not self.use_graph or return_spec or self._prof is not None or mix.shape[0] == 0 or \
+                    torch.cuda.is_current_stream_capturing():
                 return self._forward(mix, return_spec, return_lr_spec)
-        if entry is None:
-            static_in = mix.contiguous().clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):                       # allocate workspaces / pack weights / encode tensor maps outside capture
-                    self._forward(static_in, False, False)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                static_out = self._forward(static_in, False, False)
-            if len(self._graphs) >= 8:
-                self._graphs.clear()
-            entry = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
-        static_in.copy_(mix)
-        graph.replay()
-        return static_out.clone()
+            key = (tuple(mix.shape), self._weights_version(), self.precision, self.fp32_tags, self.lstm_tc, self.fuse_pre_ftb,
+                   self.snake)
+            entry = self._graphs.get(key)
+            if entry is None and self.use_graph == "auto":
+                n = self._seen.get(key, 0)
+                if n < 2:
+                    if len(self._seen) >= 64:
+                        self._seen.clear()
+                    self._seen[key] = n + 1
+                    return self._forward(mix, return_spec, return_lr_spec)
+            if entry is None:
+                static_in = mix.contiguous().clone()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):                   # allocate workspaces / pack weights / encode tensor maps outside capture
+                        self._forward(static_in, False, False)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    static_out = self._forward(static_in, False, False)
+                for gk in [gk for gk in self._graphs if gk[1] != key[1]]:     # graphs of superseded weights
+                    del self._graphs[gk]
+                entry = self._graphs[key] = (graph, static_in, static_out)
+            else:
+                self._select_shape_set((key[0], self.precision))   # keep the replayed shape's workspaces most recently used
+            graph, static_in, static_out = entry
+            static_in.copy_(mix)
+            graph.replay()
+            return static_out.clone()
 
-    @torch.no_grad()
-    def _forward(self, mix, return_spec=False, return_lr_spec=False):
-        model = self.model
-        self._require(mix)
-        if model.training:
+    def _check_mode(self):
+        if self.model.training:
             raise NotImplementedError(
                 "aero_b200: the CUDA path implements the inference forward (eval-mode BatchNorm, no autograd); "
                 "call model.eval().  Training kernels are SURVEY.md section 8f 'next'.")
+
+    @torch.no_grad()
+    def _forward(self, mix, return_spec=False, return_lr_spec=False):
+        self._require(mix)
+        self._check_mode()
         g = self.geom
         kw = g.kw
         if mix.dim() != 3 or mix.shape[1] != kw["in_channels"]:
@@ -758,11 +813,14 @@ class AeroEngine:
                 return y0, zc0
             return y0, zc0, torch.zeros(0, kw["in_channels"], Fq0, Tn, dtype=torch.complex64, device=mix.device)
         W = self._weights()
+        self._select_shape_set((tuple(mix.shape), self.precision))
         B_ = mix.shape[0]
         need = B_ + sum((2 * B_ * kw["norm_groups"] if lg.norm else 0) * 2 +
-                        (2 * kw["dconv_depth"] * B_ * lg.f_out if lg.dconv else 0) for lg in g.layers) + 64
+                        (2 * abs(kw["dconv_depth"]) * B_ * lg.f_out if lg.dconv else 0) for lg in g.layers) + 64
         if self._stats is None or self._stats.buf.device != mix.device or self._stats.buf.shape[0] < need:
             self._stats = _Stats(mix.device, capacity=max(1 << 16, need))
+            self._graphs.clear()             # captured graphs point into the statistics buffer that was just replaced
+            self._seen.clear()
         self._stats.reset()
 
         B, Cin, length = mix.shape

@@ -28,6 +28,8 @@ def enhance_long(model, lr_sig, sr, segment_sec=SEGMENT_DURATION_SEC, max_batch=
         raise ValueError(f"expected [channels, samples], got {tuple(lr_sig.shape)}")
     seg = int(sr * segment_sec)
     total = lr_sig.shape[-1]
+    if total == 0 or seg <= 0:
+        raise ValueError(f"enhance_long: empty signal or segment (samples {total}, segment {seg})")
     n_chunks = max(1, math.ceil(total / seg))
     n_full = total // seg if total % seg else n_chunks
     outs = []

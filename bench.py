@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- audio-seconds/sec of the AERO generator forward (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 4-16|12-48|11-44|train]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one forward of aero_4-16_512_64 over a batch of 32 synthetic 2-s white-noise clips per
-GPU (BASELINE.json configs[1]); clips are independent, so ranks shard the batch with no data-path
-collective ("weak" scaling: 32 clips per GPU).  Rank 0 prints ONE JSON line.
+A "step" is one forward over one batch of synthetic white-noise clips per GPU; clips are independent, so ranks shard
+the batch with no data-path collective ("weak" scaling: the per-GPU batch is fixed).  Rank 0 prints ONE JSON line.
 
-  value    : device-timed (CUDA events, max over ranks), inputs resident in HBM.
-  e2e      : same metric through the public API (`Aero.forward`) with pinned-host input, H2D and D2H of
-             the waveform inside the timed region.
-  roofline : dominant kernel family = the decoder's 3x3 rewrite tap-GEMMs (69 % of the model's FLOPs),
-             timed live with CUDA events on the launch stream during the timed steps.
-  cpu_baseline / --impl reference : the oracle port (oracle/aero_oracle.py, the same torch library calls
-             the reference makes) on the host cores.  The reference is a Python package and cannot travel to
-             the GPU box; oracle/ is its pinned restatement.
+  --config 4-16  (default) BASELINE.json configs[1]: aero_4-16_512_64, 32 x 2 s clips per GPU
+  --config 12-48           configs[2]: aero_12-48_512_128, 16 x 2 s clips per GPU (T = 751)
+  --config 11-44           configs[4]: aero_11-44_512_64 stereo, 2 x 10 s clips per GPU (8 clips on 4 GPUs; T = 6892)
+  --config train           configs[3]: one training step (generator fwd + MR-STFT loss + bwd + Adam), 8 clips per GPU
+
+  value    : device-timed (CUDA events, max over ranks), inputs resident in HBM, on the path a caller gets: the
+             CUDA-graph replay `Aero.forward` uses for a steady-state shape.
+  e2e      : same metric through the public API with pinned-host input, H2D and D2H of the waveform inside the timed
+             region; median of the per-step times (mean also given).
+  roofline : dominant kernel family = the decoder's 3x3 rewrite tap-GEMMs, timed with CUDA events on the launch stream
+             in a separate eager pass of the same K steps; fraction of the measured burst AND sustained cuBLAS bf16 rates.
+  step     : whole-step achieved TFLOP/s against the same peaks, and the step time against the sum of its launches' own
+             rooflines (tools/traffic_model.py: algorithmic bytes / FLOPs per launch).
+  cpu_baseline / --impl reference : the oracle port (oracle/aero_oracle.py, the same torch library calls the reference
+             makes) on the host cores, BASELINE.md section 3 protocol.  The reference is a Python package and cannot travel
+             to the GPU box; oracle/ is its pinned restatement.
 """
 import argparse
 import json
@@ -28,17 +35,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import torch  # noqa: E402
 
-EXPERIMENT = "aero_4-16_512_64"
-BATCH_PER_GPU = 32
-CLIP_SECONDS = 2.0
 SEED = 2036
-GFLOP_PER_CLIP = 124.16          # reference-equivalent; 102.9 with decoder-0's structural zeros skipped
-GFLOP_PER_CLIP_REQUIRED = 102.9
-# dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the family (decoder.0 rewrite, B=32) from the
-# `ncu --set full` capture summarised in profiles/ (algorithmic bytes of that launch: 514 MB); None until captured
+# workload table: experiment file, clips per GPU, low-rate samples per clip, clip seconds, reference-equivalent GFLOP per clip
+#  and the GFLOP actually required (decoder-0's structural zeros skipped)
+CONFIGS = {
+    "4-16": dict(exp="aero_4-16_512_64", batch=32, length=8000, seconds=2.0, gflop=124.16, gflop_req=102.9,
+                 name="aero_4-16_512_64 inference forward, 2 s white-noise clips 4->16 kHz (BASELINE configs[1])"),
+    "12-48": dict(exp="aero_12-48_512_128", batch=16, length=24000, seconds=2.0, gflop=185.6, gflop_req=None,
+                  name="aero_12-48_512_128 inference forward, 2 s white-noise clips 12->48 kHz (BASELINE configs[2])"),
+    "11-44": dict(exp="aero_11-44_512_64", batch=2, length=110250, seconds=10.0, gflop=1989.0, gflop_req=None,
+                  name="aero_11-44_512_64 inference forward, 10 s stereo white-noise clips 11.025->44.1 kHz (BASELINE configs[4]: "
+                       "8 clips on 4 GPUs = 2 per GPU)"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of the roofline family (decoder.0 rewrite, B=32) from the
+# `ncu --set full` capture summarised in profiles/
 TRAFFIC_NCU = {1: {"kernel": "tapgemm_tc_kernel<0,0,1,tf32> decoder.0.rw B=32", "bytes_per_launch": 473.8e6, "algorithmic_bytes": 513.7e6,
                    "tensor_pipe_pct": 80.8, "source": "profiles/r1_dec0rw_tc_ncu.md"},
                2: {"kernel": "tapgemm_tc_kernel<0,0,1,f16,f32> decoder.0.rw B=32", "bytes_per_launch": 401.7e6, "algorithmic_bytes": 453.9e6,
@@ -49,8 +63,9 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops_sustained"], "source": "measured (MEASURED_PEAKS.json, sustained)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops_sustained"], "bf16_tflops_burst": d["bf16_tflops"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
@@ -109,21 +124,52 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def build_model():
+def pin_to_gpu_numa(index):
+    """Run this process on the cores of the GPU's NUMA node (pinned buffers and the launch thread then sit next to the
+    PCIe root the GPU hangs off).  Returns the core count, or None if NVML cannot tell."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
+def build_model(cfg):
     from util import trained_like_
     from aero_b200 import Aero, aero_kwargs
     torch.manual_seed(SEED)
-    m = Aero(**aero_kwargs(EXPERIMENT)).eval()
+    m = Aero(**aero_kwargs(cfg["exp"])).eval()
     m.load_state_dict(trained_like_(m.state_dict()))
     return m
 
 
-def cpu_forward_timer(model, batch, threads, repeats=1, warmup=1):
-    """Times the oracle port (library-call form == what the reference executes) on the host."""
+def cpu_forward_times(cfg, batch, threads, repeats, warmup):
+    """Per-forward wall times of the oracle port (library-call form == what the reference executes) on the host."""
     from oracle import aero_oracle as O
     torch.set_num_threads(threads)
+    model = build_model(cfg)
     sd = {k: v.cpu() for k, v in model.state_dict().items()}
-    x = torch.randn(batch, 1, int(4000 * CLIP_SECONDS), generator=torch.Generator().manual_seed(SEED))
+    x = torch.randn(batch, model.in_channels, cfg["length"], generator=torch.Generator().manual_seed(SEED))
     times = []
     with torch.no_grad():
         for i in range(warmup + repeats):
@@ -131,65 +177,81 @@ def cpu_forward_timer(model, batch, threads, repeats=1, warmup=1):
             O.aero_forward(sd, model.geom, x)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return sorted(times)[len(times) // 2]
+    return times
 
 
-def _probe(threads, batch, repeats, timeout):
-    """Run the oracle port in a child process (a hung / oversubscribed BLAS cannot stall the bench)."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--_cpu_probe", f"{threads},{batch},{repeats}"]
+def _probe(cfg_key, threads, batch, repeats, warmup, timeout):
+    """Run the oracle port in a child process on ALL host cores' affinity (a hung / oversubscribed BLAS cannot stall the
+    bench).  Returns the list of per-forward times or None."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--config", cfg_key, "--_cpu_probe", f"{threads},{batch},{repeats},{warmup}"]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout).stdout.strip().splitlines()
-        return float(out[-1]) if out else None
+        return json.loads(out[-1]) if out else None
     except Exception:
         return None
 
 
-def pick_cpu_threads():
-    """Thread count that gives the reference's CPU path its best throughput on this host."""
+def median(v):
+    v = sorted(v)
+    return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
+
+
+def pick_cpu_threads(cfg_key):
+    """all physical cores.  A quick B=2 probe guards against a host where that many MKL/OpenMP threads
+    stall (seen on this pool with 128): fall back to half until a probe returns."""
     env = os.environ.get("AERO_CPU_THREADS")
     if env:
         return int(env)
-    n = os.cpu_count() or 1
-    cands = sorted({min(n, 64), min(n, 32), min(n, 16)}, reverse=True)
-    best, best_t = None, None
-    for c in cands:
-        t = _probe(c, 2, 1, 45)
-        if t is not None and (best_t is None or t < best_t):
-            best, best_t = c, t
-    return best or min(n, 16)
+    n = physical_cores()
+    while n > 1:
+        if _probe(cfg_key, n, 2, 1, 0, 90) is not None:
+            return n
+        n //= 2
+    return 1
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), host cores only."""
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), host cores only, the SAME batch
+    as the GPU arm's per-GPU workload."""
     if rank != 0:
         return
-    model = build_model()
-    threads = pick_cpu_threads()
-    torch.set_num_threads(threads)
-    # bounded sample: pick a batch so that (steps+warmup) forwards finish within ~3 minutes
-    probe = _probe(threads, 2, 1, 120) or 60.0
-    per_clip = probe / 2
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    batch = max(1, min(BATCH_PER_GPU, int(budget / max(per_clip, 1e-6))))
-    from oracle import aero_oracle as O
-    sd = model.state_dict()
-    x = torch.randn(batch, 1, int(4000 * CLIP_SECONDS), generator=torch.Generator().manual_seed(SEED))
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            O.aero_forward(sd, model.geom, x)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.aero_forward(sd, model.geom, x)
-        dt = (time.perf_counter() - t0) / args.steps
-    val = batch * CLIP_SECONDS / dt
+    os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    threads = pick_cpu_threads(args.config)
+    batch = cfg["batch"]
+    est = _probe(args.config, threads, 2, 1, 1, 240)
+    per_clip = (est[0] / 2) if est else 1.0
+    # keep the workload's own batch; only if (steps + warmup) forwards of it would run past ~10 minutes, shrink the sample
+    if per_clip * batch * (args.steps + args.warmup) > 600.0:
+        batch = max(1, int(600.0 / (per_clip * (args.steps + args.warmup))))
+    times = cpu_forward_times(cfg, batch, threads, args.steps, args.warmup)
+    dt = sum(times) / len(times)
+    val = batch * cfg["seconds"] / dt
+    one = _probe(args.config, 1, 1, 3, 1, 300)
     line = {"impl": "reference", "metric": "audio-seconds/sec forward", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_step_median": median(times) * 1e3,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{EXPERIMENT} forward, 2 s clips 4->16 kHz", "batch_per_step": batch},
+            "config": {"workload": cfg["name"], "batch_per_step": batch, "same_batch_as_gpu_arm": batch == cfg["batch"]},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} forwards of a {batch}-clip batch (of the {BATCH_PER_GPU}-clip workload) after {args.warmup} warm-ups, oracle library-call form"},
+                             "host_cores": {"logical": os.cpu_count(), "physical": physical_cores()},
+                             "single_thread_b1": ({"value": cfg["seconds"] / median(one), "unit": "audio-s/s", "cores": 1,
+                                                   "sample": "B=1, 1 warm-up, median of 3 (torch.set_num_threads(1), as reference enhance.py:12)"}
+                                                  if one else None),
+                             "sample": f"{args.steps} forwards of a {batch}-clip batch after {args.warmup} warm-ups on {threads} threads "
+                                       f"(all physical cores unless a probe stalled), oracle library-call form"},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def timed_steps(fn, steps, barrier):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1) / steps
 
 
 def main():
@@ -198,42 +260,50 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: BASELINE config)")
+    ap.add_argument("--config", default="4-16", choices=sorted(CONFIGS) + ["train"])
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default: the BASELINE config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the precision sub-lines and the strong-scaling sample")
     ap.add_argument("--precision", type=int, default=None,
                     help="engine precision: 2 (default) FP16-stored activations / kind::f16 tcgen05, 1 fp32 storage / kind::tf32, "
                          "0 every kernel in exact fp32")
     ap.add_argument("--_cpu_probe", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.config == "train":
+        import bench_train
+        return bench_train.main(args)
+    cfg = dict(CONFIGS[args.config])
     if args._cpu_probe:
-        th, b, rep = (int(v) for v in args._cpu_probe.split(","))
-        print(cpu_forward_timer(build_model(), b, th, repeats=rep, warmup=1), flush=True)
+        th, b, rep, wu = (int(v) for v in args._cpu_probe.split(","))
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        print(json.dumps(cpu_forward_times(cfg, b, th, rep, wu)), flush=True)
         return
+    if args.batch:
+        cfg["batch"] = args.batch
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank, world)
         return
 
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = pin_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from aero_b200 import cabi
     lib = cabi.load()
-    model = build_model().to(dev)
+    model = build_model(cfg).to(dev)
     eng = model._engine()
     if args.precision is not None:
         eng.precision = args.precision
-    B = args.batch
-    L = int(4000 * CLIP_SECONDS)
+    B, L, Cin = cfg["batch"], cfg["length"], model.in_channels
     gen = torch.Generator().manual_seed(SEED + rank)
-    host_in = torch.randn(B, 1, L, generator=gen).pin_memory()
-    host_out = torch.empty(B, 1, 4 * L).pin_memory()
+    host_in = torch.randn(B, Cin, L, generator=gen).pin_memory()
     x_dev = host_in.to(dev)
 
     def barrier():
@@ -241,55 +311,82 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also builds packed weights and workspaces)
+    # ---- warm-up: packs weights, allocates workspaces, and captures this shape's CUDA graph (the path a steady-state
+    #      caller is on from its third call; forced here so that any --warmup reaches it)
+    eng.use_graph = True
+    out = None
     for _ in range(args.warmup):
-        model(x_dev)
+        out = model(x_dev)
+    eng.use_graph = "auto"
+    host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     barrier()
+    assert len(eng._graphs) >= 1
 
-    # ---- device-resident timing; the roofline kernel family is timed with events inside the same region
+    # ---- device-resident timing on the graph path
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    eng.start_profile(("decoder.0.rw", "decoder.1.rw", "decoder.2.rw", "decoder.3.rw"))   # tags = packed-weight names
+    ms_dev = timed_steps(lambda: model(x_dev), args.steps, barrier)
+
+    # ---- the same K steps launched eagerly with CUDA events around the roofline kernel family
+    fam = ("decoder.0.rw", "decoder.1.rw", "decoder.2.rw", "decoder.3.rw")      # tags = packed-weight names
+    eng.start_profile(fam)
     launches0 = lib.aero_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        model(x_dev)
-    ev1.record()
-    barrier()
-    launches = lib.aero_launch_count() - launches0
+    ms_eager = timed_steps(lambda: model(x_dev), args.steps, barrier)
+    launches_per_step = (lib.aero_launch_count() - launches0) // args.steps
     prof = eng.stop_profile()
-    ms_dev = ev0.elapsed_time(ev1) / args.steps
 
     # ---- end to end through the public API with host buffers.  NVML queries contend with CUDA API calls for driver locks
-    #      (measured: +3-4 ms per synchronised step): the clocks were sampled during the device-timed region above, stop here.
+    #      (measured: +3-4 ms per synchronised step): the clocks were sampled during the device-timed regions above, stop here.
     sampler.paused = True
-    prev_graph, eng.use_graph = eng.use_graph, True      # make sure this shape's CUDA graph exists before the timed loop (any --warmup)
-    model(x_dev)
-    eng.use_graph = prev_graph
     barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    for _ in range(args.steps):
+    stream = torch.cuda.current_stream()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record()
+    for i in range(args.steps):
         xin = host_in.to(dev, non_blocking=True)
         out = model(xin)
         host_out.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the result every step
-    ev3.record()
+        marks[i + 1].record()
+        stream.synchronize()                      # the caller reads the result every step
     barrier()
-    ms_e2e = ev2.elapsed_time(ev3) / args.steps
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+    ms_e2e_mean, ms_e2e_med = sum(per_step) / len(per_step), median(per_step)
     sampler.stop_flag = True
 
+    extras = {}
+    if not args.no_extras:
+        # other engine precisions on the same workload (eager launches, 3 steps each after one warm-up)
+        keep = eng.precision
+        for prec in (1, 0):
+            if prec == keep:
+                continue
+            eng.precision = prec
+            eng.use_graph = False
+            model(x_dev)
+            extras[f"precision_{prec}"] = {"ms_per_step": timed_steps(lambda: model(x_dev), 3, barrier),
+                                           "what": {1: "fp32 storage rounded to TF32 / tcgen05 kind::tf32", 0: "every kernel in exact fp32 (SIMT)"}[prec]}
+        eng.precision, eng.use_graph = keep, "auto"
+        if world > 1 and B % world == 0:
+            # strong scaling sample: the ONE-GPU workload (B clips in total) split over the ranks
+            xs = x_dev[: B // world].contiguous()
+            eng.use_graph = True
+            for _ in range(3):
+                model(xs)
+            eng.use_graph = "auto"
+            extras["strong"] = {"ms_per_step": timed_steps(lambda: model(xs), args.steps, barrier), "global_batch": B}
+
     from aero_b200.parallel import reduce_max
-    ms_dev, ms_e2e = reduce_max(ms_dev, dev), reduce_max(ms_e2e, dev)
+    ms_dev, ms_eager, ms_e2e_mean, ms_e2e_med = (reduce_max(v, dev) for v in (ms_dev, ms_eager, ms_e2e_mean, ms_e2e_med))
+    for v in extras.values():
+        v["ms_per_step"] = reduce_max(v["ms_per_step"], dev)
 
     if rank == 0:
         pk = peaks()
         total_clips = B * world
-        value = total_clips * CLIP_SECONDS / (ms_dev * 1e-3)
-        e2e = total_clips * CLIP_SECONDS / (ms_e2e * 1e-3)
+        secs = cfg["seconds"]
+        value = total_clips * secs / (ms_dev * 1e-3)
+        e2e = total_clips * secs / (ms_e2e_med * 1e-3)
         # roofline of the dominant kernel family
         flops = sum(v["flops"] for v in prof.values())
         ms_k = sum(v["ms"] for v in prof.values())
@@ -297,42 +394,80 @@ def main():
         prec = eng.precision
         tf32 = prec == 1
         # kind::f16 runs at the bf16 rate the driver measured with cuBLAS; kind::tf32 at half of it (no TF32 figure is measured)
-        peak = pk["bf16_tflops"] / (2 if tf32 else 1)
+        div = 2 if tf32 else 1
+        peak_s, peak_b = pk["bf16_tflops"] / div, pk["bf16_tflops_burst"] / div
         clk = sampler.summary()
         pipe = (4096 if tf32 else 8192) * 148 * (clk.get("sm_mhz") or 1965) * 1e6 / 1e12     # tcgen05 flop/clk/SM (ncu pipe rate)
         ach = flops / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "tap-GEMM, decoder 3x3 rewrite convs (4 launches/step)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "peak_source": pk["source"] + ("; TF32 dense peak taken as half the measured bf16 cuBLAS throughput (no TF32 figure is "
-                               "measured; cuBLAS bf16 is power-capped near 1.37 GHz while this kernel holds max clock, so the fraction can "
-                               "read above 1)" if tf32 else "; cuBLAS bf16 = the kind::f16 rate") +
+                "achieved": ach, "peak": peak_b, "unit": "TFLOP/s", "frac": ach / peak_b,
+                "frac_burst": ach / peak_b, "frac_sustained": ach / peak_s, "peak_sustained": peak_s,
+                "peak_source": pk["source"] + ": cuBLAS bf16 8192^3 best-of-10 (burst; the family is a ~16 % duty cycle of a step at max "
+                               "clock, so burst is the denominator of `frac`) and back-to-back for 4 s (sustained)" +
+                               ("; TF32 dense peak taken as half the bf16 figure" if tf32 else "; cuBLAS bf16 = the kind::f16 rate") +
                                "; frac_tensor_pipe is the stricter fraction of the tensor pipe's own rate at the sampled clock",
                 "peak_tensor_pipe": pipe, "frac_tensor_pipe": ach / pipe,
                 "precision": {2: "f16 operands tcgen05 (kind::f16), fp32 accumulate", 1: "tf32 tcgen05", 0: "fp32 SIMT (no tensor pipe)"}[prec],
-                "ms_per_step_in_kernel": ms_k / args.steps, "share_of_step": (ms_k / args.steps) / ms_dev,
+                "ms_per_step_in_kernel": ms_k / args.steps, "share_of_step": (ms_k / args.steps) / ms_eager,
+                "timed_in": "eager pass of the same K steps (CUDA events on the launch stream around each launch of the family)",
                 "launches_timed": n_l,
                 "per_layer_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0) for k, v in sorted(prof.items())},
-                "traffic": TRAFFIC_NCU.get(prec)}
+                "traffic": TRAFFIC_NCU.get(prec) if args.config == "4-16" else None}
+        gflop_req = cfg["gflop_req"] or cfg["gflop"]
+        step_tflops = B * gflop_req * 1e9 / (ms_dev * 1e-3) / 1e12
+        step = {"tflops": step_tflops, "frac_sustained": step_tflops / peak_s, "frac_burst": step_tflops / peak_b,
+                "gflop_per_clip_counted": gflop_req}
+        try:
+            import traffic_model
+            sr = traffic_model.step_roofline(cfg["exp"], B, L, prec, p_tensor=peak_s * 1e12)
+            step.update({"sum_of_launch_rooflines_ms": sr["sum_roofline_ms"], "frac_of_sum_of_rooflines": sr["sum_roofline_ms"] / ms_dev,
+                         "algorithmic_hbm_gb_per_step": sr["hbm_gb"], "avg_hbm_tbs": sr["hbm_gb"] / ms_dev,
+                         "how": "tools/traffic_model.py: per launch max(read/5.55, write/3.88, (r+w)/6.49 TB/s, FLOP/sustained peak), summed"})
+        except Exception as e:          # the model is tooling; the bench line does not depend on it
+            step["sum_of_launch_rooflines_ms"] = None
+            step["traffic_model_error"] = str(e)[:200]
         line = {"metric": "audio-seconds/sec forward", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {2: "f16 tensor-core operands and activation storage (10-bit mantissa = tf32), fp32 accumulate / norm inputs / cell state",
                           1: "f32 (tf32 tensor-core operands, fp32 accumulate)", 0: "f32"}[prec], "data": "synthetic",
-                "config": {"workload": f"{EXPERIMENT} inference forward, batch {B}/GPU x 2 s white-noise clips 4->16 kHz",
+                "config": {"workload": f"{cfg['name']}, batch {B}/GPU", "config_key": args.config,
                            "global_batch": total_clips, "parallelism": f"batch-sharded x{world}, no collective",
                            "l2": "activations (>700 MB/step) exceed the 126 MB L2; no explicit flush",
-                           "gflop_per_clip": GFLOP_PER_CLIP, "gflop_per_clip_required": GFLOP_PER_CLIP_REQUIRED},
-                "model_tflops": total_clips * GFLOP_PER_CLIP_REQUIRED * 1e9 / (ms_dev * 1e-3) / 1e12,
-                "e2e": {"value": e2e, "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                           "gflop_per_clip": cfg["gflop"], "gflop_per_clip_required": gflop_req,
+                           "timed_path": "CUDA-graph replay (what Aero.forward does for a steady-state shape)",
+                           "host_numa_cores": numa_cores},
+                "ms_per_step_eager": ms_eager,
+                "model_tflops": total_clips * gflop_req * 1e9 / (ms_dev * 1e-3) / 1e12,
+                "e2e": {"value": e2e, "unit": "audio-s/s", "ms_per_step": ms_e2e_med, "ms_per_step_mean": ms_e2e_mean,
+                        "statistic": "median of per-step device times (H2D + forward + D2H, one stream sync per step)",
                         "h2d_bytes_per_step": host_in.numel() * 4 * world, "d2h_bytes_per_step": host_out.numel() * 4 * world},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+                "gpu_launches": int(launches_per_step * args.steps),
+                "gpu_launches_note": f"{launches_per_step} kernels per forward x {args.steps} steps; the timed steps replay them from a "
+                                     "CUDA graph (counted on the eager pass of the same steps)",
+                "clocks": clk, "roofline": roof, "step": step}
+        for k, v in extras.items():
+            if k == "strong":
+                v["value"] = v["global_batch"] * secs / (v["ms_per_step"] * 1e-3)
+                v["what"] = (f"strong scaling sample: {v['global_batch']} clips in total split over {world} GPUs ({v['global_batch'] // world} per GPU); "
+                             "limited by the LSTM's 200 dependent steps per window and by per-launch latency at small batch")
+            else:
+                v["value"] = total_clips * secs / (v["ms_per_step"] * 1e-3)
+            line[k] = v
         if not args.no_cpu_baseline and world == 1:
-            threads = pick_cpu_threads()
-            cb = 8
-            dt = _probe(threads, cb, 1, 150)
-            line["cpu_baseline"] = {"value": (cb * CLIP_SECONDS / dt) if dt else None, "unit": "audio-s/s", "cores": threads,
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+            threads = pick_cpu_threads(args.config)
+            # bounded sample of the BASELINE.md section 3 protocol (the full one -- 2 warm-ups, median of >= 5 -- is what
+            # `--impl reference` runs): the workload's own batch, all physical cores, 1 warm-up, median of 3
+            cb = B if args.config == "4-16" else max(1, B // 4)
+            ts = _probe(args.config, threads, cb, 3, 1, 600)
+            one = _probe(args.config, 1, 1, 3, 1, 300) if args.config == "4-16" else None
+            line["cpu_baseline"] = {"value": (cb * secs / median(ts)) if ts else None, "unit": "audio-s/s", "cores": threads,
                                     "kind": "port",
-                                    "sample": f"1 forward of {cb} clips (of the {B}-clip workload) after 1 warm-up; oracle port "
-                                              f"(same torch library calls as the reference), best of the probed thread counts on {os.cpu_count()} host cores"}
+                                    "host_cores": {"logical": os.cpu_count(), "physical": physical_cores()},
+                                    "single_thread_b1": ({"value": secs / median(one), "unit": "audio-s/s", "cores": 1,
+                                                          "sample": "B=1 (BASELINE configs[0]), 1 warm-up, median of 3"} if one else None),
+                                    "sample": f"median of 3 forwards of {cb} clips (the GPU arm's per-GPU batch is {B}) after 1 warm-up; oracle port "
+                                              f"(same torch library calls as the reference) on {threads} threads = all physical cores unless a probe stalled"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -21,27 +21,15 @@ def _view(t, sizes, strides):
 
 class EmuEngine(AeroEngine):
     def __init__(self, model):
-        self.model = model
-        self.geom = model.geom
-        self.lib = None
-        self._packed = None
-        self._packed_key = None
-        self._bufs = {}
-        self._windows = {}
-        self._stats = None
+        self._init_state(model, None)
         self.precision = 0
-        self.fuse_pre_ftb = True
         self.lstm_tc = False          # the emulation states the recurrence in PyTorch's gate layout
-        self.snake = False
-        self._flip = False
-        self._seen = {}
-        self._wh = {}
-        self._prof, self._prof_tags = None, set()
-        self._wk, self._wname = {}, {}
-        self.fp32_tags = ()
         self.use_graph = False
-        self._graphs = {}
         self.calls = []
+
+    def _on_device(self):
+        import contextlib
+        return contextlib.nullcontext()
 
     def _require(self, x):
         pass

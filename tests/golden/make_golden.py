@@ -37,7 +37,12 @@ CASES = [
     ("c4_11-44_stereo", "aero_11-44_512_64", 1, 5500),          # stereo, in/out_channels=2 (0.5 s)
     ("c5_8-24_nonpow2", "aero_8-24_512_64", 1, 4000),           # hop 21 / win 170 -> hop 63 / win 510
     ("c6_4-16_hop64_short", "aero_4-16_512_64", 3, 1600),       # T=101 (<200): single LSTM window, B=3
+    # full-shape cases (round 2): the waveform is stored sub-sampled (65536 seeded positions + its rms), not whole
+    ("c7_12-48_hop128_b2_2s", "aero_12-48_512_128", 2, 24000),  # BASELINE configs[2] clip shape: T=751, 8 LSTM windows
+    ("c8_11-44_stereo_4s", "aero_11-44_512_64", 1, 44100),      # T=2757: 28 LSTM windows, 44 attention key tiles
+    ("c9_11-44_stereo_10s", "aero_11-44_512_64", 1, 110250),    # BASELINE configs[4] clip shape: T=6892 (69 windows, 108 key tiles)
 ]
+SUBSAMPLED = {"c7_12-48_hop128_b2_2s", "c8_11-44_stereo_4s", "c9_11-44_stereo_10s"}
 
 STFT_CASES = [  # n_fft, hop, win, batch-shape, length
     (512, 16, 128, (2, 1), 8000),
@@ -53,7 +58,10 @@ def main():
     ref = import_reference()
     assert ref is not None, "needs /root/reference"
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
     for name, exp, B, L in CASES:
+        if only and name not in only:
+            continue
         kw = aero_kwargs(exp)
         torch.manual_seed(SEED)
         model = ref["aero"].Aero(**kw).eval()
@@ -77,8 +85,14 @@ def main():
             out, zc, zlr = model(mix, return_spec=True, return_lr_spec=True)
         for h in handles:
             h.remove()
-        blob = {"out": out.numpy(), "digest": np.float64(digest), "B": B, "L": L, "exp": exp,
-                "torch": torch.__version__}
+        blob = {"digest": np.float64(digest), "B": B, "L": L, "exp": exp, "torch": torch.__version__}
+        if name in SUBSAMPLED:
+            flat = out.reshape(-1)
+            oi = sample_indices(flat.numel(), 65536, seed=11)
+            blob.update({"out_shape": np.array(out.shape), "out_idx": oi.numpy().astype(np.int32), "out_val": flat[oi].numpy(),
+                         "out_rms": np.float64(flat.double().pow(2).mean().sqrt())})
+        else:
+            blob["out"] = out.numpy()
         zc_r, zlr_r = torch.view_as_real(zc).reshape(-1), torch.view_as_real(zlr).reshape(-1)
         blob["spec_idx"] = sample_indices(zc_r.numel(), 8192).numpy().astype(np.int32)
         blob["spec_val"] = zc_r[blob["spec_idx"].astype(np.int64)].numpy()
@@ -93,6 +107,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
         print(name, "out", tuple(out.shape), "rms", float(out.pow(2).mean().sqrt()), "digest", digest)
 
+    if only:
+        return
     blob = {}
     for i, (n_fft, hop, win, lead, L) in enumerate(STFT_CASES):
         x = white_noise((*lead, L), seed=SEED + i)

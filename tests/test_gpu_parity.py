@@ -24,6 +24,18 @@ def build(exp):
     return m
 
 
+def wave_error(out, g):
+    """rel-L2 of a waveform against a golden file: the whole waveform, or (full-shape cases c7-c9) its committed
+    65536-position sample, whose rms must also agree with the rms of the full reference output."""
+    if "out" in g.files:
+        assert out.shape == g["out"].shape
+        return rel_l2(out.cpu(), g["out"])
+    assert tuple(out.shape) == tuple(int(v) for v in g["out_shape"])
+    flat = out.reshape(-1).cpu()
+    assert abs(float(flat.double().pow(2).mean().sqrt()) / float(g["out_rms"]) - 1) < 2e-3
+    return rel_l2(flat[torch.from_numpy(g["out_idx"].astype(np.int64))], g["out_val"])
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_forward_matches_reference_golden(golden_dir, case):
     """All-fp32 kernels (engine.precision = 0): agreement with the reference at fp32 round-off level."""
@@ -35,8 +47,8 @@ def test_forward_matches_reference_golden(golden_dir, case):
     mix = white_noise((int(g["B"]), m.in_channels, int(g["L"]))).cuda()
     out, zc, zl = m(mix, return_spec=True, return_lr_spec=True)
     torch.cuda.synchronize()
-    assert out.shape == g["out"].shape and torch.isfinite(out).all()
-    err = rel_l2(out.cpu(), g["out"])
+    assert torch.isfinite(out).all()
+    err = wave_error(out, g)
     zc_r = torch.view_as_real(zc.contiguous()).cpu().reshape(-1)[torch.from_numpy(g["spec_idx"].astype(np.int64))]
     zl_r = torch.view_as_real(zl.contiguous()).cpu().reshape(-1)[torch.from_numpy(g["lrspec_idx"].astype(np.int64))]
     print(f"{case}: rel_l2 wave {err:.3e} spec {rel_l2(zc_r, g['spec_val']):.3e} lr_spec {rel_l2(zl_r, g['lrspec_val']):.3e}")
@@ -66,6 +78,79 @@ def test_full_batch_properties():
     assert rel_l2(torch.view_as_real(lhs).cpu(), torch.view_as_real(rhs).cpu()) < 1e-5
 
 
+def test_baseline_batch_rows_match_the_oracle():
+    """BASELINE configs[1] itself (B=32 x 2 s, default engine): rows {0, 17, 31} of the batch against the ORACLE's forward of
+    those clips (not against this repo's own B=1 forward).  north_star bar: 1e-3 relative."""
+    from oracle import aero_oracle as O
+    m = build("aero_4-16_512_64")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    mix = white_noise((32, 1, 8000))
+    rows = [0, 17, 31]
+    with torch.no_grad():
+        ref = O.aero_forward(sd, m.geom, mix[rows])
+    m = m.cuda()
+    assert m._engine().precision == 2
+    out = m(mix.cuda())
+    torch.cuda.synchronize()
+    errs = [rel_l2(out[b].cpu(), ref[i]) for i, b in enumerate(rows)]
+    print("B=32 default engine vs oracle, rows 0/17/31:", " ".join(f"{e:.3e}" for e in errs))
+    assert max(errs) < TOL
+
+
+def speech_like(shape, seed):
+    """Band-limited, amplitude-modulated noise with a 60 dB level step in the middle: most of its energy below a quarter of
+    the band (like speech), a quiet first half (1e-3 of the loud half after the per-sample standardisation of aero.py:462)."""
+    x = white_noise(shape, seed=seed)
+    n = shape[-1]
+    spec = torch.fft.rfft(x)
+    f = torch.linspace(0, 1, spec.shape[-1])
+    x = torch.fft.irfft(spec * (1.0 / (1.0 + (f / 0.12) ** 4)), n=n)
+    env = 0.55 + 0.45 * torch.sin(torch.linspace(0, 37.0, n)) ** 2
+    x = x * env
+    x[..., : n // 2] *= 1e-3
+    return (x / x.abs().max()).contiguous()
+
+
+def test_hard_input_fp16_range_and_parity():
+    """FP16 activation storage under stress: speech-like input with a 60 dB level step and weights re-scaled so that the
+    pre-normalisation tensors reach |x| ~ 1e3 (GroupNorm undoes the scale, so the reference output is well defined).
+    Checks (1) no FP16 buffer comes near saturation (cvt.rn.satfinite clamps silently at 65504), (2) the default engine agrees
+    with the oracle and with the TF32 engine within the 1e-3 bar, (3) the quiet half of the clip is reproduced too."""
+    from oracle import aero_oracle as O
+    m = build("aero_4-16_512_64")
+    sd = m.state_dict()
+    big = {}
+    for k, v in sd.items():
+        pre_norm = (k.startswith(("encoder.2.conv.", "encoder.3.conv.", "encoder.2.rewrite.", "encoder.3.rewrite.",
+                                  "decoder.0.rewrite.", "decoder.1.rewrite.", "decoder.0.conv_tr.", "decoder.1.conv_tr."))
+                    or ".dconv.layers." in k and (".conv1.0." in k or ".conv2.0." in k))
+        big[k] = v * 300.0 if pre_norm else v.clone()
+    m.load_state_dict(big)
+    mix = speech_like((2, 1, 4000), seed=21)
+    with torch.no_grad():
+        ref = O.aero_forward({k: v.clone() for k, v in m.state_dict().items()}, m.geom, mix)
+    m = m.cuda()
+    eng = m._engine()
+    eng.use_graph = False
+    outs = {}
+    for prec in (2, 1):
+        eng.precision = prec
+        outs[prec] = m(mix.cuda()).cpu()
+        if prec == 2:
+            torch.cuda.synchronize()
+            halves = [(k[0], float(t.float().abs().max())) for k, t in eng._bufs.items() if t.dtype == torch.float16]
+            assert halves, "precision 2 must store activations in FP16"
+            worst = max(halves, key=lambda kv: kv[1])
+            print(f"largest |x| in an FP16 activation buffer: {worst[1]:.1f} ({worst[0]})")
+            assert worst[1] < 0.5 * 65504
+    e2, e1, e21 = rel_l2(outs[2], ref), rel_l2(outs[1], ref), rel_l2(outs[2], outs[1])
+    half = ref.shape[-1] // 2
+    q2 = rel_l2(outs[2][..., : half - 600], ref[..., : half - 600])
+    print(f"hard input: precision 2 vs oracle {e2:.3e}, precision 1 vs oracle {e1:.3e}, 2 vs 1 {e21:.3e}, quiet half {q2:.3e}")
+    assert torch.isfinite(outs[2]).all() and e2 < TOL and e1 < TOL and e21 < TOL
+    assert q2 < 5e-3        # the part of the clip 60 dB down: same order as the bar, no blow-up from FP16 subnormals
+
+
 def test_repeatable_and_buffer_reuse():
     m = build("aero_4-16_512_256").cuda()
     a = white_noise((2, 1, 8000)).cuda()
@@ -93,7 +178,7 @@ def test_forward_tensor_core_paths_within_tolerance(golden_dir, case, precision)
     mix = white_noise((int(g["B"]), m.in_channels, int(g["L"]))).cuda()
     out, zc = m(mix, return_spec=True)
     torch.cuda.synchronize()
-    err = rel_l2(out.cpu(), g["out"])
+    err = wave_error(out, g)
     zc_r = torch.view_as_real(zc.contiguous()).cpu().reshape(-1)[torch.from_numpy(g["spec_idx"].astype(np.int64))]
     print(f"{case} [precision {precision}]: rel_l2 wave {err:.3e} spec {rel_l2(zc_r, g['spec_val']):.3e}")
     assert torch.isfinite(out).all()

@@ -15,6 +15,9 @@ from oracle import aero_oracle as O
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c*.npz")))
 FAST = {"c2_4-16_hop256_ragged", "c5_8-24_nonpow2", "c6_4-16_hop64_short"}
+# the 10-s stereo case costs ~1 minute and several GB of attention scores per oracle forward: the oracle is pinned on it
+# only when asked for (AERO_SLOW_TESTS=1); its 4-s sibling c8 exercises the same windowing / key-tile regime every run
+SLOW = {"c9_11-44_stereo_10s"}
 
 
 def build_case(golden_dir, case):
@@ -30,8 +33,14 @@ def build_case(golden_dir, case):
 
 
 def check_against_golden(g, out, zc, zlr, taps, tol):
-    assert out.shape == g["out"].shape
-    assert rel_l2(out, g["out"]) < tol
+    if "out" in g.files:
+        assert out.shape == g["out"].shape
+        assert rel_l2(out, g["out"]) < tol
+    else:                       # full-shape cases: the waveform is committed as a 65536-position sample + its rms
+        assert tuple(out.shape) == tuple(int(v) for v in g["out_shape"])
+        flat = out.reshape(-1)
+        assert rel_l2(flat[torch.from_numpy(g["out_idx"].astype(np.int64))], g["out_val"]) < tol
+        assert abs(float(flat.double().pow(2).mean().sqrt()) / float(g["out_rms"]) - 1) < 1e-4
     zc_r = torch.view_as_real(zc).reshape(-1)[torch.from_numpy(g["spec_idx"].astype(np.int64))]
     assert rel_l2(zc_r, g["spec_val"]) < tol
     zl_r = torch.view_as_real(zlr).reshape(-1)[torch.from_numpy(g["lrspec_idx"].astype(np.int64))]
@@ -45,6 +54,8 @@ def check_against_golden(g, out, zc, zlr, taps, tol):
 
 @pytest.mark.parametrize("case", CASES)
 def test_oracle_library_form_matches_reference_golden(golden_dir, case):
+    if case in SLOW and not os.environ.get("AERO_SLOW_TESTS"):
+        pytest.skip("slow (set AERO_SLOW_TESTS=1)")
     g, model, mix = build_case(golden_dir, case)
     taps = {}
     with torch.no_grad():
