@@ -48,8 +48,8 @@ constexpr int kMaxGroups = 8;
 // Thread mapping: a thread owns ONE channel quad c (gamma / beta / LayerScale loaded once) and walks over pixels
 // (t, then output rows) with a fixed stride -- no per-element index arithmetic, 16-byte accesses, consecutive lanes on
 // consecutive channel quads of the same pixel (then the next pixel), i.e. fully coalesced.
-template <int OP, typename TO>
-__global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+template <int OP, typename TO, typename TI>
+__global__ void __launch_bounds__(256) norm_act_kernel(const TI* x, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ snake_a, const float* __restrict__ scale,
                                                        const TO* residual, TO* y,
@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
         pw.next();
         const int fl1 = f_lo + pw.f, t1 = pw.t;
         pw.next();
-        const float* xp0 = x + (((int64_t)b * p.F_in + fl0 + p.f_off) * p.T + t0) * p.C + c;
-        const float* xp1 = x + (((int64_t)b * p.F_in + fl1 + p.f_off) * p.T + t1) * p.C + c;
+        const TI* xp0 = x + (((int64_t)b * p.F_in + fl0 + p.f_off) * p.T + t0) * p.C + c;
+        const TI* xp1 = x + (((int64_t)b * p.F_in + fl1 + p.f_off) * p.T + t1) * p.C + c;
         const int64_t oi0 = (((int64_t)b * p.F_out + fl0) * p.T + t0) * Cout + c;
         const int64_t oi1 = (((int64_t)b * p.F_out + fl1) * p.T + t1) * Cout + c;
-        const float4 va = *reinterpret_cast<const float4*>(xp0), vb = *reinterpret_cast<const float4*>(xp1);
-        const float4 va2 = GLU ? *reinterpret_cast<const float4*>(xp0 + Cout) : zero4;
-        const float4 vb2 = GLU ? *reinterpret_cast<const float4*>(xp1 + Cout) : zero4;
+        const float4 va = ld4(xp0), vb = ld4(xp1);
+        const float4 va2 = GLU ? ld4(xp0 + Cout) : zero4;
+        const float4 vb2 = GLU ? ld4(xp1 + Cout) : zero4;
         const float4 ra = (OP == AERO_NA_GLU_SCALE_RES) ? ld4(residual + oi0) : zero4;
         const float4 rb = (OP == AERO_NA_GLU_SCALE_RES) ? ld4(residual + oi1) : zero4;
         finish(va, va2, ra, fl0 + p.f_off, oi0);
@@ -155,10 +155,10 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float* __restrict__
     }
     if (pix < npix) {
         const int fl0 = f_lo + pw.f, t0 = pw.t;
-        const float* xp0 = x + (((int64_t)b * p.F_in + fl0 + p.f_off) * p.T + t0) * p.C + c;
+        const TI* xp0 = x + (((int64_t)b * p.F_in + fl0 + p.f_off) * p.T + t0) * p.C + c;
         const int64_t oi0 = (((int64_t)b * p.F_out + fl0) * p.T + t0) * Cout + c;
-        const float4 va = *reinterpret_cast<const float4*>(xp0);
-        const float4 va2 = GLU ? *reinterpret_cast<const float4*>(xp0 + Cout) : zero4;
+        const float4 va = ld4(xp0);
+        const float4 va2 = GLU ? ld4(xp0 + Cout) : zero4;
         const float4 ra = (OP == AERO_NA_GLU_SCALE_RES) ? ld4(residual + oi0) : zero4;
         finish(va, va2, ra, fl0 + p.f_off, oi0);
     }
@@ -179,7 +179,7 @@ extern "C" int aero_sample_norm_fwd(const float* x, const double* stats, float* 
     return check_launch("aero_sample_norm_fwd");
 }
 
-extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
+extern "C" int aero_norm_act_fwd(const void* x, const double* stats, const float* gamma, const float* beta,
                                  const float* snake_a, const float* scale, const void* residual, void* y,
                                  const aero_norm_act_params* p, aero_stream_t stream) {
     using namespace aero;
@@ -205,10 +205,12 @@ extern "C" int aero_norm_act_fwd(const float* x, const double* stats, const floa
     AERO_REQUIRE(nseg <= 65535, "aero_norm_act_fwd: at most 65535 segments (got %d)", nseg);
     dim3 grid(chunks, nseg);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool o16 = p->flags & AERO_TG_OUT_F16;
+    const bool o16 = p->flags & AERO_TG_OUT_F16, i16 = p->flags & AERO_TG_A_F16;
+    AERO_REQUIRE(!i16 || o16, "aero_norm_act_fwd: an FP16 input goes with an FP16 output");
 #define AERO_NA_LAUNCH(OP)                                                                                                  \
-    if (o16) norm_act_kernel<OP, __half><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, (const __half*)residual, (__half*)y, *p); \
-    else norm_act_kernel<OP, float><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, (const float*)residual, (float*)y, *p)
+    if (i16) norm_act_kernel<OP, __half, __half><<<grid, 256, 0, st>>>((const __half*)x, stats, gamma, beta, snake_a, scale, (const __half*)residual, (__half*)y, *p); \
+    else if (o16) norm_act_kernel<OP, __half, float><<<grid, 256, 0, st>>>((const float*)x, stats, gamma, beta, snake_a, scale, (const __half*)residual, (__half*)y, *p); \
+    else norm_act_kernel<OP, float, float><<<grid, 256, 0, st>>>((const float*)x, stats, gamma, beta, snake_a, scale, (const float*)residual, (float*)y, *p)
     switch (p->op) {
         case AERO_NA_NONE: AERO_NA_LAUNCH(AERO_NA_NONE); break;
         case AERO_NA_GELU: AERO_NA_LAUNCH(AERO_NA_GELU); break;

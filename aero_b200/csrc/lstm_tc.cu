@@ -15,10 +15,15 @@
 //   D = (4/GPT) x 16 fp32 columns of TMEM, read back with tcgen05.ld by the same threads.
 // The input-projection gate pre-activations keep PyTorch's [dir][i,f,g,o][H] column order (a warp reads the contiguous
 // cells of one gate per sequence); with one CTA per SM (GPT = 1) they are requested a whole step ahead.
+// Round 2: a CTA owns SEQ = 8 or 16 sequences (the UMMA N stays 16; unused operand rows are zero).  With 8, and W_hh for
+// 64 < H <= 96 held in 32-column SWIZZLE_64B chunks (96 KB instead of 128 KB, no zero K padding: 24 UMMAs per step instead
+// of 32), two CTAs share an SM: one CTA's MMA / barrier latency overlaps the other's exp-heavy cell update, and the
+// sequences spread over all SMs instead of 96 of them.
 // One elected lane issues the MMAs back to back from step-invariant descriptors; two mbarriers ping-pong between
 // "h ready" and "accumulators ready".  c stays in registers for the whole sequence.  8 (GPT = 2) or 16 (GPT = 1)
 // cell-update warps; in the two-gates-per-tile layout a lane finishes only its own half of the warp's sequences.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "tc_common.cuh"
 
 #ifdef AERO_TC_TRACE
@@ -33,7 +38,13 @@ extern "C" int aero_debug_lstm_trace(long long* host) {
 
 namespace aero {
 
-constexpr int kNT = 16;          // sequences per CTA (UMMA N)
+constexpr int kNT = 16;          // UMMA N (operand rows of h); a CTA fills SEQ = 8 or 16 of them
+
+// tuning knob, read from the environment once: AERO_LSTM_SEQ = 8 / 16 forces the CTA size (0 / unset: chosen per launch)
+static int lstm_seq_knob() {
+    static const int v = [] { const char* e = getenv("AERO_LSTM_SEQ"); return e ? atoi(e) : 0; }();
+    return v;
+}
 
 struct LstmTcShared {
     uint64_t w_full;
@@ -91,23 +102,34 @@ __device__ __forceinline__ void tmem_ld_n<4>(uint32_t taddr, uint32_t (&r)[4]) {
         : "memory");
 }
 
-// GPT: gates per 128-row tile.  NEW: cell-update warps (NEW/4 per TMEM lane quarter, each owning 64/NEW sequences).
-template <int GPT, int NEW, typename TO>
-__global__ void __launch_bounds__(64 + 32 * NEW, (GPT == 1 ? 1 : 2))
+// K-major shared-memory matrix descriptor for a swizzled operand whose rows are ROWB bytes (128: SWIZZLE_128B, layout type 2;
+// 64: SWIZZLE_64B, layout type 4); 8-row groups are ROWB * 8 bytes apart (SBO)
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((ROWB * 8) >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)(ROWB == 128 ? 2 : 4) << 61);
+}
+
+// GPT: gates per 128-row tile.  NEW: cell-update warps (NEW/4 per TMEM lane quarter, each owning 4*SEQ/NEW sequences).
+// SEQ: sequences per CTA (8 or 16).  ROWB: bytes of K per operand row of a chunk (128 = 64 fp16, SWIZZLE_128B; 64 = 32 fp16,
+// SWIZZLE_64B).  MINB: CTAs per SM the register budget is set for.
+template <int GPT, int NEW, int SEQ, int ROWB, int MINB, typename TO>
+__global__ void __launch_bounds__(64 + 32 * NEW, MINB)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ gin, const float* __restrict__ bias_pad,
                TO* __restrict__ hout, const aero_lstm_params p, const int nK) {
     constexpr int NM = 4 / GPT;                          // M tiles
     constexpr int CPW = 32 / GPT;                        // cells per warp
-    constexpr int kNS = 64 / NEW;                        // sequences per cell-update warp
+    constexpr int kNS = 4 * SEQ / NEW;                   // sequences per cell-update warp
+    constexpr int kATile = 128 * ROWB, kBTile = kNT * ROWB, kKC = ROWB / 2;   // bytes per A / B chunk tile, fp16 of K per chunk
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                                  // [NM][nK] tiles of 128 rows x 128 B (64 fp16 of K)
-    uint8_t* sB = smem + NM * nK * 16384;                // [nK] tiles of 16 rows x 128 B
-    LstmTcShared* sh = reinterpret_cast<LstmTcShared*>(sB + nK * 2048);
+    uint8_t* sA = smem;                                  // [NM][nK] tiles of 128 rows x ROWB bytes
+    uint8_t* sB = smem + NM * nK * kATile;               // [nK] tiles of 16 rows x ROWB bytes
+    LstmTcShared* sh = reinterpret_cast<LstmTcShared*>(sB + nK * kBTile);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    const int seq0 = blockIdx.x * kNT;
+    const int seq0 = blockIdx.x * SEQ;
     const int n_seq = p.rows * p.n_win;
     const int H = p.H;
     const int ldg = 8 * H;                               // floats per gin row: [dir][i,f,g,o][H], PyTorch's own order
@@ -118,7 +140,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         mbar_init(&sh->h_ready, 32 * NEW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < nK * 2048 / 4; i += blockDim.x) reinterpret_cast<float*>(sB)[i] = 0.f;
+    for (int i = threadIdx.x; i < nK * kBTile / 4; i += blockDim.x) reinterpret_cast<float*>(sB)[i] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(64u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -132,10 +154,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
-            mbar_expect_tx(&sh->w_full, (uint32_t)(NM * nK * 16384));
+            mbar_expect_tx(&sh->w_full, (uint32_t)(NM * nK * kATile));
             for (int m = 0; m < NM; ++m)
                 for (int kc = 0; kc < nK; ++kc)
-                    tma_load_2d(sA + (m * nK + kc) * 16384, &mapW, &sh->w_full, kc * 64, (dir * NM + m) * 128);
+                    tma_load_2d(sA + (m * nK + kc) * kATile, &mapW, &sh->w_full, kc * kKC, (dir * NM + m) * 128);
         }
     } else if (warp == 1) {
         // The whole warp walks the step loop and one elected lane issues: with `elect.sync` the compiler knows the tcgen05
@@ -146,13 +168,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             // The issuing thread is on the per-step critical path (a single thread pays ~6 cycles per dependent instruction):
             // every descriptor is step-invariant, so build them once; only the low word changes along K (+2 per 32 bytes).
-            uint32_t da_lo[NM][2], db_lo[2];
-            const uint32_t d_hi = (uint32_t)(make_desc_sw128(0) >> 32);
+            constexpr int kMaxKC = (ROWB == 128) ? 2 : 4;     // H <= 128
+            uint32_t da_lo[NM][kMaxKC], db_lo[kMaxKC];
+            const uint32_t d_hi = (uint32_t)(make_desc_kmajor<ROWB>(0) >> 32);
 #pragma unroll
-            for (int kc = 0; kc < 2; ++kc) {
-                db_lo[kc] = (uint32_t)make_desc_sw128(b0 + (uint32_t)(kc * 2048));
+            for (int kc = 0; kc < kMaxKC; ++kc) {
+                db_lo[kc] = (uint32_t)make_desc_kmajor<ROWB>(b0 + (uint32_t)(kc * kBTile));
 #pragma unroll
-                for (int m = 0; m < NM; ++m) da_lo[m][kc] = (uint32_t)make_desc_sw128(a0 + (uint32_t)((m * nK + kc) * 16384));
+                for (int m = 0; m < NM; ++m) da_lo[m][kc] = (uint32_t)make_desc_kmajor<ROWB>(a0 + (uint32_t)((m * nK + kc) * kATile));
             }
             mbar_wait(&sh->w_full, 0);
             for (int s = 1; s < p.steps; ++s) {
@@ -163,10 +186,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
 #pragma unroll
                 for (int m = 0; m < NM; ++m) {
 #pragma unroll
-                    for (int kc = 0; kc < 2; ++kc) {
+                    for (int kc = 0; kc < kMaxKC; ++kc) {
                         if (kc < nK) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {              // K = 16 fp16 = 32 B per UMMA
+                            for (int k = 0; k < ROWB / 32; ++k) {      // K = 16 fp16 = 32 B per UMMA
                                 if (kc == 0 && k == 0) umma_f16_lohi<false>(tmem_base + (uint32_t)(m * kNT), da_lo[m][kc], db_lo[kc], d_hi, idesc);
                                 else umma_f16_lohi<true>(tmem_base + (uint32_t)(m * kNT), da_lo[m][kc] + 2 * k, db_lo[kc] + 2 * k, d_hi, idesc);
                             }
@@ -204,8 +227,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         int goff[kNS], g_lo[kNS], g_len[kNS];
         int ooff[kMS], w_lo[kMS], w_len[kMS];
         uint32_t baddr[kMS];
-        const int jq = (cell & 63) >> 3;
-        const uint32_t bbase = smem_u32(sB) + (uint32_t)((cell >> 6) * 2048 + ((cell & 7) << 1));
+        const int jq = (cell & (kKC - 1)) >> 3;                              // 16-byte unit of this cell inside its chunk row
+        const uint32_t bbase = smem_u32(sB) + (uint32_t)((cell / kKC) * kBTile + ((cell & 7) << 1));
 #pragma unroll
         for (int i = 0; i < kNS; ++i) {
             const int n = wp * kNS + i;
@@ -235,8 +258,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
             if (!exists || !cell_ok) hi = lo;
             w_lo[ii] = dir ? p.steps - hi : lo;
             w_len[ii] = max(0, hi - lo);
-            // swizzled B-operand address of (sequence n, k = cell), fp16: tile kc = cell/64, row n (128 B), chunk (j/8)^(n%8)
-            baddr[ii] = bbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((jq ^ (n & 7)) << 4));
+            // swizzled B-operand address of (sequence n, k = cell), fp16: chunk tile cell / kKC, row n (ROWB bytes), 16-byte unit
+            // jq XOR-ed with the row (SWIZZLE_128B: n % 8; SWIZZLE_64B: (n / 2) % 4)
+            baddr[ii] = bbase + (uint32_t)((n >> 3) * (8 * ROWB) + (n & 7) * ROWB + ((jq ^ (ROWB == 128 ? (n & 7) : ((n >> 1) & 3))) << 4));
         }
         const float* bptr = bias_pad + gcol;
         const int gstep = dpos * ldg, ostep = dpos * 2 * H;
@@ -355,11 +379,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
     }
 }
 
-template <int GPT, int NEW, typename TO>
+template <int GPT, int NEW, int SEQ, int ROWB, int MINB, typename TO>
 static void lstm_tc_go(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mW, const float* gin, const float* bias_pad, void* hout,
                        const aero_lstm_params& p, int nK) {
-    cudaFuncSetAttribute(lstm_tc_kernel<GPT, NEW, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lstm_tc_kernel<GPT, NEW, TO><<<grid, 64 + 32 * NEW, smem, st>>>(mW, gin, bias_pad, static_cast<TO*>(hout), p, nK);
+    cudaFuncSetAttribute(lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO><<<grid, 64 + 32 * NEW, smem, st>>>(mW, gin, bias_pad, static_cast<TO*>(hout), p, nK);
 }
 
 int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
@@ -369,35 +393,55 @@ int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, v
         set_error("aero_lstm_rec_fwd(tcgen05): hidden size %d unsupported (multiple of 4 in (32, 128])", H);
         return AERO_ERR_UNSUPPORTED;
     }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_seq = p.rows * p.n_win;
     const int gpt = H <= 64 ? 2 : 1;
-    const int nM = 4 / gpt, nK = (H + 63) / 64;
-    const int Kp = nK * 64;                              // the host pads W_hh rows to a multiple of 64 fp16 (128 bytes)
+    const int nM = 4 / gpt;
+    const int Kp = ((H + 63) / 64) * 64;                 // the host pads W_hh rows to a multiple of 64 fp16 (128 bytes)
+    // Small CTAs (8 sequences) whenever all of them fit on the GPU at once at the co-residency they allow: twice the SMs
+    // busy and, where two or three share an SM, one CTA's barrier / MMA latency hides behind another's cell update.
+    // GPT = 1 keeps W_hh in 32-column SWIZZLE_64B chunks then (no K padding; two CTAs per SM up to H = 96).
+    const int knob = lstm_seq_knob();
+    const bool small = knob ? knob == 8 : (int64_t)cdiv(n_seq, 8) * 2 <= (int64_t)num_sms * (gpt == 1 ? (H <= 96 ? 2 : 1) : 3);
+    const int rowb = (gpt == 1 && small) ? 64 : 128;
+    const int kc_elems = rowb / 2;
+    const int nK = (H + kc_elems - 1) / kc_elems;
     CUtensorMap mW;
     uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)(2 * nM * 128)};
     uint64_t strides[1] = {(uint64_t)Kp * 2};
-    uint32_t box[2] = {64, 128};
-    int rc = encode_map(&mW, whh_r, 2, dims, strides, box, false, 2);
+    uint32_t box[2] = {(uint32_t)kc_elems, 128};
+    int rc = encode_map(&mW, whh_r, 2, dims, strides, box, rowb == 64 ? 2 : 0, 2);
     if (rc != AERO_OK) return rc;
-    const size_t smem = (size_t)nM * nK * 16384 + (size_t)nK * 2048 + sizeof(LstmTcShared) + 1024;
+    const size_t smem = (size_t)nM * nK * 128 * rowb + (size_t)nK * kNT * rowb + sizeof(LstmTcShared) + 1024;
     if (smem > 227 * 1024) {
         set_error("aero_lstm_rec_fwd(tcgen05): hidden size %d needs %zu bytes of shared memory", H, smem);
         return AERO_ERR_UNSUPPORTED;
     }
-    const int n_seq = p.rows * p.n_win;
     const int64_t max_rows = (int64_t)n_seq * p.steps > (int64_t)p.rows * p.T ? (int64_t)n_seq * p.steps : (int64_t)p.rows * p.T;
     if ((max_rows + p.steps) * (8ll * H) >= (1ll << 31)) {
         set_error("aero_lstm_rec_fwd(tcgen05): problem too large for 32-bit offsets (%lld rows)", (long long)max_rows);
         return AERO_ERR_UNSUPPORTED;
     }
-    dim3 grid(cdiv(n_seq, kNT), 2);
+    dim3 grid(cdiv(n_seq, small ? 8 : kNT), 2);
     const bool o16 = p.flags & AERO_TG_OUT_F16;
+#define AERO_LSTM_GO(GPT, NEW, SEQ, ROWB, MINB)                                                              \
+    do {                                                                                                      \
+        if (o16) lstm_tc_go<GPT, NEW, SEQ, ROWB, MINB, __half>(grid, smem, st, mW, gin, bias_pad, hout, p, nK); \
+        else lstm_tc_go<GPT, NEW, SEQ, ROWB, MINB, float>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);      \
+    } while (0)
     if (gpt == 1) {
-        if (o16) lstm_tc_go<1, 16, __half>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
-        else lstm_tc_go<1, 16, float>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
+        if (small) AERO_LSTM_GO(1, 8, 8, 64, 2);
+        else AERO_LSTM_GO(1, 16, 16, 128, 1);
     } else {
-        if (o16) lstm_tc_go<2, 8, __half>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
-        else lstm_tc_go<2, 8, float>(grid, smem, st, mW, gin, bias_pad, hout, p, nK);
+        if (small) AERO_LSTM_GO(2, 8, 8, 128, 3);
+        else AERO_LSTM_GO(2, 8, 16, 128, 2);
     }
+#undef AERO_LSTM_GO
     return check_launch("aero_lstm_rec_fwd(tcgen05)");
 }
 

@@ -192,6 +192,9 @@ __device__ __forceinline__ void epilogue_fast_tile(TcShared* sh, const TapGemmAr
                 if (affine) { x.x = fmaf(x.x, sa, sb); x.y = fmaf(x.y, sa, sb); x.z = fmaf(x.z, sa, sb); x.w = fmaf(x.w, sa, sb); }
                 if (rnd) { x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w); }
                 if (STATS) {
+                    if (sizeof(TO) == 2) {               // statistics describe the values as stored (FP16 pre-normalisation tensors)
+                        x.x = stored(x.x, op); x.y = stored(x.y, op); x.z = stored(x.z, op); x.w = stored(x.w, op);
+                    }
                     ls += (x.x + x.y) + (x.z + x.w);
                     lq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
                 }
@@ -301,6 +304,10 @@ __device__ __forceinline__ void epilogue_direct(TcShared* sh, const TapGemmArgs&
             if (rnd) {
 #pragma unroll
                 for (int j = 0; j < CNT; ++j) o[j] = round_tf32_rna(o[j]);
+            }
+            if (F16 && STATS) {                          // statistics describe the values as stored
+#pragma unroll
+                for (int j = 0; j < CNT; ++j) o[j] = stored(o[j], orow);
             }
             if (F16) {
 #pragma unroll
@@ -611,6 +618,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
                                 if (rp) x += ldf(rp + nn);
                                 x = x * sa + sb;
                                 if (rnd) x = round_tf32_rna(x);
+                                x = stored(x, op);
                                 o[jj] = x;
                                 ssum += x;
                                 ssq += x * x;
@@ -693,14 +701,14 @@ struct MapKeyHash {
 };
 
 int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, bool swizzle_32b_atom, int elem_bytes) {
+               const uint32_t* box, int swizzle_mode, int elem_bytes) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key;
     std::memset(&key, 0, sizeof(key));
     key.base = base;
     key.rank = rank;
-    key.swz = (swizzle_32b_atom ? 1u : 0u) | ((uint32_t)elem_bytes << 8);
+    key.swz = (uint32_t)swizzle_mode | ((uint32_t)elem_bytes << 8);
     for (uint32_t i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.box[i] = box[i]; }
     for (uint32_t i = 0; i + 1 < rank; ++i) key.s[i] = strides_bytes[i];
     {
@@ -716,7 +724,8 @@ int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t
     for (uint32_t i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (uint32_t i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_mode == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -786,8 +795,8 @@ static KernelFn pick_kernel(int amode, bool res, bool stats) {
             {{AERO_TC_K(2, false, false), AERO_TC_K(2, false, true)}, {AERO_TC_K(2, true, false), AERO_TC_K(2, true, true)}},
             {{AERO_TC_K(3, false, false), AERO_TC_K(3, false, true)}, {AERO_TC_K(3, true, false), AERO_TC_K(3, true, true)}}};
         return table[amode][res][stats];
-    } else if constexpr (F16O) {                   // FP16 outputs: no statistics; residual only without activation
-        if (stats) return nullptr;
+    } else if constexpr (F16O) {                   // FP16 outputs: statistics / residual only without activation
+        if (stats) return (amode == 0 && !res) ? AERO_TC_K(0, false, true) : nullptr;
         if (res) return amode == 0 ? AERO_TC_K(0, true, false) : nullptr;
         switch (amode) {
             case 0: return AERO_TC_K(0, false, false);
@@ -803,7 +812,7 @@ static KernelFn pick_kernel(int amode, bool res, bool stats) {
             case 0: return AERO_TC_K(0, false, false);
             case 1: return AERO_TC_K(1, false, false);
             case 2: return AERO_TC_K(2, false, false);
-            default: return nullptr;
+            default: return AERO_TC_K(3, false, false);      // fp32 GLU output: the last decoder layer (feeds the exact-fp32 conv-T)
         }
     }
 #undef AERO_TC_K

@@ -6,9 +6,10 @@
 namespace aero {
 
 // host: cached cuTensorMapEncodeTiled (fp32, SWIZZLE_128B, zero OOB fill); implemented in tapgemm_tc.cu
-// swizzle_32b_atom: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (pairs with UMMA SWIZZLE_128B_BASE32B, the only layout for MN-major tf32)
+// swizzle_mode: 0 = CU_TENSOR_MAP_SWIZZLE_128B; 1 = SWIZZLE_128B_ATOM_32B (pairs with UMMA SWIZZLE_128B_BASE32B, the only layout
+// for MN-major tf32); 2 = SWIZZLE_64B (64-byte operand rows)
 int encode_map(CUtensorMap* out, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, bool swizzle_32b_atom = false, int elem_bytes = 4);
+               const uint32_t* box, int swizzle_mode = 0, int elem_bytes = 4);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -175,9 +175,11 @@ typedef struct {
     int32_t groups, scope, op;
     float eps;
     int32_t flags;                    /* AERO_TG_ROUND_TF32: round stored fp32 outputs to TF32 for a tensor-core consumer;
-                                         AERO_TG_OUT_F16: y and residual are FP16 (x is always fp32: GroupNorm inputs stay fp32) */
+                                         AERO_TG_OUT_F16: y and residual are FP16; AERO_TG_A_F16: x is FP16 too (pre-normalisation
+                                         tensors stored in FP16; the statistics were taken from the stored values); x == y is
+                                         allowed when they have the same type and the op keeps the channel count */
 } aero_norm_act_params;
-int aero_norm_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
+int aero_norm_act_fwd(const void* x, const double* stats, const float* gamma, const float* beta,
                       const float* snake_a, const float* scale, const void* residual, void* y,
                       const aero_norm_act_params* p, aero_stream_t stream);
 

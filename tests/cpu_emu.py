@@ -109,6 +109,7 @@ class EmuEngine(AeroEngine):
             v = v * samp_affine.double()[:, 0].view(B, 1, 1, 1) + samp_affine.double()[:, 1].view(B, 1, 1, 1)
         vf = v.float()
         _view(out, (B, F_out, T, n_out), (*o_s, 1)).copy_(vf)
+        vf = _view(out, (B, F_out, T, n_out), (*o_s, 1)).float()          # statistics describe the values as stored (FP16 raws)
         if stats_mode == 1:
             g = vf.double().view(B, F_out * T, groups, n_out // groups)
             stats[:, 0] += g.sum((1, 3)).reshape(-1)
