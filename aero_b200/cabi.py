@@ -16,13 +16,15 @@ vp = C.c_void_p
 class StftParams(C.Structure):
     _fields_ = [("n_fft", i32), ("hop", i32), ("win", i32), ("n_signals", i32), ("channels", i32),
                 ("length", i32), ("frames", i32), ("bins_out", i32),
-                ("z_stride_b", i64), ("z_stride_c", i64), ("z_stride_k", i64), ("z_stride_t", i64)]
+                ("z_stride_b", i64), ("z_stride_c", i64), ("z_stride_k", i64), ("z_stride_t", i64),
+                ("flags", i32), ("reserved", i32)]
 
 
 class IstftParams(C.Structure):
     _fields_ = [("n_fft", i32), ("hop", i32), ("win", i32), ("n_signals", i32), ("channels", i32),
                 ("frames", i32), ("bins_in", i32), ("out_len", i32),
-                ("z_stride_b", i64), ("z_stride_c", i64), ("z_stride_k", i64), ("z_stride_t", i64)]
+                ("z_stride_b", i64), ("z_stride_c", i64), ("z_stride_k", i64), ("z_stride_t", i64),
+                ("flags", i32), ("reserved", i32)]
 
 
 class TapGemmParams(C.Structure):
@@ -59,11 +61,13 @@ class AttnParams(C.Structure):
     _fields_ = [("rows", i32), ("T", i32), ("H", i32), ("heads", i32), ("ndecay", i32), ("ld", i32), ("flags", i32)]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TAPS_CONV, TAPS_CONVT, TAPS_MIX = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 TG_ROUND_TF32, TG_A_F16, TG_OUT_F16, TG_REVERSE = 1, 2, 4, 8      # storage-type flags (AERO_TG_*)
-NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES = 0, 1, 2, 3, 4
+NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES, NA_RELU = 0, 1, 2, 3, 4, 5
+NA_NO_NORM = 16
+STFT_ZERO_PAD, STFT_ADJ_SCALE, ISTFT_RAW = 1, 2, 1
 
 # every symbol include/aero_b200.h declares (tests/test_cabi.py checks the library exports them all)
 SYMBOLS = {
@@ -84,6 +88,18 @@ SYMBOLS = {
     "aero_local_attn_fwd": (C.c_int, [vp, vp, C.POINTER(AttnParams), vp]),
     "aero_lsd_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "aero_stft_loss_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    # training
+    "aero_tapgemm_wgrad": (C.c_int, [vp, vp, vp, vp, C.POINTER(TapGemmParams), i64, i64, i64, vp]),
+    "aero_colsum": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i64, i64, i64, i32, i64, i64, vp]),
+    "aero_add": (C.c_int, [vp, vp, i64, f32, vp]),
+    "aero_norm_act_train_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
+    "aero_norm_act_train_bwd": (C.c_int, [vp] * 13 + [i32, C.POINTER(NormActParams), vp]),
+    "aero_adam_step": (C.c_int, [vp, i32, f32, f32, f32, f32, i32, f32, vp]),
+    "aero_lstm_train_fwd": (C.c_int, [vp] * 7 + [C.POINTER(LstmParams), vp]),
+    "aero_lstm_bwd": (C.c_int, [vp] * 5 + [C.POINTER(LstmParams), vp]),
+    "aero_lstm_fold": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "aero_local_attn_train_fwd": (C.c_int, [vp, vp, vp, C.POINTER(AttnParams), vp]),
+    "aero_local_attn_bwd": (C.c_int, [vp] * 5 + [C.POINTER(AttnParams), vp]),
 }
 
 

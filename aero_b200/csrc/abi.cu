@@ -25,7 +25,7 @@ int check_launch(const char* what) {
 }  // namespace aero
 
 extern "C" {
-int aero_abi_version(void) { return 2; }
+int aero_abi_version(void) { return 3; }
 const char* aero_last_error(void) { return aero::g_err; }
 uint64_t aero_launch_count(void) { return aero::g_launches.load(); }
 int aero_device_arch(void) {

@@ -83,11 +83,13 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(const float* __restrict_
     const int seg_len = (nfr - 1) * p.hop + N;
     const float* xs = x + (int64_t)sig * L;
     const int q0 = t0 * p.hop - N / 2;
+    const bool zero_pad = p.flags & AERO_STFT_ZERO_PAD;
     for (int i = threadIdx.x; i < seg_len; i += kThreads) {
         int src = q0 + i;
+        const bool inside = src >= 0 && src < L;
         if (src < 0) src = -src;
         if (src >= L) src = 2 * (L - 1) - src;
-        seg[i] = xs[src];
+        seg[i] = (zero_pad && !inside) ? 0.f : xs[src];
     }
     __syncthreads();
 
@@ -120,7 +122,11 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(const float* __restrict_
     float lsum = 0.f, lsq = 0.f;
     for (int i = threadIdx.x; i < p.bins_out * nfr; i += kThreads) {
         const int k = i / nfr, fr = i - k * nfr;
-        const float2 v = stage[k * FB + fr];
+        float2 v = stage[k * FB + fr];
+        if (p.flags & AERO_STFT_ADJ_SCALE) {          // adjoint of the C2R transform: interior bins count twice, DC / Nyquist are real
+            if (k == 0 || k == M) v.y = 0.f;
+            else { v.x *= 2.0f; v.y *= 2.0f; }
+        }
         *reinterpret_cast<float2*>(zs + (int64_t)k * p.z_stride_k + (int64_t)(t0 + fr) * p.z_stride_t) = v;
         lsum += v.x + v.y;
         lsq += v.x * v.x + v.y * v.y;
@@ -160,7 +166,8 @@ template <int LOGN>
 struct IstftCfg {
     static constexpr int N = 1 << LOGN;
     static constexpr int M = N / 2;
-    static constexpr int NF = (8192 / M) > 32 ? 32 : (8192 / M);       // frames resident per CTA (64 KB)
+    static constexpr int NF = (8192 / M) > 32 ? 32 : ((8192 / M) < 12 ? 12 : (8192 / M));   // frames resident per CTA (64 KB; >= 12 so that
+                                                                                             // n_fft 2048 / hop 240 of the MR-STFT loss fits)
 };
 
 template <int LOGN>
@@ -222,9 +229,10 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float* __restrict
     const int p0 = blk * OB * p.hop;
     const int span = OB * p.hop;
     float* ys = y + (int64_t)sig * p.out_len;
+    const bool raw = p.flags & AERO_ISTFT_RAW;                          // no centre trim, no envelope division (adjoint of the STFT)
     for (int i = threadIdx.x; i < span; i += kThreads) {
         const int pos = p0 + i;
-        const int n_out = pos - N / 2;
+        const int n_out = raw ? pos : pos - N / 2;
         if (n_out < 0 || n_out >= p.out_len) continue;
         int ta = (pos - N + p.hop) / p.hop;                             // ceil((pos-N+1)/hop) for pos-N+1 > 0
         if (pos - N + 1 <= 0) ta = 0;
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float* __restrict
             acc += frames[(t - t_lo) * N + n] * w;
             env += w * w;
         }
-        ys[n_out] = acc * scale / env;
+        ys[n_out] = raw ? acc * scale : acc * scale / env;
     }
 }
 
@@ -252,8 +260,12 @@ static int launch_istft(const float* z, const float* window, float* y, const aer
     }
     const size_t smem = sizeof(float2) * (C::NF * C::M + C::NF * (C::M + 1) + C::M) + sizeof(float) * C::N;
     cudaFuncSetAttribute(istft_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // padded positions that can produce output: [N/2, N/2 + out_len)
-    const int last_pos = C::N / 2 + p.out_len - 1;
+    if (smem > 227 * 1024) {
+        set_error("aero_istft_fwd: n_fft %d needs %zu bytes of shared memory", p.n_fft, smem);
+        return AERO_ERR_UNSUPPORTED;
+    }
+    // padded positions that can produce output: [N/2, N/2 + out_len)  (raw mode: [0, out_len))
+    const int last_pos = ((p.flags & AERO_ISTFT_RAW) ? 0 : C::N / 2) + p.out_len - 1;
     dim3 grid(last_pos / (OB * p.hop) + 1, p.n_signals);
     istft_kernel<LOGN><<<grid, kThreads, smem, st>>>(z, window, y, p, OB, halo);
     return check_launch("aero_istft_fwd");
@@ -546,14 +558,14 @@ extern "C" int aero_stft_fwd(const float* x, const float* window, float* z, doub
     const int lg = log2_exact(p->n_fft);
     AERO_REQUIRE(lg >= 6 && lg <= 12, "aero_stft_fwd: n_fft=%d must be a power of two in [64,4096]", p->n_fft);
     AERO_REQUIRE(p->win >= 1 && p->win <= p->n_fft && p->hop >= 1, "aero_stft_fwd: bad win/hop %d/%d", p->win, p->hop);
-    AERO_REQUIRE(p->length > p->n_fft / 2, "aero_stft_fwd: reflect padding needs length (%d) > n_fft/2", p->length);
+    AERO_REQUIRE((p->flags & AERO_STFT_ZERO_PAD) || p->length > p->n_fft / 2, "aero_stft_fwd: reflect padding needs length (%d) > n_fft/2", p->length);
     AERO_REQUIRE(p->frames == 1 + p->length / p->hop, "aero_stft_fwd: frames=%d != 1+length/hop", p->frames);
     AERO_REQUIRE(p->bins_out >= 1 && p->bins_out <= p->n_fft / 2 + 1, "aero_stft_fwd: bins_out=%d", p->bins_out);
     AERO_REQUIRE(p->n_signals >= 1 && p->channels >= 1 && p->n_signals % p->channels == 0, "aero_stft_fwd: signals/channels");
     AERO_REQUIRE(((p->z_stride_b | p->z_stride_c | p->z_stride_k | p->z_stride_t) & 1) == 0 && ((uintptr_t)z & 7) == 0,
                  "aero_stft_fwd: output strides must keep float2 alignment");
     cudaStream_t st = (cudaStream_t)stream;
-    if (lg == 9 && p->hop % 2 == 0 && (size_t)(kF512 - 1) * p->hop * 4 <= 96 * 1024) return launch_stft512(x, window, z, stats, *p, st);
+    if (lg == 9 && p->flags == 0 && p->hop % 2 == 0 && (size_t)(kF512 - 1) * p->hop * 4 <= 96 * 1024) return launch_stft512(x, window, z, stats, *p, st);
     switch (lg) {
         case 6: return launch_stft<6>(x, window, z, stats, *p, st);
         case 7: return launch_stft<7>(x, window, z, stats, *p, st);
@@ -573,12 +585,13 @@ extern "C" int aero_istft_fwd(const float* z, const float* window, float* y, con
     AERO_REQUIRE(lg >= 6 && lg <= 12, "aero_istft_fwd: n_fft=%d must be a power of two in [64,4096]", p->n_fft);
     AERO_REQUIRE(p->win >= 1 && p->win <= p->n_fft && p->hop >= 1, "aero_istft_fwd: bad win/hop");
     AERO_REQUIRE(p->bins_in >= 1 && p->bins_in <= p->n_fft / 2 + 1, "aero_istft_fwd: bins_in=%d", p->bins_in);
-    AERO_REQUIRE(p->out_len >= 1 && p->out_len <= p->hop * (p->frames - 1), "aero_istft_fwd: out_len=%d > hop*(frames-1)", p->out_len);
+    AERO_REQUIRE(p->out_len >= 1 && p->out_len <= p->hop * (p->frames - 1) + ((p->flags & AERO_ISTFT_RAW) ? p->n_fft : 0),
+                 "aero_istft_fwd: out_len=%d > hop*(frames-1)", p->out_len);
     AERO_REQUIRE(p->n_signals >= 1 && p->channels >= 1 && p->n_signals % p->channels == 0, "aero_istft_fwd: signals/channels");
     AERO_REQUIRE(((p->z_stride_b | p->z_stride_c | p->z_stride_k | p->z_stride_t) & 1) == 0 && ((uintptr_t)z & 7) == 0,
                  "aero_istft_fwd: input strides must keep float2 alignment");
     cudaStream_t st = (cudaStream_t)stream;
-    if (lg == 9) {
+    if (lg == 9 && p->flags == 0) {
         bool taken = false;
         const int rc = launch_istft512(z, window, y, *p, st, &taken);
         if (taken || rc != AERO_OK) return rc;

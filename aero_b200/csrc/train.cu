@@ -1,0 +1,669 @@
+// Training-side kernels of the AERO generator: weight gradients of the tap-GEMM, column
+// reductions (bias / BatchNorm statistics / embedding gradients), GroupNorm / BatchNorm + activation forward (training
+// form: nothing folded) and backward, fused multi-tensor Adam.  All fp32 (the training engine keeps fp32 storage: the
+// gradient-parity bar is 1e-3 against reference autograd).  Contracts: include/aero_b200.h, "Training".
+//
+// Data gradients of every convolution are NOT here: the adjoint of a tap-GEMM is a tap-GEMM (flipped taps, transposed
+// weights, conv <-> transposed conv), so dgrad runs on aero_tapgemm_fwd itself.
+#include "common.cuh"
+
+namespace aero {
+
+// ------------------------------------------------------------------------------------------------------------ wgrad
+// dW[slab][k][n] += sum over output pixels (b, fo, t) of  A(b, fi, t + dt, k) * dY(b, fo, t, n)
+// with (fi, dt, slab) the tap geometry of the forward (include/aero_b200.h, aero_tapgemm_fwd).  One CTA: a 128 (k) x 64 (n)
+// tile of one slab over a strided subset of 32-pixel chunks (consecutive t of one output row); partial sums are added
+// to dW with fp32 atomics (dW is zeroed by the caller).
+constexpr int kWgK = 128, kWgN = 64, kWgP = 32;
+
+struct WgradArgs {
+    const float* a1;
+    const float* a2;
+    const float* dy;
+    float* dw;
+    aero_tapgemm_params p;
+    int64_t dw_sn, dw_sk, dw_ss;      // element strides of dW along n, k, slab
+    int tiles_t, k_tiles, n_tiles, vec;
+};
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
+    __shared__ __align__(16) float Xs[kWgP][kWgK];
+    __shared__ __align__(16) float Ys[kWgP][kWgN];
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1 + p.C2;
+    const int kt_i = blockIdx.x % g.k_tiles, nt_i = blockIdx.x / g.k_tiles;
+    const int k0 = kt_i * kWgK, n0 = nt_i * kWgN;
+    const int slab = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;            // micro tile: k = ty*8 .. +7, n = tx*4 .. +3
+
+    // tap geometry of this slab
+    int jf = 0, dt = 0, conv_t_r = 0, conv_t_tap = 0;
+    if (p.mode == AERO_TAPS_CONV) {
+        jf = slab / p.kt;
+        dt = (slab - jf * p.kt) * p.dil_t - p.pad_t;
+    } else {
+        conv_t_r = slab % p.stride_f;
+        conv_t_tap = slab / p.stride_f;
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int64_t n_chunks = (int64_t)p.B * p.F_out * g.tiles_t;
+    for (int64_t ch = blockIdx.z; ch < n_chunks; ch += gridDim.z) {
+        const int tt = (int)(ch % g.tiles_t);
+        const int row = (int)(ch / g.tiles_t);
+        const int b = row / p.F_out, fo = row - b * p.F_out;
+        int fi;
+        if (p.mode == AERO_TAPS_CONV) {
+            fi = fo * p.stride_f + jf - p.pad_f;
+        } else {
+            const int fof = fo + p.f_out_offset;
+            if (fof % p.stride_f != conv_t_r) continue;
+            fi = fof / p.stride_f - conv_t_tap;
+        }
+        if (fi < 0 || fi >= p.F_in) continue;
+        const int t0 = tt * kWgP;
+        __syncthreads();
+        // ---- load the activation tile [32 pixels][128 channels] and the gradient tile [32][64]
+        for (int i = tid; i < kWgP * (kWgK / 4); i += 256) {
+            const int pp = i / (kWgK / 4), c4 = (i - pp * (kWgK / 4)) * 4;
+            const int t = t0 + pp, ti = t + dt;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < p.T && ti >= 0 && ti < p.T_in) {
+                const int kk = k0 + c4;
+                if (g.vec && kk + 3 < K) {
+                    const float* src = (kk < p.C1) ? g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)ti * p.a1_st + kk
+                                                   : g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (int64_t)ti * p.a2_st + (kk - p.C1);
+                    v = *reinterpret_cast<const float4*>(src);
+                } else {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int kq = kk + u;
+                        e[u] = 0.f;
+                        if (kq < K)
+                            e[u] = (kq < p.C1) ? g.a1[(int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)ti * p.a1_st + kq]
+                                               : g.a2[(int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (int64_t)ti * p.a2_st + (kq - p.C1)];
+                    }
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            *reinterpret_cast<float4*>(&Xs[pp][c4]) = v;
+        }
+        for (int i = tid; i < kWgP * (kWgN / 4); i += 256) {
+            const int pp = i / (kWgN / 4), c4 = (i - pp * (kWgN / 4)) * 4;
+            const int t = t0 + pp;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < p.T) {
+                const int nn = n0 + c4;
+                const float* src = g.dy + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st + nn;
+                if (g.vec && nn + 3 < p.N) {
+                    v = *reinterpret_cast<const float4*>(src);
+                } else {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = (nn + u < p.N) ? src[u] : 0.f;
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            *reinterpret_cast<float4*>(&Ys[pp][c4]) = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int pp = 0; pp < kWgP; ++pp) {
+            const float4 xa = *reinterpret_cast<const float4*>(&Xs[pp][ty * 8]);
+            const float4 xb = *reinterpret_cast<const float4*>(&Xs[pp][ty * 8 + 4]);
+            const float4 yv = *reinterpret_cast<const float4*>(&Ys[pp][tx * 4]);
+            const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ys[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int kk = k0 + ty * 8 + i;
+        if (kk >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nn = n0 + tx * 4 + j;
+            if (nn < p.N && acc[i][j] != 0.f)
+                atomicAdd(g.dw + (int64_t)nn * g.dw_sn + (int64_t)kk * g.dw_sk + (int64_t)slab * g.dw_ss, acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------ colsum
+// out1[seg][n] += sum_{o < n_outer, i < n_inner} x[seg*seg_sx + o*outer_s + i*inner_s + n]
+// out2[seg][n] += the same sum of x * z (z addressed like x); either output may be null.  OUT = float or double.
+template <typename OUT>
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, const float* __restrict__ z, OUT* out1, OUT* out2,
+                                                     int N, int64_t n_inner, int64_t inner_s, int64_t n_outer, int64_t outer_s,
+                                                     int64_t seg_sx, int64_t seg_so) {
+    __shared__ float s1[8][32], s2[8][32];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int seg = blockIdx.z;
+    const int64_t rows = n_inner * n_outer;
+    float a1 = 0.f, a2 = 0.f;
+    if (col < N) {
+        const float* xb = x + (int64_t)seg * seg_sx + col;
+        const float* zb = z ? z + (int64_t)seg * seg_sx + col : nullptr;
+        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
+            const int64_t o = r / n_inner, i = r - o * n_inner;
+            const int64_t off = o * outer_s + i * inner_s;
+            const float v = xb[off];
+            a1 += v;
+            if (zb) a2 = fmaf(v, zb[off], a2);
+        }
+    }
+    s1[threadIdx.y][threadIdx.x] = a1;
+    s2[threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < N) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t1 += s1[k][threadIdx.x]; t2 += s2[k][threadIdx.x]; }
+        if (out1) atomicAdd(out1 + (int64_t)seg * seg_so + col, (OUT)t1);
+        if (out2) atomicAdd(out2 + (int64_t)seg * seg_so + col, (OUT)t2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------ add
+__global__ void __launch_bounds__(256) add_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, float alpha) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 d = reinterpret_cast<float4*>(dst)[i];
+        const float4 s = reinterpret_cast<const float4*>(src)[i];
+        d.x = fmaf(alpha, s.x, d.x); d.y = fmaf(alpha, s.y, d.y); d.z = fmaf(alpha, s.z, d.z); d.w = fmaf(alpha, s.w, d.w);
+        reinterpret_cast<float4*>(dst)[i] = d;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) dst[i] = fmaf(alpha, src[i], dst[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------ norm + act (training)
+// y = act(norm(x)):  norm = GroupNorm (scope 1: per sample and channel group over all rows; scope 2: per (b, f) row, one
+// group), BatchNorm with batch statistics (scope 3: per channel over every pixel of the batch) or none (AERO_NA_NO_NORM).
+// act: AERO_NA_* of the inference kernel plus AERO_NA_RELU.  Thread mapping as in norm_act_kernel: a thread owns one quad
+// of OUTPUT channels and walks pixels.
+constexpr int kNaMaxGroups = 8;
+constexpr int kNaMaxC = 1536;
+
+struct NaConst {        // per-thread constants of its channel quad(s)
+    float m[4], r[4], ga[4], be[4];
+};
+
+__device__ __forceinline__ void na_load_const(NaConst& k, const aero_norm_act_params& p, const double* stats, const float* gamma,
+                                              const float* beta, int seg, int c) {
+    const bool nonorm = p.flags & AERO_NA_NO_NORM;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        k.m[u] = 0.f; k.r[u] = 1.f; k.ga[u] = 1.f; k.be[u] = 0.f;
+    }
+    if (nonorm) return;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        k.ga[u] = gamma[c + u];
+        k.be[u] = beta[c + u];
+        double n;
+        int64_t slot;
+        if (p.scope == 1) { n = (double)p.F_in * p.T * (p.C / p.groups); slot = (int64_t)seg * p.groups + (c + u) / (p.C / p.groups); }
+        else if (p.scope == 2) { n = (double)p.T * p.C; slot = seg; }
+        else { n = (double)p.B * p.F_in * p.T; slot = c + u; }
+        const double mean = stats[2 * slot] / n;
+        double var = stats[2 * slot + 1] / n - mean * mean;
+        if (var < 0) var = 0;
+        k.m[u] = (float)mean;
+        k.r[u] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+}
+
+// activation value and derivative pieces for one element.  For GLU the caller handles the pair.
+__device__ __forceinline__ float na_act(int op, float g, float al) {
+    if (op == AERO_NA_GELU) return gelu_exact(g);
+    if (op == AERO_NA_RELU) return fmaxf(g, 0.f);
+    if (op == AERO_NA_SNAKE) { const float sn = sinf(g * al); return g + sn * sn / al; }
+    return g;
+}
+__device__ __forceinline__ float na_dact(int op, float g, float al) {
+    if (op == AERO_NA_GELU) {
+        // d/dg [0.5 g (1 + erf(g/sqrt2))] = 0.5 (1 + erf(g/sqrt2)) + g * exp(-g^2/2) / sqrt(2 pi)
+        return 0.5f * (1.0f + erff(g * 0.70710678118654752440f)) + g * 0.3989422804014327f * expf(-0.5f * g * g);
+    }
+    if (op == AERO_NA_RELU) return g > 0.f ? 1.f : 0.f;
+    if (op == AERO_NA_SNAKE) { return 1.0f + sinf(2.0f * g * al); }          // 1 + 2 sin(ag) cos(ag)
+    return 1.f;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) na_train_fwd_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ snake_a, const float* __restrict__ scale,
+                                                           const float* __restrict__ residual, float* __restrict__ y,
+                                                           const aero_norm_act_params p) {
+    constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
+    const int seg = blockIdx.y;
+    const int Cout = GLU ? p.C / 2 : p.C;
+    const int c4n = Cout >> 2;
+    const int ppp = 256 / c4n;
+    const int cq = threadIdx.x % c4n, dp = threadIdx.x / c4n;
+    if (dp >= ppp) return;
+    const int c = cq * 4;
+    int b, f_lo, f_hi;
+    if (p.scope == 2) { b = seg / p.F_in; f_lo = seg % p.F_in; f_hi = f_lo + 1; } else { b = seg; f_lo = 0; f_hi = p.F_out; }
+    NaConst k0, k1;
+    na_load_const(k0, p, stats, gamma, beta, seg, c);
+    if (GLU) na_load_const(k1, p, stats, gamma, beta, seg, c + Cout);
+    float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    if (OP == AERO_NA_GLU_SCALE_RES) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sc[u] = scale[c + u];
+    }
+    const int64_t npix = (int64_t)(f_hi - f_lo) * p.T;
+    for (int64_t pix = (int64_t)blockIdx.x * ppp + dp; pix < npix; pix += (int64_t)gridDim.x * ppp) {
+        const int fl = f_lo + (int)(pix / p.T), t = (int)(pix % p.T);
+        const float* xp = x + (((int64_t)b * p.F_in + fl + p.f_off) * p.T + t) * p.C + c;
+        const int64_t oi = (((int64_t)b * p.F_out + fl) * p.T + t) * Cout + c;
+        const float4 v = *reinterpret_cast<const float4*>(xp);
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float o[4];
+        if (GLU) {
+            const float4 v2 = *reinterpret_cast<const float4*>(xp + Cout);
+            const float xw[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float ga = fmaf((xv[u] - k0.m[u]) * k0.r[u], k0.ga[u], k0.be[u]);
+                const float gb = fmaf((xw[u] - k1.m[u]) * k1.r[u], k1.ga[u], k1.be[u]);
+                o[u] = ga * sigmoid_f(gb);
+            }
+            if (OP == AERO_NA_GLU_SCALE_RES) {
+                const float4 rs = *reinterpret_cast<const float4*>(residual + oi);
+                o[0] = fmaf(sc[0], o[0], rs.x); o[1] = fmaf(sc[1], o[1], rs.y); o[2] = fmaf(sc[2], o[2], rs.z); o[3] = fmaf(sc[3], o[3], rs.w);
+            }
+        } else {
+            const float al = (OP == AERO_NA_SNAKE) ? snake_a[fl + p.f_off] : 1.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = na_act(OP, fmaf((xv[u] - k0.m[u]) * k0.r[u], k0.ga[u], k0.be[u]), al);
+        }
+        *reinterpret_cast<float4*>(y + oi) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Backward, pass 1 (APPLY = false): accumulates  dgamma[c] += sum dg * xh,  dbeta[c] += sum dg,  dscale[c] += sum dy * glu,
+// dsnake[f] += sum dy * d act / d a,  and the per-(segment, group) sums  ws[slot] += {sum dxh, sum dxh * xh}  (dxh = dg * gamma)
+// that the GroupNorm backward needs (scope 1 / 2; BatchNorm derives them from dgamma / dbeta).
+// Pass 2 (APPLY = true):  dx = rstd * (dxh - S1/n - xh * S2/n)   (no norm: dx = dg) for every input row (rows outside the
+// crop [f_off, f_off + F_out) have dy = 0 but still receive the mean terms).
+template <int OP, bool APPLY>
+__global__ void __launch_bounds__(256) na_train_bwd_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ snake_a, const float* __restrict__ scale,
+                                                           const float* __restrict__ dy, float* __restrict__ dx,
+                                                           float* dgamma, float* dbeta, float* dscale, float* dsnake, double* ws,
+                                                           const aero_norm_act_params p) {
+    constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
+    __shared__ float s_dg[APPLY ? 1 : kNaMaxC], s_db[APPLY ? 1 : kNaMaxC], s_ds[APPLY ? 1 : kNaMaxC / 2];
+    __shared__ double s_grp[kNaMaxGroups][2];
+    __shared__ float s_da;
+    const bool nonorm = p.flags & AERO_NA_NO_NORM;
+    const int seg = blockIdx.y;
+    const int Cout = GLU ? p.C / 2 : p.C;
+    const int c4n = Cout >> 2;
+    const int ppp = 256 / c4n;
+    const int cq = threadIdx.x % c4n, dp = threadIdx.x / c4n;
+    if (!APPLY) {
+        for (int i = threadIdx.x; i < p.C; i += 256) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+        for (int i = threadIdx.x; i < Cout; i += 256) s_ds[i] = 0.f;
+        if (threadIdx.x < kNaMaxGroups) { s_grp[threadIdx.x][0] = 0.0; s_grp[threadIdx.x][1] = 0.0; }
+        if (threadIdx.x == 0) s_da = 0.f;
+        __syncthreads();
+    }
+    const bool active = dp < ppp;
+    const int c = cq * 4;
+    int b, f_lo, f_hi;                  // INPUT rows covered by this segment
+    if (p.scope == 2) { b = seg / p.F_in; f_lo = seg % p.F_in; f_hi = f_lo + 1; } else { b = seg; f_lo = 0; f_hi = p.F_in; }
+    NaConst k0, k1;
+    float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    float m1a[4] = {0.f, 0.f, 0.f, 0.f}, m2a[4] = {0.f, 0.f, 0.f, 0.f}, m1b[4] = {0.f, 0.f, 0.f, 0.f}, m2b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        na_load_const(k0, p, stats, gamma, beta, seg, c);
+        if (GLU) na_load_const(k1, p, stats, gamma, beta, seg, c + Cout);
+        if (OP == AERO_NA_GLU_SCALE_RES) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sc[u] = scale[c + u];
+        }
+        if (APPLY && !nonorm) {
+            // means of dxh and dxh * xh over the normalisation set of each channel
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (p.scope == 3) {
+                    const double n = (double)p.B * p.F_in * p.T;
+                    m1a[u] = (float)((double)k0.ga[u] * dbeta[c + u] / n);
+                    m2a[u] = (float)((double)k0.ga[u] * dgamma[c + u] / n);
+                    if (GLU) {
+                        m1b[u] = (float)((double)k1.ga[u] * dbeta[c + Cout + u] / n);
+                        m2b[u] = (float)((double)k1.ga[u] * dgamma[c + Cout + u] / n);
+                    }
+                } else {
+                    const int gw = p.C / p.groups;
+                    const double n = (p.scope == 1) ? (double)p.F_in * p.T * gw : (double)p.T * p.C;
+                    const int64_t sa = (p.scope == 1) ? (int64_t)seg * p.groups + (c + u) / gw : seg;
+                    m1a[u] = (float)(ws[2 * sa] / n);
+                    m2a[u] = (float)(ws[2 * sa + 1] / n);
+                    if (GLU) {
+                        const int64_t sb = (p.scope == 1) ? (int64_t)seg * p.groups + (c + Cout + u) / gw : seg;
+                        m1b[u] = (float)(ws[2 * sb] / n);
+                        m2b[u] = (float)(ws[2 * sb + 1] / n);
+                    }
+                }
+            }
+        }
+    }
+    float adg[4] = {0.f, 0.f, 0.f, 0.f}, adb[4] = {0.f, 0.f, 0.f, 0.f}, bdg[4] = {0.f, 0.f, 0.f, 0.f}, bdb[4] = {0.f, 0.f, 0.f, 0.f};
+    float ads[4] = {0.f, 0.f, 0.f, 0.f};
+    double g1a = 0.0, g2a = 0.0, g1b = 0.0, g2b = 0.0;
+    float da_acc = 0.f;
+    const int64_t npix = (int64_t)(f_hi - f_lo) * p.T;
+    if (active)
+    for (int64_t pix = (int64_t)blockIdx.x * ppp + dp; pix < npix; pix += (int64_t)gridDim.x * ppp) {
+        const int fin = f_lo + (int)(pix / p.T), t = (int)(pix % p.T);
+        const int fout = fin - p.f_off;
+        const bool has_dy = fout >= 0 && fout < p.F_out;
+        if (!APPLY && !has_dy) continue;
+        const int64_t xi = (((int64_t)b * p.F_in + fin) * p.T + t) * p.C + c;
+        const float4 v = *reinterpret_cast<const float4*>(x + xi);
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float dyv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_dy) {
+            const float4 d = *reinterpret_cast<const float4*>(dy + (((int64_t)b * p.F_out + fout) * p.T + t) * Cout + c);
+            dyv[0] = d.x; dyv[1] = d.y; dyv[2] = d.z; dyv[3] = d.w;
+        }
+        float xha[4], dga[4], xhb[4], dgb[4];
+        if (GLU) {
+            const float4 v2 = *reinterpret_cast<const float4*>(x + xi + Cout);
+            const float xw[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                xha[u] = (xv[u] - k0.m[u]) * k0.r[u];
+                xhb[u] = (xw[u] - k1.m[u]) * k1.r[u];
+                const float ga = fmaf(xha[u], k0.ga[u], k0.be[u]), gb = fmaf(xhb[u], k1.ga[u], k1.be[u]);
+                const float sg = sigmoid_f(gb);
+                const float de = dyv[u] * sc[u];
+                dga[u] = de * sg;
+                dgb[u] = de * ga * sg * (1.0f - sg);
+                if (!APPLY && OP == AERO_NA_GLU_SCALE_RES) ads[u] = fmaf(dyv[u], ga * sg, ads[u]);
+            }
+        } else {
+            const float al = (OP == AERO_NA_SNAKE) ? snake_a[fin] : 1.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                xha[u] = (xv[u] - k0.m[u]) * k0.r[u];
+                const float ga = fmaf(xha[u], k0.ga[u], k0.be[u]);
+                dga[u] = dyv[u] * na_dact(OP, ga, al);
+                if (!APPLY && OP == AERO_NA_SNAKE) {
+                    // d/da [g + sin^2(a g) / a] = g sin(2 a g) / a - sin^2(a g) / a^2
+                    const float sn = sinf(al * ga);
+                    da_acc = fmaf(dyv[u], ga * sinf(2.0f * al * ga) / al - sn * sn / (al * al), da_acc);
+                }
+            }
+        }
+        if (!APPLY) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                adb[u] += dga[u];
+                adg[u] = fmaf(dga[u], xha[u], adg[u]);
+                const float dxh = dga[u] * k0.ga[u];
+                g1a += dxh;
+                g2a += dxh * xha[u];
+                if (GLU) {
+                    bdb[u] += dgb[u];
+                    bdg[u] = fmaf(dgb[u], xhb[u], bdg[u]);
+                    const float dxb = dgb[u] * k1.ga[u];
+                    g1b += dxb;
+                    g2b += dxb * xhb[u];
+                }
+            }
+        } else {
+            float o[4], o2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nonorm) {
+                    o[u] = dga[u];
+                    if (GLU) o2[u] = dgb[u];
+                } else {
+                    o[u] = k0.r[u] * (dga[u] * k0.ga[u] - m1a[u] - xha[u] * m2a[u]);
+                    if (GLU) o2[u] = k1.r[u] * (dgb[u] * k1.ga[u] - m1b[u] - xhb[u] * m2b[u]);
+                }
+            }
+            *reinterpret_cast<float4*>(dx + xi) = make_float4(o[0], o[1], o[2], o[3]);
+            if (GLU) *reinterpret_cast<float4*>(dx + xi + Cout) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        }
+    }
+    if (APPLY) return;
+    if (active) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            atomicAdd(&s_dg[c + u], adg[u]);
+            atomicAdd(&s_db[c + u], adb[u]);
+            if (GLU) { atomicAdd(&s_dg[c + Cout + u], bdg[u]); atomicAdd(&s_db[c + Cout + u], bdb[u]); }
+            if (OP == AERO_NA_GLU_SCALE_RES) atomicAdd(&s_ds[c + u], ads[u]);
+        }
+        if (!nonorm && p.scope != 3) {
+            const int gw = p.C / p.groups;
+            const int ga_i = (p.scope == 1) ? c / gw : 0;
+            atomicAdd(&s_grp[ga_i][0], g1a);
+            atomicAdd(&s_grp[ga_i][1], g2a);
+            if (GLU) {
+                const int gb_i = (p.scope == 1) ? (c + Cout) / gw : 0;
+                atomicAdd(&s_grp[gb_i][0], g1b);
+                atomicAdd(&s_grp[gb_i][1], g2b);
+            }
+        }
+        if (OP == AERO_NA_SNAKE) atomicAdd(&s_da, da_acc);
+    }
+    __syncthreads();
+    if (!nonorm) {
+        for (int i = threadIdx.x; i < p.C; i += 256) {
+            if (s_dg[i] != 0.f) atomicAdd(dgamma + i, s_dg[i]);
+            if (s_db[i] != 0.f) atomicAdd(dbeta + i, s_db[i]);
+        }
+        if (p.scope != 3 && threadIdx.x < p.groups) {
+            const int64_t slot = (p.scope == 1) ? (int64_t)seg * p.groups + threadIdx.x : seg;
+            atomicAdd(ws + 2 * slot, s_grp[threadIdx.x][0]);
+            atomicAdd(ws + 2 * slot + 1, s_grp[threadIdx.x][1]);
+        }
+    }
+    if (OP == AERO_NA_GLU_SCALE_RES)
+        for (int i = threadIdx.x; i < Cout; i += 256)
+            if (s_ds[i] != 0.f) atomicAdd(dscale + i, s_ds[i]);
+    if (OP == AERO_NA_SNAKE && threadIdx.x == 0 && s_da != 0.f) atomicAdd(dsnake + f_lo, s_da);
+}
+
+// ------------------------------------------------------------------------------------------------------------ Adam
+// One launch for every parameter tensor: chunk table [n_chunks] of {param, grad, exp_avg, exp_avg_sq, count}.
+// torch.optim.Adam semantics (no amsgrad, no weight decay): m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+// p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps).
+struct AdamChunk {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float grad_scale) {
+    const AdamChunk ch = chunks[blockIdx.x];
+    const float step = lr / bc1;
+    for (int64_t i = threadIdx.x; i < ch.n; i += 256) {
+        const float g = ch.g[i] * grad_scale;
+        const float m = fmaf(b1, ch.m[i], (1.0f - b1) * g);
+        const float v = fmaf(b2, ch.v[i], (1.0f - b2) * g * g);
+        ch.m[i] = m;
+        ch.v[i] = v;
+        ch.p[i] -= step * m / (sqrtf(v) / bc2_sqrt + eps);
+    }
+}
+
+}  // namespace aero
+
+// ================================================================================================================ C ABI
+extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float* dy, float* dw, const aero_tapgemm_params* p,
+                                  int64_t dw_sn, int64_t dw_sk, int64_t dw_ss, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(dy && dw && p && (a1 || a2), "aero_tapgemm_wgrad: null argument");
+    AERO_REQUIRE(p->mode == AERO_TAPS_CONV || p->mode == AERO_TAPS_CONVT, "aero_tapgemm_wgrad: mode %d", p->mode);
+    AERO_REQUIRE((p->C1 == 0 || a1) && (p->C2 == 0 || a2) && p->C1 + p->C2 >= 1 && p->N >= 1, "aero_tapgemm_wgrad: channels");
+    AERO_REQUIRE(p->mode != AERO_TAPS_CONVT || (p->kt == 1 && p->kf % p->stride_f == 0), "aero_tapgemm_wgrad: transposed-conv geometry");
+    WgradArgs g;
+    g.a1 = a1; g.a2 = a2; g.dy = dy; g.dw = dw; g.p = *p;
+    g.dw_sn = dw_sn; g.dw_sk = dw_sk; g.dw_ss = dw_ss;
+    const int K = p->C1 + p->C2;
+    g.tiles_t = cdiv(p->T, kWgP);
+    g.k_tiles = cdiv(K, kWgK);
+    g.n_tiles = cdiv(p->N, kWgN);
+    auto al4 = [](int64_t v) { return (v & 3) == 0; };
+    g.vec = (p->C1 % 4 == 0) && (p->C2 % 4 == 0) && (p->N % 4 == 0) && al4(p->a1_sb) && al4(p->a1_sf) && al4(p->a1_st) && al4(p->a2_sb) &&
+            al4(p->a2_sf) && al4(p->a2_st) && al4(p->o_sb) && al4(p->o_sf) && al4(p->o_st) &&
+            ((((uintptr_t)a1 | (uintptr_t)a2 | (uintptr_t)dy) & 15) == 0);
+    const int nslab = (p->mode == AERO_TAPS_CONVT) ? p->kf : p->kf * p->kt;
+    const int64_t n_chunks = (int64_t)p->B * p->F_out * g.tiles_t;
+    // enough CTAs to fill the GPU a few times over, never more than chunks
+    int64_t tiles = (int64_t)g.k_tiles * g.n_tiles * nslab;
+    int64_t splits = (148 * 6 + tiles - 1) / tiles;
+    if (splits > n_chunks) splits = n_chunks;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    AERO_REQUIRE(nslab <= 65535, "aero_tapgemm_wgrad: too many taps");
+    dim3 grid((unsigned)(g.k_tiles * g.n_tiles), (unsigned)nslab, (unsigned)splits);
+    wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+    return check_launch("aero_tapgemm_wgrad");
+}
+
+extern "C" int aero_colsum(const float* x, const float* z, void* out1, void* out2, int32_t out_double, int32_t N, int64_t n_inner,
+                           int64_t inner_stride, int64_t n_outer, int64_t outer_stride, int32_t n_seg, int64_t seg_stride_x,
+                           int64_t seg_stride_out, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && (out1 || out2) && N >= 1 && n_inner >= 1 && n_outer >= 1 && n_seg >= 1 && n_seg <= 65535, "aero_colsum: bad argument");
+    const int64_t rows = n_inner * n_outer;
+    int64_t ysplit = (rows + 8 * 64 - 1) / (8 * 64);
+    const int64_t cap = (int64_t)148 * 16 / (cdiv(N, 32) * (int64_t)n_seg) + 1;
+    if (ysplit > cap) ysplit = cap;
+    if (ysplit < 1) ysplit = 1;
+    if (ysplit > 65535) ysplit = 65535;
+    dim3 grid((unsigned)cdiv(N, 32), (unsigned)ysplit, (unsigned)n_seg), block(32, 8);
+    if (out_double)
+        colsum_kernel<double><<<grid, block, 0, (cudaStream_t)stream>>>(x, z, (double*)out1, (double*)out2, N, n_inner, inner_stride, n_outer,
+                                                                       outer_stride, seg_stride_x, seg_stride_out);
+    else
+        colsum_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, z, (float*)out1, (float*)out2, N, n_inner, inner_stride, n_outer,
+                                                                      outer_stride, seg_stride_x, seg_stride_out);
+    return check_launch("aero_colsum");
+}
+
+extern "C" int aero_add(float* dst, const float* src, int64_t n, float alpha, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(dst && src && n >= 0 && ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0), "aero_add: bad argument");
+    if (n == 0) return AERO_OK;
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n, alpha);
+    return check_launch("aero_add");
+}
+
+static int na_train_check(const aero_norm_act_params* p) {
+    using namespace aero;
+    AERO_REQUIRE(p->scope >= 1 && p->scope <= 3, "aero_norm_act_train: scope=%d", p->scope);
+    const bool glu = (p->op == AERO_NA_GLU || p->op == AERO_NA_GLU_SCALE_RES);
+    const int Cout = glu ? p->C / 2 : p->C;
+    AERO_REQUIRE(p->C % 4 == 0 && Cout % 4 == 0 && Cout / 4 <= 256 && p->C <= kNaMaxC, "aero_norm_act_train: C=%d", p->C);
+    const bool nonorm = p->flags & AERO_NA_NO_NORM;
+    AERO_REQUIRE(nonorm || p->scope != 1 || (p->groups >= 1 && p->groups <= kNaMaxGroups && p->C % p->groups == 0), "aero_norm_act_train: groups");
+    AERO_REQUIRE(p->scope == 1 || (p->f_off == 0 && p->F_in == p->F_out), "aero_norm_act_train: crop needs scope 1");
+    AERO_REQUIRE(p->f_off >= 0 && p->f_off + p->F_out <= p->F_in, "aero_norm_act_train: crop out of range");
+    AERO_REQUIRE(p->op != AERO_NA_SNAKE || p->scope == 2, "aero_norm_act_train: snake needs the per-row scope");
+    return AERO_OK;
+}
+
+static dim3 na_train_grid(const aero_norm_act_params* p, bool input_rows) {
+    const bool glu = (p->op == AERO_NA_GLU || p->op == AERO_NA_GLU_SCALE_RES);
+    const int Cout = glu ? p->C / 2 : p->C;
+    const int ppp = 256 / (Cout / 4);
+    const int rows = input_rows ? p->F_in : p->F_out;
+    const int64_t npix = (p->scope == 2) ? (int64_t)p->T : (int64_t)rows * p->T;
+    const int nseg = (p->scope == 2) ? p->B * p->F_in : p->B;
+    int chunks = (int)((npix + (int64_t)ppp * 8 - 1) / ((int64_t)ppp * 8));
+    if (chunks < 1) chunks = 1;
+    return dim3((unsigned)chunks, (unsigned)nseg);
+}
+
+extern "C" int aero_norm_act_train_fwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
+                                       const float* scale, const float* residual, float* y, const aero_norm_act_params* p,
+                                       aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && y && p, "aero_norm_act_train_fwd: null argument");
+    int rc = na_train_check(p);
+    if (rc != AERO_OK) return rc;
+    AERO_REQUIRE((p->flags & AERO_NA_NO_NORM) || (stats && gamma && beta), "aero_norm_act_train_fwd: statistics / affine missing");
+    const dim3 grid = na_train_grid(p, false);
+    AERO_REQUIRE(grid.y <= 65535, "aero_norm_act_train_fwd: too many segments");
+    cudaStream_t st = (cudaStream_t)stream;
+#define AERO_NAT(OP) na_train_fwd_kernel<OP><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, residual, y, *p)
+    switch (p->op) {
+        case AERO_NA_NONE: AERO_NAT(AERO_NA_NONE); break;
+        case AERO_NA_GELU: AERO_NAT(AERO_NA_GELU); break;
+        case AERO_NA_GLU: AERO_NAT(AERO_NA_GLU); break;
+        case AERO_NA_SNAKE: AERO_NAT(AERO_NA_SNAKE); break;
+        case AERO_NA_GLU_SCALE_RES: AERO_NAT(AERO_NA_GLU_SCALE_RES); break;
+        case AERO_NA_RELU: AERO_NAT(AERO_NA_RELU); break;
+        default: set_error("aero_norm_act_train_fwd: op=%d", p->op); return AERO_ERR_INVALID;
+    }
+#undef AERO_NAT
+    return check_launch("aero_norm_act_train_fwd");
+}
+
+extern "C" int aero_norm_act_train_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
+                                       const float* scale, const float* dy, float* dx, float* dgamma, float* dbeta, float* dscale,
+                                       float* dsnake, double* ws, int32_t pass, const aero_norm_act_params* p, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && dy && p && (pass == 1 || pass == 2), "aero_norm_act_train_bwd: null argument");
+    int rc = na_train_check(p);
+    if (rc != AERO_OK) return rc;
+    const bool nonorm = p->flags & AERO_NA_NO_NORM;
+    AERO_REQUIRE(nonorm || (stats && gamma && beta && dgamma && dbeta && (p->scope == 3 || ws)), "aero_norm_act_train_bwd: missing buffers");
+    AERO_REQUIRE(pass == 1 || dx, "aero_norm_act_train_bwd: dx missing");
+    const dim3 grid = na_train_grid(p, true);
+    AERO_REQUIRE(grid.y <= 65535, "aero_norm_act_train_bwd: too many segments");
+    cudaStream_t st = (cudaStream_t)stream;
+#define AERO_NAB(OP)                                                                                                                    \
+    if (pass == 1) na_train_bwd_kernel<OP, false><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, dy, dx, dgamma, dbeta, dscale, dsnake, ws, *p); \
+    else na_train_bwd_kernel<OP, true><<<grid, 256, 0, st>>>(x, stats, gamma, beta, snake_a, scale, dy, dx, dgamma, dbeta, dscale, dsnake, ws, *p)
+    switch (p->op) {
+        case AERO_NA_NONE: AERO_NAB(AERO_NA_NONE); break;
+        case AERO_NA_GELU: AERO_NAB(AERO_NA_GELU); break;
+        case AERO_NA_GLU: AERO_NAB(AERO_NA_GLU); break;
+        case AERO_NA_SNAKE: AERO_NAB(AERO_NA_SNAKE); break;
+        case AERO_NA_GLU_SCALE_RES: AERO_NAB(AERO_NA_GLU_SCALE_RES); break;
+        case AERO_NA_RELU: AERO_NAB(AERO_NA_RELU); break;
+        default: set_error("aero_norm_act_train_bwd: op=%d", p->op); return AERO_ERR_INVALID;
+    }
+#undef AERO_NAB
+    return check_launch("aero_norm_act_train_bwd");
+}
+
+extern "C" int aero_adam_step(const void* chunk_table, int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step,
+                              float grad_scale, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(chunk_table && n_chunks >= 1 && step >= 1, "aero_adam_step: bad argument");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(static_cast<const AdamChunk*>(chunk_table), lr, beta1, beta2, eps, (float)bc1,
+                                                                     (float)sqrt(bc2), grad_scale);
+    return check_launch("aero_adam_step");
+}

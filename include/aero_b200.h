@@ -38,7 +38,7 @@ enum aero_status {
     AERO_ERR_NO_DEVICE = -4
 };
 
-int aero_abi_version(void);            /* 2: storage-type flags (AERO_TG_*), precision 2 */
+int aero_abi_version(void);            /* 3: training entry points */
 const char* aero_last_error(void);
 /* compute capability of the current device as 10*major+minor (100 on B200); <0 if no device */
 int aero_device_arch(void);
@@ -63,7 +63,14 @@ typedef struct {
     int32_t n_signals, channels;
     int32_t length, frames, bins_out;
     int64_t z_stride_b, z_stride_c, z_stride_k, z_stride_t;
+    int32_t flags;                    /* 0, or AERO_STFT_* (training: this kernel is also the adjoint of the iSTFT) */
+    int32_t reserved;
 } aero_stft_params;
+enum {
+    AERO_STFT_ZERO_PAD = 1,           /* samples outside [0, length) are zero instead of reflected */
+    AERO_STFT_ADJ_SCALE = 2           /* bins 1 .. n_fft/2-1 are doubled and the imaginary parts of DC / Nyquist zeroed: with ZERO_PAD and
+                                         x = dy / envelope (zero-extended to hop*(frames-1)) this is dL/dz of aero_istft_fwd */
+};
 int aero_stft_fwd(const float* x, const float* window, float* z, double* stats,
                   const aero_stft_params* p, aero_stream_t stream);
 
@@ -79,7 +86,14 @@ typedef struct {
     int32_t n_signals, channels;
     int32_t frames, bins_in, out_len;
     int64_t z_stride_b, z_stride_c, z_stride_k, z_stride_t;
+    int32_t flags;                    /* 0, or AERO_ISTFT_RAW */
+    int32_t reserved;
 } aero_istft_params;
+enum {
+    AERO_ISTFT_RAW = 1                /* y[pos] = OLA(irfft(z * sqrt(n_fft)) * window)[pos], pos < out_len <= hop*(frames-1) + n_fft: no centre
+                                         trim and no envelope division.  Applied to dL/dz with the interior bins halved this is the
+                                         gradient of the reflect-PADDED input of aero_stft_fwd (the caller folds the padding back). */
+};
 int aero_istft_fwd(const float* z, const float* window, float* y,
                    const aero_istft_params* p, aero_stream_t stream);
 
@@ -169,7 +183,9 @@ int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* s
  *     AERO_NA_SNAKE y = g + sin(a[f]*g)^2 / a[f];
  *     AERO_NA_GLU_SCALE_RES y[c] = residual[c] + scale[c] * glu(g)[c].
  */
-enum { AERO_NA_NONE = 0, AERO_NA_GELU = 1, AERO_NA_GLU = 2, AERO_NA_SNAKE = 3, AERO_NA_GLU_SCALE_RES = 4 };
+enum { AERO_NA_NONE = 0, AERO_NA_GELU = 1, AERO_NA_GLU = 2, AERO_NA_SNAKE = 3, AERO_NA_GLU_SCALE_RES = 4,
+       AERO_NA_RELU = 5 /* training entry points only */ };
+enum { AERO_NA_NO_NORM = 16 };      /* aero_norm_act_params.flags, training entry points: skip the normalisation (activation only) */
 typedef struct {
     int32_t B, F_in, F_out, f_off, T, C;
     int32_t groups, scope, op;
@@ -277,6 +293,77 @@ int aero_lsd_fwd(const float* z_ref, const float* z_est, double* out_sum, int32_
  */
 int aero_stft_loss_fwd(const float* z_est, const float* z_ref, double* sums, int32_t B, int32_t bins, int32_t frames,
                        int32_t n_fft, aero_stream_t stream);
+
+/* ==========================================================================================
+ * Training (backward of the custom ops + fused Adam; reference callers src/solver.py:292-342,
+ * 602-605 `loss.backward(); optimizer.step()`, train.py:83 `torch.optim.Adam`).  All tensors fp32.
+ *
+ * Data gradients of every convolution / linear layer run on aero_tapgemm_fwd itself: the adjoint of a tap-GEMM is a
+ * tap-GEMM (taps flipped, weights transposed, AERO_TAPS_CONV <-> AERO_TAPS_CONVT for strided layers).
+ * ========================================================================================== */
+
+/* Weight gradient of a tap-GEMM:  dW(n, k, slab) += sum_{b,fo,t} A(b, fi, ti, k) * dY(b, fo, t, n)  with (fi, ti, slab) the tap
+ * geometry of aero_tapgemm_fwd for `p` (mode AERO_TAPS_CONV or AERO_TAPS_CONVT; A = channel concat of a1, a2).  dY is addressed
+ * with p->o_sb / o_sf / o_st; element (n, k, slab) of dW lives at dw + n*dw_sn + k*dw_sk + slab*dw_ss (so the gradient can be
+ * written straight into PyTorch's [N][K][kf][kt] or ConvTranspose [K][N][kf][1] parameter layout).  The caller zeroes dW.
+ * Replaces the cuDNN wgrad kernels behind autograd of nn.Conv2d / ConvTranspose2d / Conv1d / Linear. */
+int aero_tapgemm_wgrad(const float* a1, const float* a2, const float* dy, float* dw, const aero_tapgemm_params* p,
+                       int64_t dw_sn, int64_t dw_sk, int64_t dw_ss, aero_stream_t stream);
+
+/* Column sums:  out1[seg][n] += sum_{o < n_outer, i < n_inner} x[seg*seg_stride_x + o*outer_stride + i*inner_stride + n],
+ * out2[seg][n] += the same sum of x * z (z addressed like x; NULL: skipped).  out_double: outputs are fp64 (statistics) else fp32.
+ * Bias gradients, BatchNorm batch statistics (z = x), frequency-embedding gradients.  The caller zeroes the outputs. */
+int aero_colsum(const float* x, const float* z, void* out1, void* out2, int32_t out_double, int32_t N, int64_t n_inner,
+                int64_t inner_stride, int64_t n_outer, int64_t outer_stride, int32_t n_seg, int64_t seg_stride_x,
+                int64_t seg_stride_out, aero_stream_t stream);
+
+/* dst[i] += alpha * src[i] (gradient accumulation where a tensor has several consumers). */
+int aero_add(float* dst, const float* src, int64_t n, float alpha, aero_stream_t stream);
+
+/* Normalisation + activation, training form (nothing folded, fp32): y = act(norm(x)) with
+ *   scope 1 / 2: GroupNorm as in aero_norm_act_fwd;  scope 3: BatchNorm with BATCH statistics, stats = [C][2] fp64 {sum, sumsq}
+ *   over all B*F_in*T pixels (reference modules.py:287-300 in train mode);  flags & AERO_NA_NO_NORM: activation only.
+ * ops: AERO_NA_* (SNAKE needs scope 2).  x [B][F_in][T][C], y [B][F_out][T][C or C/2]. */
+int aero_norm_act_train_fwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
+                            const float* scale, const float* residual, float* y, const aero_norm_act_params* p,
+                            aero_stream_t stream);
+/* Backward of the above.  pass 1 accumulates dgamma[C], dbeta[C], dscale[C/2] (GLU_SCALE_RES), dsnake[F_in] (SNAKE) and the
+ * per-(segment, group) sums ws[slot] = {sum dxh, sum dxh*xh} (fp64, same slots as `stats`; unused for scope 3);
+ * pass 2 writes dx[B][F_in][T][C] = rstd * (dxh - mean(dxh) - xh * mean(dxh * xh)) (every input row, cropped rows included).
+ * The gradient of the residual input of GLU_SCALE_RES is dy itself (the caller accumulates it).  The caller zeroes the
+ * accumulators before pass 1. */
+int aero_norm_act_train_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
+                            const float* scale, const float* dy, float* dx, float* dgamma, float* dbeta, float* dscale,
+                            float* dsnake, double* ws, int32_t pass, const aero_norm_act_params* p, aero_stream_t stream);
+
+/* LSTM layer, training form (fp32 SIMT recurrence; reference modules.py:28-65 under autograd, i.e. cuDNN's RNN training
+ * forward and backward-data).  Forward = aero_lstm_rec_fwd (precision 0) that also saves, WINDOWED as [rows*n_win][steps][2][..],
+ * the post-activation gates (i,f,g,o: 4H), the cell state c (H) and the hidden state h (H) of every step; hout is the
+ * de-windowed output (may be NULL when out_windowed: h_s is that output).
+ * Backward: dhout in the layout of the forward's output (windowed [n_seq][steps][2H] or de-windowed [rows][T][2H]);
+ * dgin_w = gradient of the gate pre-activations, windowed [n_seq][steps][2][4H] (every position, padding frames included).
+ * The caller finishes with GEMMs over dgin_w: bias = column sums, W_hh = aero_tapgemm_wgrad against h_s shifted by one step,
+ * W_ih / input gradient from dgin (aero_lstm_fold sums the windowed rows back onto un-windowed frames for the first layer). */
+int aero_lstm_train_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout, float* gates_s, float* c_s,
+                        float* h_s, const aero_lstm_params* p, aero_stream_t stream);
+int aero_lstm_bwd(const float* dhout, const float* gates_s, const float* c_s, const float* whh, float* dgin_w,
+                  const aero_lstm_params* p, aero_stream_t stream);
+int aero_lstm_fold(const float* dgin_w, float* dgin, int32_t rows, int32_t T, int32_t n_win, int32_t steps, int32_t win_stride,
+                   int32_t C, aero_stream_t stream);
+
+/* LocalState attention, training form (reference modules.py:104-124 under autograd): exact-fp32 forward that also returns
+ * lse[rows][heads][T] (log-sum-exp over keys per query), and the backward: dqkvd[rows][T][ld] (q | k | v | decay-logit columns,
+ * every column written) from dout[rows][T][H]; scores are recomputed flash-style (no T x T tensor). */
+int aero_local_attn_train_fwd(const float* qkvd, float* out, float* lse, const aero_attn_params* p, aero_stream_t stream);
+int aero_local_attn_bwd(const float* qkvd, const float* out, const float* lse, const float* dout, float* dqkvd,
+                        const aero_attn_params* p, aero_stream_t stream);
+
+/* Fused multi-tensor Adam (torch.optim.Adam semantics, no amsgrad / weight decay; reference train.py:83).  chunk_table: device
+ * array of n_chunks records {float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64 count}; one CTA per
+ * record.  step >= 1 is the step count AFTER this update (bias corrections 1 - beta^step); grad_scale multiplies every
+ * gradient (1/world_size after a sum all-reduce). */
+int aero_adam_step(const void* chunk_table, int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step,
+                   float grad_scale, aero_stream_t stream);
 
 #ifdef __cplusplus
 }

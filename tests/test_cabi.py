@@ -36,7 +36,7 @@ def test_no_torch_types_in_abi():
 
 
 def test_version_and_error_channel(lib):
-    assert lib.aero_abi_version() == 2
+    assert lib.aero_abi_version() == 3
     # parameter validation happens before any device work: a null call must fail cleanly
     rc = lib.aero_stft_fwd(None, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.aero_last_error()
@@ -44,8 +44,8 @@ def test_version_and_error_channel(lib):
 
 def test_struct_sizes_match_header(lib):
     import ctypes
-    assert ctypes.sizeof(cabi.StftParams) == 8 * 4 + 4 * 8
-    assert ctypes.sizeof(cabi.IstftParams) == 8 * 4 + 4 * 8
+    assert ctypes.sizeof(cabi.StftParams) == 8 * 4 + 4 * 8 + 2 * 4
+    assert ctypes.sizeof(cabi.IstftParams) == 8 * 4 + 4 * 8 + 2 * 4
     assert ctypes.sizeof(cabi.TapGemmParams) == 20 * 4 + 15 * 8 + 8
     assert ctypes.sizeof(cabi.NormActParams) == 11 * 4
     assert ctypes.sizeof(cabi.LstmParams) == 10 * 4
