@@ -92,6 +92,9 @@ SYMBOLS = {
     "aero_tapgemm_wgrad": (C.c_int, [vp, vp, vp, vp, C.POINTER(TapGemmParams), i64, i64, i64, vp]),
     "aero_colsum": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i64, i64, i64, i32, i64, i64, vp]),
     "aero_add": (C.c_int, [vp, vp, i64, f32, vp]),
+    "aero_gram": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i64, i64, i64, vp]),
+    "aero_bcast_add": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "aero_scale_rows": (C.c_int, [vp, vp, vp, i32, i64, i32, vp]),
     "aero_norm_act_train_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
     "aero_norm_act_train_bwd": (C.c_int, [vp] * 13 + [i32, C.POINTER(NormActParams), vp]),
     "aero_adam_step": (C.c_int, [vp, i32, f32, f32, f32, f32, i32, f32, vp]),

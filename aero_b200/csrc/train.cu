@@ -139,6 +139,83 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------ gram
+// out[i][j] += sum_{b, m} P[b][i][m] * gate[b][m] * Q[b][j][m]   (i, j < F rows; m < M contiguous positions): the weight
+// gradient of FTB's frequency mix `freq_fc` (modules.py:296,317-320), whose contraction runs over the CONTIGUOUS axis of two
+// channels-last tensors.  64 x 64 output tile per CTA, 32 positions per step, split over (b, m chunks), fp32 atomics.
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ gate,
+                                                   float* __restrict__ out, int F, int64_t M, int64_t sb_p, int64_t sb_q, int64_t sb_g,
+                                                   int chunks_per_b) {
+    __shared__ float Ps[32][65], Qs[32][65];
+    const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    const int b = blockIdx.z / chunks_per_b, ck = blockIdx.z % chunks_per_b;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    const float* Pb = P + (int64_t)b * sb_p;
+    const float* Qb = Q + (int64_t)b * sb_q;
+    const float* Gb = gate ? gate + (int64_t)b * sb_g : nullptr;
+    for (int64_t m0 = (int64_t)ck * 32; m0 < M; m0 += (int64_t)chunks_per_b * 32) {
+        __syncthreads();
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, mm = e & 31;
+            const int64_t m = m0 + mm;
+            float pv = 0.f, qv = 0.f;
+            if (m < M) {
+                const float gv = Gb ? Gb[m] : 1.f;
+                if (i0 + r < F) pv = Pb[(int64_t)(i0 + r) * M + m] * gv;
+                if (j0 + r < F) qv = Qb[(int64_t)(j0 + r) * M + m];
+            }
+            Ps[mm][r] = pv;
+            Qs[mm][r] = qv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int mm = 0; mm < 32; ++mm) {
+            float pa[4], qa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { pa[u] = Ps[mm][ty * 4 + u]; qa[u] = Qs[mm][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(pa[u], qa[v], acc[u][v]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+            if (i < F && j < F && acc[u][v] != 0.f) atomicAdd(out + (int64_t)i * F + j, acc[u][v]);
+        }
+}
+
+// x[b][f][t][c] += addend[f][c]   (frequency embedding, aero.py:475-480, un-fused for training)
+__global__ void __launch_bounds__(256) bcast_add_kernel(float* __restrict__ x, const float* __restrict__ addend, int64_t total4, int F, int T,
+                                                        int C) {
+    const int c4n = C >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
+        const int c4 = (int)(i % c4n);
+        const int f = (int)((i / c4n / T) % F);
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        const float4 a = reinterpret_cast<const float4*>(addend + (int64_t)f * C)[c4];
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+}
+
+// y[b][i] = x[b][i] * s[b * s_stride]   (de-normalisation backward: per-sample scale)
+__global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ s,
+                                                         int64_t per_sample, int s_stride) {
+    const float k = s[(int64_t)blockIdx.y * s_stride];
+    const float* xb = x + (int64_t)blockIdx.y * per_sample;
+    float* yb = y + (int64_t)blockIdx.y * per_sample;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * 256) yb[i] = xb[i] * k;
+}
+
 // ------------------------------------------------------------------------------------------------------------ colsum
 // out1[seg][n] += sum_{o < n_outer, i < n_inner} x[seg*seg_sx + o*outer_s + i*inner_s + n]
 // out2[seg][n] += the same sum of x * z (z addressed like x); either output may be null.  OUT = float or double.
@@ -565,6 +642,40 @@ extern "C" int aero_colsum(const float* x, const float* z, void* out1, void* out
         colsum_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, z, (float*)out1, (float*)out2, N, n_inner, inner_stride, n_outer,
                                                                       outer_stride, seg_stride_x, seg_stride_out);
     return check_launch("aero_colsum");
+}
+
+extern "C" int aero_gram(const float* P, const float* Q, const float* gate, float* out, int32_t B, int32_t F, int64_t M, int64_t sb_p,
+                         int64_t sb_q, int64_t sb_g, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(P && Q && out && B >= 1 && F >= 1 && M >= 1, "aero_gram: bad argument");
+    const int tiles = cdiv(F, 64);
+    int chunks = (148 * 4) / (tiles * tiles * B) + 1;
+    const int64_t max_chunks = (M + 31) / 32;
+    if (chunks > max_chunks) chunks = (int)max_chunks;
+    AERO_REQUIRE((int64_t)B * chunks <= 65535, "aero_gram: too many z blocks");
+    dim3 grid((unsigned)tiles, (unsigned)tiles, (unsigned)(B * chunks));
+    gram_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, Q, gate, out, F, M, sb_p, sb_q, sb_g, chunks);
+    return check_launch("aero_gram");
+}
+
+extern "C" int aero_bcast_add(float* x, const float* addend, int32_t B, int32_t F, int32_t T, int32_t C, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && addend && B >= 1 && F >= 1 && T >= 1 && C >= 4 && C % 4 == 0, "aero_bcast_add: bad argument");
+    const int64_t total4 = (int64_t)B * F * T * (C / 4);
+    int64_t blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    bcast_add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, addend, total4, F, T, C);
+    return check_launch("aero_bcast_add");
+}
+
+extern "C" int aero_scale_rows(const float* x, float* y, const float* s, int32_t B, int64_t per_sample, int32_t s_stride, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && y && s && B >= 1 && B <= 65535 && per_sample >= 1, "aero_scale_rows: bad argument");
+    int64_t blocks = (per_sample + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 4096) blocks = 4096;
+    dim3 grid((unsigned)blocks, (unsigned)B);
+    scale_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, s, per_sample, s_stride);
+    return check_launch("aero_scale_rows");
 }
 
 extern "C" int aero_add(float* dst, const float* src, int64_t n, float alpha, aero_stream_t stream) {

@@ -232,6 +232,29 @@ _DEFAULTS = dict(
 )
 
 
+class _AeroTrainFn(torch.autograd.Function):
+    """forward = TrainEngine.forward (records a tape), backward = TrainEngine.backward (parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, mix, model, names, *params):
+        from .train_engine import TrainEngine
+        if not mix.is_cuda or next(model.parameters()).device != mix.device:
+            raise RuntimeError("aero_b200.Aero trains on CUDA only (sm_100a kernels in libaero_b200.so); there is no CPU path")
+        with torch.cuda.device(mix.device):
+            eng = TrainEngine(model)
+            wave, spec = eng.forward(mix)
+        ctx.eng, ctx.names, ctx.dev = eng, names, mix.device
+        ctx.set_materialize_grads(False)
+        return wave, spec
+
+    @staticmethod
+    def backward(ctx, d_wave, d_spec):
+        with torch.cuda.device(ctx.dev):
+            grads = ctx.eng.backward(d_wave, d_spec)
+        ctx.eng = None
+        return (None, None, None, *[grads.get(n) for n in ctx.names])
+
+
 class Aero(nn.Module):
     """AERO generator (audio super-resolution in the spectral domain), B200-native.
 
@@ -353,4 +376,24 @@ class Aero(nn.Module):
         return self._engine().ispec(z)
 
     def forward(self, mix, return_spec=False, return_lr_spec=False):
+        if self.training:
+            return self._train_forward(mix, return_spec, return_lr_spec)
         return self._engine().forward(mix, return_spec=return_spec, return_lr_spec=return_lr_spec)
+
+    def _train_forward(self, mix, return_spec, return_lr_spec):
+        """Training mode (reference solver.py:305 `self.dmodel(lr)` under autograd): the forward and its backward both run on
+        the CUDA kernels (aero_b200/train_engine.py) behind ONE autograd node, so `loss.backward()`, `optimizer.step()`, DDP
+        gradient hooks and `return_spec` all behave as with the reference nn.Module."""
+        names = [n for n, p in self.named_parameters() if p.requires_grad]
+        params = [p for _, p in self.named_parameters() if p.requires_grad]
+        wave, spec = _AeroTrainFn.apply(mix, self, names, *params)
+        if not return_spec:
+            return wave
+        B, Fq, T, C2 = spec.shape
+        zc = torch.view_as_complex(spec.reshape(B, Fq, T, C2 // 2, 2)).permute(0, 3, 1, 2)
+        if not return_lr_spec:
+            return wave, zc
+        with torch.no_grad():
+            was = self.training
+            zl = self._engine().spec(mix.detach())
+        return wave, zc, zl

@@ -317,6 +317,14 @@ int aero_colsum(const float* x, const float* z, void* out1, void* out2, int32_t 
                 int64_t inner_stride, int64_t n_outer, int64_t outer_stride, int32_t n_seg, int64_t seg_stride_x,
                 int64_t seg_stride_out, aero_stream_t stream);
 
+/* out[i][j] += sum_{b, m} P[b][i][m] * gate[b][m] * Q[b][j][m],  i, j < F,  m < M contiguous (batch strides sb_*; gate may be
+ * NULL): weight gradient of FTB's `freq_fc` (modules.py:296,317-320), P = dY, Q = x, gate = the FTB gate.  Caller zeroes out. */
+int aero_gram(const float* P, const float* Q, const float* gate, float* out, int32_t B, int32_t F, int64_t M, int64_t sb_p,
+              int64_t sb_q, int64_t sb_g, aero_stream_t stream);
+/* x[b][f][t][c] += addend[f][c]  (frequency embedding, aero.py:475-480; fused into a GEMM epilogue at inference). */
+int aero_bcast_add(float* x, const float* addend, int32_t B, int32_t F, int32_t T, int32_t C, aero_stream_t stream);
+/* y[b][i] = x[b][i] * s[b*s_stride], i < per_sample  (backward of the per-sample de-normalisation aero.py:497-498). */
+int aero_scale_rows(const float* x, float* y, const float* s, int32_t B, int64_t per_sample, int32_t s_stride, aero_stream_t stream);
 /* dst[i] += alpha * src[i] (gradient accumulation where a tensor has several consumers). */
 int aero_add(float* dst, const float* src, int64_t n, float alpha, aero_stream_t stream);
 

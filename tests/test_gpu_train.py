@@ -1,0 +1,97 @@
+"""-m gpu: the training path -- `model.train(); loss.backward()` on the CUDA kernels against the
+parameter gradients of the unmodified reference under autograd (tests/golden/t*.npz, made by make_golden_train.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import SEED, rel_l2, trained_like_, weights_digest, white_noise
+
+from aero_b200 import Aero, aero_kwargs
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "t*.npz")))
+GRAD_TOL = 1e-3
+
+
+def cotangent(shape, seed):
+    return white_noise(shape, seed=seed + 77)
+
+
+def grad_report(model, g):
+    """Per-parameter relative error on the committed samples.  Parameters whose reference gradient is tiny against the
+    largest one are judged on the absolute error at that scale (a relative error of a rounding-level number says nothing)."""
+    rows = []
+    gmax = max(float(g[k]) for k in g.files if k.startswith("g_rms/"))
+    for name, p in model.named_parameters():
+        ref = torch.from_numpy(g["g_val/" + name]).double()
+        idx = torch.from_numpy(g["g_idx/" + name].astype(np.int64))
+        assert p.grad is not None, f"no gradient for {name}"
+        got = p.grad.detach().reshape(-1).cpu().double()[idx]
+        rms = float(g["g_rms/" + name])
+        denom = max(float(ref.norm()), 1e-4 * gmax * ref.numel() ** 0.5)
+        rows.append((float((got - ref).norm()) / denom, name, rms))
+    return sorted(rows, reverse=True)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_parameter_gradients_match_reference_autograd(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    torch.manual_seed(SEED)
+    m = Aero(**aero_kwargs(str(g["exp"])))
+    m.load_state_dict(trained_like_(m.state_dict()))
+    assert weights_digest(m.state_dict()) == pytest.approx(float(g["digest"]), rel=1e-12)
+    m = m.cuda().train()
+    mix = white_noise((int(g["B"]), m.in_channels, int(g["L"]))).cuda()
+    out = m(mix)
+    assert tuple(out.shape) == tuple(int(v) for v in g["out_shape"]) and out.requires_grad
+    flat = out.detach().reshape(-1).cpu()
+    e_out = rel_l2(flat[torch.from_numpy(g["out_idx"].astype(np.int64))], g["out_val"])
+    R = cotangent(tuple(out.shape), SEED).cuda()
+    loss = (out * R).sum() / out.numel()
+    loss.backward()
+    torch.cuda.synchronize()
+    rows = grad_report(m, g)
+    print(f"{case}: train-mode output rel_l2 {e_out:.3e}, loss {float(loss):.6e} (ref {float(g['loss']):.6e}); worst gradients:")
+    for err, name, rms in rows[:8]:
+        print(f"   {err:.3e}  {name}  (ref rms {rms:.3e})")
+    assert e_out < 2e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * max(abs(float(g["loss"])), 1e-6) + 1e-9
+    assert rows[0][0] < GRAD_TOL, rows[:5]
+    # BatchNorm running buffers were updated as nn.BatchNorm does in train mode
+    for k in g.files:
+        if k.startswith("buf/"):
+            got = dict(m.named_buffers())[k[4:]].cpu()
+            assert rel_l2(got, g[k]) < 1e-5, k
+
+
+def test_train_step_with_fused_adam_reduces_the_loss():
+    """A few optimisation steps through the public API: forward (train), backward, aero_b200.optim.FusedAdam."""
+    from aero_b200.optim import FusedAdam
+    torch.manual_seed(SEED)
+    m = Aero(**aero_kwargs("aero_4-16_512_256"))
+    m.load_state_dict(trained_like_(m.state_dict()))
+    m = m.cuda().train()
+    ref = torch.optim.Adam([p.detach().clone().requires_grad_(True) for p in m.parameters()], lr=3e-4, betas=(0.9, 0.999))
+    opt = FusedAdam(m.parameters(), lr=3e-4, betas=(0.9, 0.999))
+    mix = white_noise((2, 1, 4000)).cuda()
+    target = white_noise((2, 1, 16000), seed=5).cuda() * 0.1
+    losses = []
+    for step in range(4):
+        opt.zero_grad()
+        out = m(mix)
+        loss = (out - target).abs().mean()
+        loss.backward()
+        if step == 0:       # one step of torch.optim.Adam on the same gradients gives the same parameters
+            for q, p in zip(ref.param_groups[0]["params"], m.parameters()):
+                q.grad = p.grad.detach().clone()
+            ref.step()
+        opt.step()
+        if step == 0:
+            for q, p in zip(ref.param_groups[0]["params"], m.parameters()):
+                assert rel_l2(p.detach().cpu(), q.detach().cpu()) < 1e-6
+        losses.append(float(loss))
+    print("losses:", losses)
+    assert losses[-1] < losses[0]
