@@ -88,6 +88,7 @@ SYMBOLS = {
     "aero_local_attn_fwd": (C.c_int, [vp, vp, C.POINTER(AttnParams), vp]),
     "aero_lsd_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "aero_stft_loss_fwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "aero_stft_loss_bwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp]),
     # training
     "aero_tapgemm_wgrad": (C.c_int, [vp, vp, vp, vp, C.POINTER(TapGemmParams), i64, i64, i64, vp]),
     "aero_colsum": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i64, i64, i64, i32, i64, i64, vp]),

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) na_train_bwd_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ snake_a, const float* __restrict__ scale,
                                                            const float* __restrict__ dy, float* __restrict__ dx,
-                                                           float* dgamma, float* dbeta, float* dscale, float* dsnake, double* ws,
+                                                           double* dgamma, double* dbeta, double* dscale, double* dsnake, double* ws,
                                                            const aero_norm_act_params p) {
     constexpr bool GLU = (OP == AERO_NA_GLU || OP == AERO_NA_GLU_SCALE_RES);
     __shared__ float s_dg[APPLY ? 1 : kNaMaxC], s_db[APPLY ? 1 : kNaMaxC], s_ds[APPLY ? 1 : kNaMaxC / 2];
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256) na_train_bwd_kernel(const float* __restri
                     if (GLU) {
                         m1b[u] = (float)((double)k1.ga[u] * dbeta[c + Cout + u] / n);
                         m2b[u] = (float)((double)k1.ga[u] * dgamma[c + Cout + u] / n);
-                    }
+                    }   // (dgamma / dbeta are the fp64 accumulators of pass 1)
                 } else {
                     const int gw = p.C / p.groups;
                     const double n = (p.scope == 1) ? (double)p.F_in * p.T * gw : (double)p.T * p.C;
@@ -547,8 +547,8 @@ __global__ void __launch_bounds__(256) na_train_bwd_kernel(const float* __restri
     __syncthreads();
     if (!nonorm) {
         for (int i = threadIdx.x; i < p.C; i += 256) {
-            if (s_dg[i] != 0.f) atomicAdd(dgamma + i, s_dg[i]);
-            if (s_db[i] != 0.f) atomicAdd(dbeta + i, s_db[i]);
+            if (s_dg[i] != 0.f) atomicAdd(dgamma + i, (double)s_dg[i]);
+            if (s_db[i] != 0.f) atomicAdd(dbeta + i, (double)s_db[i]);
         }
         if (p.scope != 3 && threadIdx.x < p.groups) {
             const int64_t slot = (p.scope == 1) ? (int64_t)seg * p.groups + threadIdx.x : seg;
@@ -558,8 +558,8 @@ __global__ void __launch_bounds__(256) na_train_bwd_kernel(const float* __restri
     }
     if (OP == AERO_NA_GLU_SCALE_RES)
         for (int i = threadIdx.x; i < Cout; i += 256)
-            if (s_ds[i] != 0.f) atomicAdd(dscale + i, s_ds[i]);
-    if (OP == AERO_NA_SNAKE && threadIdx.x == 0 && s_da != 0.f) atomicAdd(dsnake + f_lo, s_da);
+            if (s_ds[i] != 0.f) atomicAdd(dscale + i, (double)s_ds[i]);
+    if (OP == AERO_NA_SNAKE && threadIdx.x == 0 && s_da != 0.f) atomicAdd(dsnake + f_lo, (double)s_da);
 }
 
 // ------------------------------------------------------------------------------------------------------------ Adam
@@ -696,7 +696,8 @@ static int na_train_check(const aero_norm_act_params* p) {
     const int Cout = glu ? p->C / 2 : p->C;
     AERO_REQUIRE(p->C % 4 == 0 && Cout % 4 == 0 && Cout / 4 <= 256 && p->C <= kNaMaxC, "aero_norm_act_train: C=%d", p->C);
     const bool nonorm = p->flags & AERO_NA_NO_NORM;
-    AERO_REQUIRE(nonorm || p->scope != 1 || (p->groups >= 1 && p->groups <= kNaMaxGroups && p->C % p->groups == 0), "aero_norm_act_train: groups");
+    AERO_REQUIRE(nonorm || p->scope != 1 || (p->groups >= 1 && p->groups <= kNaMaxGroups && p->C % p->groups == 0 && (p->C / p->groups) % 4 == 0),
+                 "aero_norm_act_train: groups (group width must be a multiple of 4)");
     AERO_REQUIRE(p->scope == 1 || (p->f_off == 0 && p->F_in == p->F_out), "aero_norm_act_train: crop needs scope 1");
     AERO_REQUIRE(p->f_off >= 0 && p->f_off + p->F_out <= p->F_in, "aero_norm_act_train: crop out of range");
     AERO_REQUIRE(p->op != AERO_NA_SNAKE || p->scope == 2, "aero_norm_act_train: snake needs the per-row scope");
@@ -741,8 +742,8 @@ extern "C" int aero_norm_act_train_fwd(const float* x, const double* stats, cons
 }
 
 extern "C" int aero_norm_act_train_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
-                                       const float* scale, const float* dy, float* dx, float* dgamma, float* dbeta, float* dscale,
-                                       float* dsnake, double* ws, int32_t pass, const aero_norm_act_params* p, aero_stream_t stream) {
+                                       const float* scale, const float* dy, float* dx, double* dgamma, double* dbeta, double* dscale,
+                                       double* dsnake, double* ws, int32_t pass, const aero_norm_act_params* p, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(x && dy && p && (pass == 1 || pass == 2), "aero_norm_act_train_bwd: null argument");
     int rc = na_train_check(p);

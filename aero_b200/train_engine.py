@@ -180,10 +180,12 @@ class TrainEngine:
                 (full[:, wslice] if cv.kind == "conv" else full[wslice]).add_(gw.view(w.shape))
             # ---- bias gradient: column sums over every output pixel
             if bias is not None:
-                gb = torch.zeros_like(bias) if b_back is not None else self.pgrad(bname)
+                gb = self._new(N, zero=True, dtype=torch.float64)
                 self._colsum(dy, gb, N, T, os_[2], n_outer=F_out, outer_s=os_[1], n_seg=B, seg_sx=os_[0], seg_so=0)
                 if b_back is not None:
-                    b_back(gb)
+                    b_back(gb.float())
+                else:
+                    self.pgrad(bname).add_(gb.float())
             # ---- data gradients: the adjoint tap-GEMM reads dy (with the forward's output strides)
             for src, lo, cs in ((x1, 0, C1), (x2, C1, C2)):
                 if src is None or cs == 0 or id(src) in self.no_grad:
@@ -234,12 +236,14 @@ class TrainEngine:
             dy = self.grad(y)
             if dy is None:
                 return
-            dgamma = dbeta = None
+            # parameter gradients are sums over every pixel whose terms largely cancel: accumulated in fp64 by the kernel
+            dgamma = dbeta = dscale = dsn = None
             if not no_norm:
-                dgamma = torch.zeros_like(gamma) if g_back is not None else self.pgrad(gname)
-                dbeta = torch.zeros_like(beta) if b_back is not None else self.pgrad(bname)
-            dscale = self.pgrad(scale) if scale else None
-            dsn = self.pgrad(snake).view(-1) if snake else None
+                dgamma, dbeta = self._new(C_, zero=True, dtype=torch.float64), self._new(C_, zero=True, dtype=torch.float64)
+            if scale:
+                dscale = self._new(Cout, zero=True, dtype=torch.float64)
+            if snake:
+                dsn = self._new(sa.numel(), zero=True, dtype=torch.float64)
             nslot = B * groups if scope == 1 else (B * F_in if scope == 2 else 1)
             ws = self._new(nslot, 2, zero=True, dtype=torch.float64)
             dx = self._new(x.numel())
@@ -248,8 +252,15 @@ class TrainEngine:
                                                              _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dscale), _ptr(dsn), _ptr(ws), pas,
                                                              C.byref(p), self._stream()))
             if g_back is not None:
-                g_back(dgamma)
-                b_back(dbeta)
+                g_back(dgamma.float())
+                b_back(dbeta.float())
+            elif not no_norm:
+                self.pgrad(gname).add_(dgamma.float())
+                self.pgrad(bname).add_(dbeta.float())
+            if scale:
+                self.pgrad(scale).add_(dscale.float().view_as(self.pgrad(scale)))
+            if snake:
+                self.pgrad(snake).add_(dsn.float().view_as(self.pgrad(snake)))
             self.acc(x, dx)
             if residual is not None:
                 self.acc(residual, dy)
@@ -327,6 +338,7 @@ class TrainEngine:
         # conv2 on cat([Y, x]) + BN2d + ReLU
         O_raw = self.conv(Y, x, Cc, Cc, q + ".conv2.0.weight", q + ".conv2.0.bias", _C1x1, B, Fq, Fq, T, Cc)
         st3 = self._batch_stats(O_raw, Cc, q + ".conv2.1", Cc)
+        self._dbg = dict(R_raw=R_raw, R=R, G_raw=G_raw, G=G, Y=Y, O_raw=O_raw, st3=st3)
         return self.norm_act(O_raw, NA_RELU, B=B, F_in=Fq, T=T, C_=Cc, scope=3, gname=q + ".conv2.1.weight", bname=q + ".conv2.1.bias",
                              stats=st3)
 
@@ -394,10 +406,10 @@ class TrainEngine:
                     # input with the bias only, so the bias also collects what the fold drops
                     dgin = self._new(rows * T * G)
                     self._check(lib.aero_lstm_fold(_ptr(dgin_w), _ptr(dgin), rows, T, n_win, steps, stride, G, self._stream()))
-                    g_all, g_real = self._new(G, zero=True), self._new(G, zero=True)
+                    g_all, g_real = self._new(G, zero=True, dtype=torch.float64), self._new(G, zero=True, dtype=torch.float64)
                     self._colsum(dgin_w, g_all, G, n_seq * steps, G)
                     self._colsum(dgin, g_real, G, rows * T, G)
-                    extra = g_all - g_real
+                    extra = (g_all - g_real).float()
                     for i, n in enumerate(bnames):
                         self.pgrad(n).add_(extra[(i // 2) * 4 * H:(i // 2 + 1) * 4 * H])
                 else:
@@ -512,9 +524,9 @@ class TrainEngine:
                 dy = self.grad(out)
                 if dy is None:
                     return
-                ge = self._new(Fo * Cc, zero=True)
+                ge = self._new(Fo * Cc, zero=True, dtype=torch.float64)
                 self._colsum(dy, ge, Cc, T, Cc, n_outer=B, outer_s=Fo * T * Cc, n_seg=Fo, seg_sx=T * Cc, seg_so=Cc)
-                self.pgrad("freq_emb.embedding.weight").add_(ge.view(Fo, Cc) * k)
+                self.pgrad("freq_emb.embedding.weight").add_((ge.view(Fo, Cc) * k).float())
             self.tape.append(emb_bwd)
         return out
 
@@ -619,24 +631,29 @@ class TrainEngine:
         return e
 
     @torch.no_grad()
+    def istft_adjoint(self, d_wave, B, Cout, T, Fq, out_len):
+        """Gradient of the output spectrogram [B, Fq, T, 2 C_out] from the gradient of the waveform: the adjoint of
+        aero_istft_fwd = zero-extend, divide by the window envelope, then the STFT kernel with zero padding and the C2R
+        adjoint scaling (include/aero_b200.h, AERO_STFT_ZERO_PAD | AERO_STFT_ADJ_SCALE)."""
+        g = self.geom
+        N, hop = g.nfft, g.hop_out
+        full = hop * (T - 1)
+        u = torch.zeros(B * Cout, full, device=d_wave.device)
+        u[:, :out_len] = d_wave.reshape(B * Cout, out_len).float()
+        u.div_(self._envelope(T)[N // 2:N // 2 + full])
+        dz = self._new(B, Fq, T, 2 * Cout)
+        sp = cabi.StftParams(N, hop, g.win_out, B * Cout, Cout, full, T, Fq, Fq * T * 2 * Cout, 2, T * 2 * Cout, 2 * Cout,
+                             cabi.STFT_ZERO_PAD | cabi.STFT_ADJ_SCALE, 0)
+        self._check(self.lib.aero_stft_fwd(_ptr(u), _ptr(self._window(g.win_out)), _ptr(dz), None, C.byref(sp), self._stream()))
+        return dz
+
+    @torch.no_grad()
     def backward(self, d_wave, d_spec=None):
         """d_wave: gradient of the waveform [B, C_out, out_len] (or None); d_spec: gradient of the output spectrogram as real
         pairs [B, Fq, T, 2 C_out] (or None).  Returns {parameter name: gradient}."""
         lib, g = self.lib, self.geom
         h, B, Cout, T, Fq, out_len = self._final
-        dz = None
-        if d_wave is not None:
-            # adjoint of the iSTFT: zero-extend, divide by the window envelope, then the STFT kernel with zero padding
-            # and the C2R adjoint scaling (include/aero_b200.h, AERO_STFT_ADJ_SCALE)
-            N, hop = g.nfft, g.hop_out
-            full = hop * (T - 1)
-            u = torch.zeros(B * Cout, full, device=d_wave.device)
-            u[:, :out_len] = d_wave.reshape(B * Cout, out_len).float()
-            u.div_(self._envelope(T)[N // 2:N // 2 + full])
-            dz = self._new(B, Fq, T, 2 * Cout)
-            sp = cabi.StftParams(N, hop, g.win_out, B * Cout, Cout, full, T, Fq, Fq * T * 2 * Cout, 2, T * 2 * Cout, 2 * Cout,
-                                 cabi.STFT_ZERO_PAD | cabi.STFT_ADJ_SCALE, 0)
-            self._check(lib.aero_stft_fwd(_ptr(u), _ptr(self._window(g.win_out)), _ptr(dz), None, C.byref(sp), self._stream()))
+        dz = self.istft_adjoint(d_wave, B, Cout, T, Fq, out_len) if d_wave is not None else None
         if d_spec is not None:
             ds = d_spec.contiguous().float().clone()
             dz = ds if dz is None else dz.add_(ds.view_as(dz))

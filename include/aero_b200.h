@@ -294,6 +294,14 @@ int aero_lsd_fwd(const float* z_ref, const float* z_est, double* out_sum, int32_
 int aero_stft_loss_fwd(const float* z_est, const float* z_ref, double* sums, int32_t B, int32_t bins, int32_t frames,
                        int32_t n_fft, aero_stream_t stream);
 
+/* Backward of the above for the estimate: with the `sums` of the forward, g_est[B][bins][frames] (float2) = gradient of
+ *   c_sc * sqrt(sums[0]/sums[1]) + c_mag * sums[2] / (B*bins*frames)
+ * with respect to the normalised spectrogram z_est, the interior bins already halved: feeding g_est to aero_istft_fwd with
+ * AERO_ISTFT_RAW gives the gradient of the reflect-padded waveform (the caller folds the padding back).  bins = n_fft/2+1.
+ * (reference: autograd through stft_loss.py:11-63, called with gradients at solver.py:470-473) */
+int aero_stft_loss_bwd(const float* z_est, const float* z_ref, const double* sums, float* g_est, int32_t B, int32_t bins,
+                       int32_t frames, int32_t n_fft, float c_sc, float c_mag, aero_stream_t stream);
+
 /* ==========================================================================================
  * Training (backward of the custom ops + fused Adam; reference callers src/solver.py:292-342,
  * 602-605 `loss.backward(); optimizer.step()`, train.py:83 `torch.optim.Adam`).  All tensors fp32.
@@ -335,14 +343,16 @@ int aero_add(float* dst, const float* src, int64_t n, float alpha, aero_stream_t
 int aero_norm_act_train_fwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
                             const float* scale, const float* residual, float* y, const aero_norm_act_params* p,
                             aero_stream_t stream);
-/* Backward of the above.  pass 1 accumulates dgamma[C], dbeta[C], dscale[C/2] (GLU_SCALE_RES), dsnake[F_in] (SNAKE) and the
- * per-(segment, group) sums ws[slot] = {sum dxh, sum dxh*xh} (fp64, same slots as `stats`; unused for scope 3);
+/* Backward of the above.  pass 1 accumulates dgamma[C], dbeta[C], dscale[C/2] (GLU_SCALE_RES), dsnake[F_in] (SNAKE) -- all fp64:
+ * these are sums over every pixel of the batch whose terms largely cancel, and fp32 atomics across hundreds of CTAs lose
+ * ~1e-3 of the result -- and the per-(segment, group) sums ws[slot] = {sum dxh, sum dxh*xh} (fp64, same slots as `stats`;
+ * unused for scope 3, which reads dgamma / dbeta instead);
  * pass 2 writes dx[B][F_in][T][C] = rstd * (dxh - mean(dxh) - xh * mean(dxh * xh)) (every input row, cropped rows included).
  * The gradient of the residual input of GLU_SCALE_RES is dy itself (the caller accumulates it).  The caller zeroes the
  * accumulators before pass 1. */
 int aero_norm_act_train_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* snake_a,
-                            const float* scale, const float* dy, float* dx, float* dgamma, float* dbeta, float* dscale,
-                            float* dsnake, double* ws, int32_t pass, const aero_norm_act_params* p, aero_stream_t stream);
+                            const float* scale, const float* dy, float* dx, double* dgamma, double* dbeta, double* dscale,
+                            double* dsnake, double* ws, int32_t pass, const aero_norm_act_params* p, aero_stream_t stream);
 
 /* LSTM layer, training form (fp32 SIMT recurrence; reference modules.py:28-65 under autograd, i.e. cuDNN's RNN training
  * forward and backward-data).  Forward = aero_lstm_rec_fwd (precision 0) that also saves, WINDOWED as [rows*n_win][steps][2][..],

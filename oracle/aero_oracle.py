@@ -94,9 +94,18 @@ def group_norm(x, groups, weight, bias, eps=1e-5, explicit=False):
     return y * weight.view(shape) + bias.view(shape)
 
 
+BN_TRAIN = False      # tests of the training path set this: BatchNorm then uses batch statistics (nn.BatchNorm in train mode)
+
+
 def batch_norm_eval(x, sd, prefix, eps=1e-5):
-    """Eval-mode BatchNorm (running statistics), reference modules.py:287,293,300."""
+    """BatchNorm of the FTB blocks, reference modules.py:287,293,300: running statistics (eval mode), or -- when the module
+    flag BN_TRAIN is set -- the statistics of the batch (biased variance), as nn.BatchNorm normalises in train mode."""
     shape = [1, -1] + [1] * (x.dim() - 2)
+    if BN_TRAIN:
+        dims = [0] + list(range(2, x.dim()))
+        mu = x.mean(dims, keepdim=True)
+        var = ((x - mu) ** 2).mean(dims, keepdim=True)
+        return (x - mu) * torch.rsqrt(var + eps) * sd[prefix + ".weight"].view(shape) + sd[prefix + ".bias"].view(shape)
     inv = torch.rsqrt(sd[prefix + ".running_var"] + eps) * sd[prefix + ".weight"]
     return (x - sd[prefix + ".running_mean"].view(shape)) * inv.view(shape) + sd[prefix + ".bias"].view(shape)
 

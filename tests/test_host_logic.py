@@ -99,9 +99,13 @@ def test_train_mode_and_cpu_fail_loudly():
     m = Aero(**aero_kwargs("aero_4-16_512_256"))
     with pytest.raises(RuntimeError, match="CUDA only"):
         m.eval()(torch.zeros(1, 1, 4000))
-    emulated(m).train()
-    with pytest.raises(NotImplementedError, match="eval"):
+    # training mode has its own CUDA path (aero_b200/train_engine.py): a CPU tensor fails just as loudly there
+    m.train()
+    with pytest.raises(RuntimeError, match="CUDA only"):
         m(torch.zeros(1, 1, 4000))
+    # ... and the INFERENCE engine never runs a model that is in training mode (it would silently use eval BatchNorm)
+    with pytest.raises(NotImplementedError, match="eval"):
+        emulated(m)._engine().forward(torch.zeros(1, 1, 4000))
 
 
 def test_enhance_long_equals_serial_chunks():
