@@ -57,6 +57,8 @@ class TrainEngine:
         self.pg = {}           # parameter name -> gradient tensor (PyTorch layout)
         self.keep = []         # tensors the tape refers to by id
         self.no_grad = set()   # ids of activations that need no gradient (the input spectrogram)
+        self._sink = None      # optional name -> preallocated gradient tensor
+        self.marks = []        # (tape length, layer tag) after each encoder / decoder layer of the forward
 
     # ------------------------------------------------------------------ plumbing
     def _device(self):
@@ -88,7 +90,11 @@ class TrainEngine:
     def pgrad(self, name):
         t = self.pg.get(name)
         if t is None:
-            t = self.pg[name] = torch.zeros_like(self.params[name], dtype=torch.float32, memory_format=torch.contiguous_format)
+            if self._sink is not None:          # caller-owned, zeroed buffer (the trainer's flat gradient buffer)
+                t = self._sink(name)
+            else:
+                t = torch.zeros_like(self.params[name], dtype=torch.float32, memory_format=torch.contiguous_format)
+            self.pg[name] = t
         return t
 
     def _window(self, win):
@@ -600,9 +606,11 @@ class TrainEngine:
         for lg in g.layers:
             h = self.encode(h, lg, B, T)
             saved.append(h)
+            self.marks.append((len(self.tape), f"encoder.{lg.index}"))
         h = None
         for j, lg in enumerate(reversed(g.layers)):
             h = self.decode(h, saved.pop(), lg, j, B, T, lg.index == 0, affine)
+            self.marks.append((len(self.tape), f"decoder.{j}"))
         Cout = kw["out_channels"]
         out_len = min(int(length * g.scale), g.hop_out * (T - 1))
         y = self._new(B * Cout, out_len)
@@ -648,9 +656,12 @@ class TrainEngine:
         return dz
 
     @torch.no_grad()
-    def backward(self, d_wave, d_spec=None):
+    def backward(self, d_wave, d_spec=None, grad_sink=None, on_layer_done=None):
         """d_wave: gradient of the waveform [B, C_out, out_len] (or None); d_spec: gradient of the output spectrogram as real
-        pairs [B, Fq, T, 2 C_out] (or None).  Returns {parameter name: gradient}."""
+        pairs [B, Fq, T, 2 C_out] (or None).  Returns {parameter name: gradient}.
+        grad_sink(name) -> zeroed tensor to accumulate that parameter's gradient into (else fresh tensors);
+        on_layer_done(tag) is called when every gradient of layer `tag` ("decoder.3", ..., "encoder.0") is final."""
+        self._sink = grad_sink
         lib, g = self.lib, self.geom
         h, B, Cout, T, Fq, out_len = self._final
         dz = self.istft_adjoint(d_wave, B, Cout, T, Fq, out_len) if d_wave is not None else None
@@ -660,8 +671,15 @@ class TrainEngine:
         if dz is None:
             return {}
         self.acc(h, dz)
-        for fn in reversed(self.tape):
-            fn()
+        starts = {0: None}
+        prev = 0
+        for end, tag in self.marks:                       # layer `tag` owns tape[prev:end]; it is done once tape[prev] has run
+            starts[prev] = tag
+            prev = end
+        for i in range(len(self.tape) - 1, -1, -1):
+            self.tape[i]()
+            if on_layer_done is not None and starts.get(i) is not None:
+                on_layer_done(starts[i])
         grads = self.pg
         self._reset()
         return grads
