@@ -435,8 +435,11 @@ def test_encoder_and_decoder_layers_as_blocks(exp, B, L):
                     rows.append((float((got - v.grad).norm() / max(float(v.grad.norm()), 1e-4 * gmax * v.numel() ** 0.5)), k))
             rows.sort(reverse=True)
             print(f"{exp} encoder.{lg.index}:", [(f"{a:.2e}", b) for a, b in rows[:4]])
-            # (3e-3: one activation within fp32 rounding of a BatchNorm+ReLU kink moves the FTB gradients by ~1e-3; see test_gpu_train.py)
-            assert rows[0][0] < 3e-3, rows[:6]
+            # everything downstream of the FTB block in the backward order is exact to fp32 round-off; the FTB parameters and dx sit
+            # behind BatchNorm + ReLU, where one activation within fp32 rounding of the kink moves them by up to ~1e-2 (test_gpu_train.py)
+            exact = [r for r in rows if "freq_attn_block" not in r[1] and "pre_conv" not in r[1] and r[1] != "dx"]
+            assert exact[0][0] < 2e-4, exact[:6]
+            assert rows[0][0] < 3e-2, rows[:6]
         for j, lg in enumerate(reversed(geom.layers)):
             last = lg.index == 0
             xin = None if j == 0 else rnd(B, lg.ch, lg.f_out, T, seed=30 + j).double().requires_grad_(True)
