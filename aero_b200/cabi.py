@@ -65,7 +65,7 @@ ABI_VERSION = 3
 TAPS_CONV, TAPS_CONVT, TAPS_MIX = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 TG_ROUND_TF32, TG_A_F16, TG_OUT_F16, TG_REVERSE = 1, 2, 4, 8      # storage-type flags (AERO_TG_*)
-NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES, NA_RELU = 0, 1, 2, 3, 4, 5
+NA_NONE, NA_GELU, NA_GLU, NA_SNAKE, NA_GLU_SCALE_RES, NA_RELU, NA_LEAKY = 0, 1, 2, 3, 4, 5, 6
 NA_NO_NORM = 16
 STFT_ZERO_PAD, STFT_ADJ_SCALE, ISTFT_RAW = 1, 2, 1
 
@@ -99,6 +99,11 @@ SYMBOLS = {
     "aero_norm_act_train_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
     "aero_norm_act_train_bwd": (C.c_int, [vp] * 13 + [i32, C.POINTER(NormActParams), vp]),
     "aero_adam_step": (C.c_int, [vp, i32, f32, f32, f32, f32, i32, f32, vp]),
+    "aero_gconv1d_fwd": (C.c_int, [vp, vp, vp, vp] + [i32] * 9 + [vp]),
+    "aero_gconv1d_dgrad": (C.c_int, [vp, vp, vp] + [i32] * 9 + [vp]),
+    "aero_gconv1d_wgrad": (C.c_int, [vp, vp, vp] + [i32] * 9 + [vp]),
+    "aero_weight_norm_fwd": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+    "aero_weight_norm_bwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "aero_lstm_train_fwd": (C.c_int, [vp] * 7 + [C.POINTER(LstmParams), vp]),
     "aero_lstm_bwd": (C.c_int, [vp] * 5 + [C.POINTER(LstmParams), vp]),
     "aero_lstm_fold": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -1,0 +1,281 @@
+// MelGAN multi-scale discriminator kernels (reference src/models/discriminators.py:14-78,
+// src/models/modules.py WNConv1d): the grouped, strided 1-D convolutions (k = 41, stride 4, groups = C_in / 4) that cuDNN serves
+// poorly -- forward, data gradient and weight gradient -- and weight normalisation (w = g * v / ||v||) forward / backward.
+// Activations are channels-last [B][T][C] like everywhere else in the library; the dense layers of the discriminator (k = 15, 5, 3)
+// run on the tap-GEMM.  fp32.
+#include "common.cuh"
+
+namespace aero {
+
+constexpr int kGcCo = 64;       // output channels per CTA
+constexpr int kGcT = 32;        // output time steps per CTA (forward / wgrad)
+
+struct GconvP {
+    int B, Tin, Tout, Cin, Cout, groups, k, stride, pad;
+};
+
+// y[b][to][co] = bias[co] + sum_{c < cpg, j < k} x[b][to*stride + j - pad][g*cpg + c] * w[co][c][j],  g = co / (Cout/groups)
+__global__ void __launch_bounds__(256) gconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ y, const GconvP p) {
+    extern __shared__ float sm[];
+    const int cpg = p.Cin / p.groups, opg = p.Cout / p.groups;
+    const int co0 = blockIdx.x * kGcCo, to0 = blockIdx.y * kGcT, b = blockIdx.z;
+    const int nco = min(kGcCo, p.Cout - co0);
+    const int g0 = co0 / opg, ng = (co0 + nco - 1) / opg - g0 + 1;      // groups touched by this tile
+    const int nch = ng * cpg;                                           // input channels needed
+    const int win = (kGcT - 1) * p.stride + p.k;                        // input time steps needed
+    float* ws = sm;                                                     // [nco][cpg*k]
+    float* xs = sm + kGcCo * cpg * p.k;                                 // [win][nch]
+    const int wl = cpg * p.k;
+    for (int i = threadIdx.x; i < nco * wl; i += 256) ws[i] = w[(int64_t)co0 * wl + i];
+    const int ti0 = to0 * p.stride - p.pad;
+    for (int i = threadIdx.x; i < win * nch; i += 256) {
+        const int tt = i / nch, c = i - tt * nch;
+        const int ti = ti0 + tt;
+        xs[i] = (ti >= 0 && ti < p.Tin) ? x[((int64_t)b * p.Tin + ti) * p.Cin + g0 * cpg + c] : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < kGcT * nco; o += 256) {
+        const int tl = o / nco, cl = o - tl * nco;
+        const int to = to0 + tl;
+        if (to >= p.Tout) continue;
+        const int co = co0 + cl;
+        const int gl = co / opg - g0;
+        const float* wr = ws + cl * wl;
+        const float* xr = xs + (tl * p.stride) * nch + gl * cpg;
+        float acc = bias ? bias[co] : 0.f;
+        for (int c = 0; c < cpg; ++c)
+            for (int j = 0; j < p.k; ++j) acc = fmaf(xr[j * nch + c], wr[c * p.k + j], acc);
+        y[((int64_t)b * p.Tout + to) * p.Cout + co] = acc;
+    }
+}
+
+// dx[b][ti][ci] = sum_{co in group(ci)} sum_{j : (ti + pad - j) % stride == 0} dy[b][(ti + pad - j)/stride][co] * w[co][ci % cpg][j]
+constexpr int kGdT = 128;       // input time steps per CTA
+__global__ void __launch_bounds__(256) gconv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                                          const GconvP p) {
+    extern __shared__ float sm[];
+    const int cpg = p.Cin / p.groups, opg = p.Cout / p.groups;
+    const int gt = max(1, kGcCo / opg);                                 // groups per CTA
+    const int g0 = blockIdx.x * gt, ti0 = blockIdx.y * kGdT, b = blockIdx.z;
+    const int ng = min(gt, p.groups - g0);
+    const int nco = ng * opg, nci = ng * cpg;
+    const int wl = cpg * p.k;
+    float* ws = sm;                                                     // [nco][cpg*k]
+    float* ds = sm + kGcCo * wl;                                        // [rows][nco]
+    for (int i = threadIdx.x; i < nco * wl; i += 256) ws[i] = w[(int64_t)g0 * opg * wl + i];
+    // output rows that can touch ti in [ti0, ti0 + kGdT): to in [ceil((ti0 + pad - k + 1)/s), floor((ti0 + kGdT - 1 + pad)/s)]
+    int to_lo = ti0 + p.pad - (p.k - 1);
+    to_lo = to_lo <= 0 ? 0 : (to_lo + p.stride - 1) / p.stride;
+    const int to_hi = min(p.Tout - 1, (ti0 + kGdT - 1 + p.pad) / p.stride);
+    const int rows = max(0, to_hi - to_lo + 1);
+    for (int i = threadIdx.x; i < rows * nco; i += 256) {
+        const int r = i / nco, c = i - r * nco;
+        ds[i] = dy[((int64_t)b * p.Tout + to_lo + r) * p.Cout + g0 * opg + c];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < kGdT * nci; o += 256) {
+        const int tl = o / nci, cl = o - tl * nci;
+        const int ti = ti0 + tl;
+        if (ti >= p.Tin) continue;
+        const int gl = cl / cpg, c = cl - gl * cpg;
+        float acc = 0.f;
+        const int jr = (ti + p.pad) % p.stride;                         // j = jr, jr + s, ...
+        for (int j = jr; j < p.k; j += p.stride) {
+            const int to = (ti + p.pad - j) / p.stride;
+            if (ti + p.pad - j < 0) break;
+            if (to > to_hi || to < to_lo) continue;
+            const float* dr = ds + (to - to_lo) * nco + gl * opg;
+            const float* wr = ws + (gl * opg) * wl + c * p.k + j;
+            for (int q = 0; q < opg; ++q) acc = fmaf(dr[q], wr[q * wl], acc);
+        }
+        dx[((int64_t)b * p.Tin + ti) * p.Cin + g0 * cpg + cl] = acc;
+    }
+}
+
+// dw[co][c][j] += sum_{b, to} dy[b][to][co] * x[b][to*stride + j - pad][g*cpg + c]   (fp32 atomics over (b, time chunks))
+__global__ void __launch_bounds__(256) gconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                                          const GconvP p, const int chunks) {
+    extern __shared__ float sm[];
+    const int cpg = p.Cin / p.groups, opg = p.Cout / p.groups;
+    const int co0 = blockIdx.x * kGcCo;
+    const int nco = min(kGcCo, p.Cout - co0);
+    const int g0 = co0 / opg, ng = (co0 + nco - 1) / opg - g0 + 1;
+    const int nch = ng * cpg;
+    const int win = (kGcT - 1) * p.stride + p.k;
+    float* dsm = sm;                                                    // [kGcT][nco]
+    float* xs = sm + kGcT * kGcCo;                                      // [win][nch]
+    // thread -> (co, c) pairs; each accumulates the k taps of its pairs
+    const int npair = nco * cpg;
+    float acc[2][41];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 41; ++j) acc[u][j] = 0.f;
+    const int tiles_t = (p.Tout + kGcT - 1) / kGcT;
+    const int64_t n_tiles = (int64_t)p.B * tiles_t;
+    for (int64_t tile = blockIdx.y; tile < n_tiles; tile += chunks) {
+        const int b = (int)(tile / tiles_t), to0 = (int)(tile % tiles_t) * kGcT;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kGcT * nco; i += 256) {
+            const int tl = i / nco, cl = i - tl * nco;
+            dsm[i] = (to0 + tl < p.Tout) ? dy[((int64_t)b * p.Tout + to0 + tl) * p.Cout + co0 + cl] : 0.f;
+        }
+        const int ti0 = to0 * p.stride - p.pad;
+        for (int i = threadIdx.x; i < win * nch; i += 256) {
+            const int tt = i / nch, c = i - tt * nch;
+            const int ti = ti0 + tt;
+            xs[i] = (ti >= 0 && ti < p.Tin) ? x[((int64_t)b * p.Tin + ti) * p.Cin + g0 * cpg + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int pr = threadIdx.x + u * 256;
+            if (pr >= npair) continue;
+            const int cl = pr / cpg, c = pr - cl * cpg;
+            const int gl = (co0 + cl) / opg - g0;
+            const float* xc = xs + gl * cpg + c;
+            for (int tl = 0; tl < kGcT; ++tl) {
+                const float d = dsm[tl * nco + cl];
+                const float* xr = xc + (tl * p.stride) * nch;
+#pragma unroll
+                for (int j = 0; j < 41; ++j)
+                    if (j < p.k) acc[u][j] = fmaf(d, xr[j * nch], acc[u][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int pr = threadIdx.x + u * 256;
+        if (pr >= npair) continue;
+        const int cl = pr / cpg, c = pr - cl * cpg;
+        float* out = dw + ((int64_t)(co0 + cl) * cpg + c) * p.k;
+#pragma unroll
+        for (int j = 0; j < 41; ++j)
+            if (j < p.k && acc[u][j] != 0.f) atomicAdd(out + j, acc[u][j]);
+    }
+}
+
+// weight normalisation, one CTA per output channel (row):  w = g * v / ||v||
+__global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
+                                                              float* __restrict__ norms, int len) {
+    __shared__ double red[8];
+    const int r = blockIdx.x;
+    const float* vr = v + (int64_t)r * len;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < len; i += 256) s += (double)vr[i] * vr[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    const float nrm = (float)sqrt(t);
+    if (threadIdx.x == 0 && norms) norms[r] = nrm;
+    const float k = g[r] / nrm;
+    for (int i = threadIdx.x; i < len; i += 256) w[(int64_t)r * len + i] = vr[i] * k;
+}
+
+// dg = sum(dw * v) / ||v||;   dv = g / ||v|| * (dw - v * sum(dw * v) / ||v||^2)     (both ADDED to the outputs)
+__global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ dw,
+                                                              float* __restrict__ dv, float* __restrict__ dg, int len) {
+    __shared__ double red[2][8];
+    const int r = blockIdx.x;
+    const float* vr = v + (int64_t)r * len;
+    const float* dr = dw + (int64_t)r * len;
+    double s = 0.0, d = 0.0;
+    for (int i = threadIdx.x; i < len; i += 256) { s += (double)vr[i] * vr[i]; d += (double)vr[i] * dr[i]; }
+    s = warp_sum(s); d = warp_sum(d);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = d; }
+    __syncthreads();
+    double ts = 0.0, td = 0.0;
+    for (int k = 0; k < 8; ++k) { ts += red[0][k]; td += red[1][k]; }
+    const double nrm = sqrt(ts);
+    if (threadIdx.x == 0) dg[r] += (float)(td / nrm);
+    const float a = (float)(g[r] / nrm), bq = (float)(td / ts);
+    for (int i = threadIdx.x; i < len; i += 256) dv[(int64_t)r * len + i] += a * (dr[i] - vr[i] * bq);
+}
+
+static int gconv_check(const GconvP& p) {
+    AERO_REQUIRE(p.B >= 1 && p.Tin >= 1 && p.Tout >= 1 && p.groups >= 1 && p.Cin % p.groups == 0 && p.Cout % p.groups == 0, "aero_gconv1d: sizes");
+    AERO_REQUIRE(p.k >= 1 && p.k <= 41 && p.stride >= 1 && p.pad >= 0, "aero_gconv1d: k=%d (<= 41) stride=%d", p.k, p.stride);
+    AERO_REQUIRE(p.Tout == (p.Tin + 2 * p.pad - p.k) / p.stride + 1, "aero_gconv1d: Tout=%d inconsistent", p.Tout);
+    const int cpg = p.Cin / p.groups, opg = p.Cout / p.groups;
+    AERO_REQUIRE(cpg <= 8 && (kGcCo % opg == 0 || opg % kGcCo == 0), "aero_gconv1d: %d inputs / %d outputs per group unsupported", cpg, opg);
+    AERO_REQUIRE(p.B <= 65535, "aero_gconv1d: batch too large");
+    return AERO_OK;
+}
+
+static size_t gconv_smem(const GconvP& p, int rows_extra) {
+    const int cpg = p.Cin / p.groups, opg = p.Cout / p.groups;
+    const int ng = kGcCo / opg + 1;
+    const int win = (kGcT - 1) * p.stride + p.k;
+    return sizeof(float) * ((size_t)kGcCo * cpg * p.k + (size_t)(win > rows_extra ? win : rows_extra) * (size_t)(ng * cpg > kGcCo ? ng * cpg : kGcCo) + kGcT * kGcCo);
+}
+
+}  // namespace aero
+
+extern "C" int aero_gconv1d_fwd(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Tin, int32_t Tout, int32_t Cin,
+                                int32_t Cout, int32_t groups, int32_t k, int32_t stride, int32_t pad, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && w && y, "aero_gconv1d_fwd: null argument");
+    const GconvP p{B, Tin, Tout, Cin, Cout, groups, k, stride, pad};
+    int rc = gconv_check(p);
+    if (rc != AERO_OK) return rc;
+    const size_t smem = gconv_smem(p, 0);
+    cudaFuncSetAttribute(gconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(cdiv(Cout, kGcCo), cdiv(Tout, kGcT), B);
+    gconv_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, y, p);
+    return check_launch("aero_gconv1d_fwd");
+}
+
+extern "C" int aero_gconv1d_dgrad(const float* dy, const float* w, float* dx, int32_t B, int32_t Tin, int32_t Tout, int32_t Cin, int32_t Cout,
+                                  int32_t groups, int32_t k, int32_t stride, int32_t pad, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(dy && w && dx, "aero_gconv1d_dgrad: null argument");
+    const GconvP p{B, Tin, Tout, Cin, Cout, groups, k, stride, pad};
+    int rc = gconv_check(p);
+    if (rc != AERO_OK) return rc;
+    const int opg = Cout / groups;
+    const int gt = kGcCo / opg > 0 ? kGcCo / opg : 1;
+    const int rows = (kGdT + k) / stride + 2;
+    const size_t smem = gconv_smem(p, rows) + sizeof(float) * (size_t)rows * kGcCo;
+    cudaFuncSetAttribute(gconv_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(cdiv(groups, gt), cdiv(Tin, kGdT), B);
+    gconv_dgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dy, w, dx, p);
+    return check_launch("aero_gconv1d_dgrad");
+}
+
+extern "C" int aero_gconv1d_wgrad(const float* x, const float* dy, float* dw, int32_t B, int32_t Tin, int32_t Tout, int32_t Cin, int32_t Cout,
+                                  int32_t groups, int32_t k, int32_t stride, int32_t pad, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && dy && dw, "aero_gconv1d_wgrad: null argument");
+    const GconvP p{B, Tin, Tout, Cin, Cout, groups, k, stride, pad};
+    int rc = gconv_check(p);
+    if (rc != AERO_OK) return rc;
+    const int cpg = Cin / groups;
+    AERO_REQUIRE(kGcCo * cpg <= 512, "aero_gconv1d_wgrad: at most 8 input channels per group");
+    const size_t smem = gconv_smem(p, 0);
+    cudaFuncSetAttribute(gconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t n_tiles = (int64_t)B * cdiv(Tout, kGcT);
+    int chunks = (148 * 4) / cdiv(Cout, kGcCo) + 1;
+    if (chunks > n_tiles) chunks = (int)n_tiles;
+    if (chunks > 65535) chunks = 65535;
+    dim3 grid(cdiv(Cout, kGcCo), chunks);
+    gconv_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, dy, dw, p, chunks);
+    return check_launch("aero_gconv1d_wgrad");
+}
+
+extern "C" int aero_weight_norm_fwd(const float* v, const float* g, float* w, int32_t rows, int32_t len, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(v && g && w && rows >= 1 && len >= 1, "aero_weight_norm_fwd: bad argument");
+    weight_norm_fwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(v, g, w, nullptr, len);
+    return check_launch("aero_weight_norm_fwd");
+}
+
+extern "C" int aero_weight_norm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t rows, int32_t len,
+                                    aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(v && g && dw && dv && dg && rows >= 1 && len >= 1, "aero_weight_norm_bwd: bad argument");
+    weight_norm_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(v, g, dw, dv, dg, len);
+    return check_launch("aero_weight_norm_bwd");
+}

@@ -130,7 +130,7 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ conv (tap-GEMM) op
     def conv(self, x1, x2, C1, C2, wname, bname, cv, B, F_in, F_out, T, N, *, wslice=None, residual=None, samp_affine=None,
-             stats=None, stats_mode=0, groups=1, w_override=None, b_override=None, o_s=None):
+             stats=None, stats_mode=0, groups=1, w_override=None, b_override=None, o_s=None, T_in=None):
         """out[B,F_out,T,N] = tap-GEMM(cat[x1 (C1 channels), x2 (C2)]) + bias (+ residual) (* samp_affine); records its backward.
         wname / bname: parameter names (PyTorch layout: Conv [N,K,kf,kt] / ConvTranspose [K,N,kf,1]); wslice: slice of the
         weight's input-channel axis actually used (decoder 0 keeps only the skip half).  w_override / b_override =
@@ -159,7 +159,8 @@ class TrainEngine:
         os_ = o_s or (F_out * T * N, T * N, N)
         out = self._new(B * F_out * T * N) if o_s is None else self._new(B * os_[0])
         geo = dict(B=B, F_out=F_out, T=T, N=N, C1=C1, C2=C2, F_in=F_in, mode=mode, kf=cv.kf, kt=cv.kt, stride_f=cv.stride_f, pad_f=cv.pad_f,
-                   dil_t=cv.dil_t, pad_t=cv.pad_t, f_off=cv.f_off, o_s=os_)
+                   dil_t=cv.dil_t, pad_t=cv.pad_t, f_off=cv.f_off, o_s=os_, T_in=T_in)
+        Ti = T if T_in is None else T_in        # input frames (differs from T only for un-padded time kernels: the discriminator's first layer)
         p = self._tg(stats_mode=stats_mode, groups=groups, r_s=os_ if residual is not None else None, **geo)
         self._gemm_call(p, out, wp, a1=x1, a2=x2, bias=bias, residual=residual, samp_affine=samp_affine, stats=stats)
 
@@ -200,8 +201,8 @@ class TrainEngine:
                     ws = w4[:, lo:lo + cs]
                     if cv.stride_f == 1:
                         wd = pack_taps(ws.flip(2, 3).permute(1, 0, 2, 3).reshape(cs, N, cv.kf * cv.kt))
-                        pd = self._tg(B=B, F_out=F_in, T=T, N=cs, C1=N, F_in=F_out, mode=TAPS_CONV, kf=cv.kf, kt=cv.kt,
-                                      pad_f=cv.kf - 1 - cv.pad_f, dil_t=cv.dil_t, pad_t=cv.dil_t * (cv.kt - 1) - cv.pad_t, a1_s=os_)
+                        pd = self._tg(B=B, F_out=F_in, T=Ti, N=cs, C1=N, F_in=F_out, mode=TAPS_CONV, kf=cv.kf, kt=cv.kt,
+                                      pad_f=cv.kf - 1 - cv.pad_f, dil_t=cv.dil_t, pad_t=cv.dil_t * (cv.kt - 1) - cv.pad_t, a1_s=os_, T_in=T)
                     else:
                         assert cv.kt == 1
                         wd = pack_taps(ws[:, :, :, 0].permute(1, 0, 2))
@@ -211,7 +212,7 @@ class TrainEngine:
                     wd = pack_taps(w4[lo:lo + cs, :, :, 0])                 # [cs, N, kf] = [N', K', taps]
                     pd = self._tg(B=B, F_out=F_in, T=T, N=cs, C1=N, F_in=F_out, mode=TAPS_CONV, kf=cv.kf, stride_f=cv.stride_f,
                                   pad_f=cv.f_off, a1_s=os_)
-                dx = self._new(B * F_in * T * cs)
+                dx = self._new(B * F_in * Ti * cs)
                 self._gemm_call(pd, dx, wd, a1=dy)
                 self.acc(src, dx)
         self.tape.append(bwd)

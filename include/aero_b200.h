@@ -184,7 +184,7 @@ int aero_sample_norm_fwd(const float* x, const double* stats, float* y, float* s
  *     AERO_NA_GLU_SCALE_RES y[c] = residual[c] + scale[c] * glu(g)[c].
  */
 enum { AERO_NA_NONE = 0, AERO_NA_GELU = 1, AERO_NA_GLU = 2, AERO_NA_SNAKE = 3, AERO_NA_GLU_SCALE_RES = 4,
-       AERO_NA_RELU = 5 /* training entry points only */ };
+       AERO_NA_RELU = 5, AERO_NA_LEAKY = 6 /* LeakyReLU(0.2) */ /* 5, 6: training entry points only */ };
 enum { AERO_NA_NO_NORM = 16 };      /* aero_norm_act_params.flags, training entry points: skip the normalisation (activation only) */
 typedef struct {
     int32_t B, F_in, F_out, f_off, T, C;
@@ -375,6 +375,22 @@ int aero_lstm_fold(const float* dgin_w, float* dgin, int32_t rows, int32_t T, in
 int aero_local_attn_train_fwd(const float* qkvd, float* out, float* lse, const aero_attn_params* p, aero_stream_t stream);
 int aero_local_attn_bwd(const float* qkvd, const float* out, const float* lse, const float* dout, float* dqkvd,
                         const aero_attn_params* p, aero_stream_t stream);
+
+/* MelGAN multi-scale discriminator (reference src/models/discriminators.py:14-78): grouped strided
+ * Conv1d (k <= 41, <= 8 input channels per group) on channels-last tensors x [B][Tin][Cin] -> y [B][Tout][Cout], weights in
+ * PyTorch's layout w [Cout][Cin/groups][k]; Tout = (Tin + 2 pad - k) / stride + 1.  dgrad writes dx; wgrad ADDS into dw (caller zeroes).
+ * The dense layers of the discriminator (k = 15 / 5 / 3) run on aero_tapgemm_fwd / aero_tapgemm_wgrad. */
+int aero_gconv1d_fwd(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Tin, int32_t Tout, int32_t Cin,
+                     int32_t Cout, int32_t groups, int32_t k, int32_t stride, int32_t pad, aero_stream_t stream);
+int aero_gconv1d_dgrad(const float* dy, const float* w, float* dx, int32_t B, int32_t Tin, int32_t Tout, int32_t Cin, int32_t Cout,
+                       int32_t groups, int32_t k, int32_t stride, int32_t pad, aero_stream_t stream);
+int aero_gconv1d_wgrad(const float* x, const float* dy, float* dw, int32_t B, int32_t Tin, int32_t Tout, int32_t Cin, int32_t Cout,
+                       int32_t groups, int32_t k, int32_t stride, int32_t pad, aero_stream_t stream);
+/* Weight normalisation (torch.nn.utils.weight_norm, reference modules.py WNConv1d): w[r][:] = g[r] * v[r][:] / ||v[r][:]||, and its
+ * backward, which ADDS  dg[r] += <dw[r], v[r]> / ||v[r]||  and  dv[r] += g[r]/||v[r]|| * (dw[r] - v[r] <dw[r], v[r]> / ||v[r]||^2). */
+int aero_weight_norm_fwd(const float* v, const float* g, float* w, int32_t rows, int32_t len, aero_stream_t stream);
+int aero_weight_norm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t rows, int32_t len,
+                         aero_stream_t stream);
 
 /* Fused multi-tensor Adam (torch.optim.Adam semantics, no amsgrad / weight decay; reference train.py:83).  chunk_table: device
  * array of n_chunks records {float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64 count}; one CTA per

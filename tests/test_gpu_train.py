@@ -125,3 +125,41 @@ def test_train_step_with_fused_adam_reduces_the_loss():
         losses.append(float(loss))
     print("losses:", losses)
     assert losses[-1] < losses[0]
+
+
+def test_melgan_discriminator_matches_reference(golden_dir):
+    """aero_b200.discriminator.Discriminator (grouped-conv / weight-norm kernels) against the
+    reference's features and gradients (tests/golden/disc_melgan.npz, fp64 reference)."""
+    from util import disc_recipe_state
+    from aero_b200.discriminator import Discriminator
+    g = np.load(os.path.join(golden_dir, "disc_melgan.npz"))
+    d = Discriminator(3, 16, 4, 4)
+    assert len(d.state_dict()) == 63 and sum(p.numel() for p in d.parameters()) == 16924086
+    d.load_state_dict(disc_recipe_state(d.state_dict()))
+    assert weights_digest(d.state_dict()) == pytest.approx(float(g["digest"]), rel=1e-12)
+    d = d.cuda()
+    B, L = int(g["B"]), int(g["L"])
+    x = white_noise((B, 1, L), seed=SEED + 3).cuda().requires_grad_(True)
+    feats = d(x)
+    loss = 0.0
+    worst_f = 0.0
+    for i, scale in enumerate(feats):
+        assert len(scale) == 7
+        for j, f in enumerate(scale):
+            assert tuple(f.shape) == tuple(int(v) for v in g[f"f_shape/{i}/{j}"])
+            flat = f.detach().reshape(-1).cpu()
+            worst_f = max(worst_f, rel_l2(flat[torch.from_numpy(g[f"f_idx/{i}/{j}"].astype(np.int64))], g[f"f_val/{i}/{j}"]))
+            loss = loss + (f * white_noise(tuple(f.shape), seed=SEED + 1000 + 10 * i + j).cuda()).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    e_dx = rel_l2(x.grad.cpu(), g["dx"])
+    rows = []
+    gmax = max(float(g[k]) for k in g.files if k.startswith("g_rms/"))
+    for name, p in d.named_parameters():
+        ref = torch.from_numpy(g["g_val/" + name]).double()
+        got = p.grad.reshape(-1).cpu().double()[torch.from_numpy(g["g_idx/" + name].astype(np.int64))]
+        rows.append((float((got - ref).norm()) / max(float(ref.norm()), 1e-4 * gmax * ref.numel() ** 0.5), name))
+    rows.sort(reverse=True)
+    print(f"discriminator: features {worst_f:.2e}, loss {float(loss):.6e} (ref {float(g['loss']):.6e}), d input {e_dx:.2e}; worst parameter gradients:",
+          [(f"{a:.1e}", b) for a, b in rows[:4]])
+    assert worst_f < 2e-5 and e_dx < 1e-4 and rows[0][0] < 1e-3

@@ -87,3 +87,22 @@ def import_reference():
         sys.modules.update(saved)
     assert all(ref_root in m.__file__ for m in mods.values())
     return mods
+
+
+def disc_recipe_state(state, seed=SEED):
+    """Deterministic weights for the MelGAN discriminator (reference and aero_b200 share the state_dict keys): weight_v ~
+    N(0, 0.02^2) as the reference's `weights_init`, weight_g = ||v|| moved off its init by up to +-30 %, biases N(0, 0.05^2).
+    Pure function of (key order, shapes, seed), like `trained_like_`."""
+    g = torch.Generator().manual_seed(seed + 5)
+    out = {}
+    for k, v in state.items():
+        if k.endswith("weight_v"):
+            out[k] = 0.02 * torch.randn(v.shape, generator=g)
+    for k, v in state.items():
+        r = torch.randn(v.shape, generator=g)
+        if k.endswith("weight_g"):
+            vv = out[k[:-1] + "v"]
+            out[k] = vv.flatten(1).norm(dim=1).view(v.shape) * (1.0 + 0.3 * torch.tanh(r))
+        elif k.endswith("bias"):
+            out[k] = 0.05 * r
+    return {k: out[k].to(state[k].dtype) for k in state}
