@@ -130,3 +130,64 @@ class GeneratorTrainer:
             self.backward(eng, pr.grad)
             self.opt.step(grad_scale=1.0 / self.world)
         return loss.detach()
+
+
+class GanTrainer(GeneratorTrainer):
+    """The reference's full step with ``adversarial: True`` (``conf/experiment/aero_*.yaml``, ``src/solver.py:292-342,475-520,602-612``):
+    generator loss = MR-STFT + hinge adversarial + 100 x feature matching against the MelGAN multi-scale discriminator, then the
+    discriminator's hinge loss on (detached estimate, target); both optimisers are fused Adams; under ``torch.distributed`` the
+    discriminator's gradients are summed in one flat NCCL all-reduce as well."""
+
+    def __init__(self, model, disc, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, features_loss_lambda=100.0, n_layers=4, pieces=4):
+        super().__init__(model, lr=lr, betas=betas, eps=eps, pieces=pieces)
+        self.disc = disc
+        self.lmbda, self.n_layers = features_loss_lambda, n_layers
+        dps = list(disc.parameters())
+        self.d_flat = torch.zeros(sum(p.numel() for p in dps), device=dps[0].device)
+        off = 0
+        for p in dps:
+            p.grad = self.d_flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.d_opt = FusedAdam(dps, lr=lr, betas=betas, eps=eps)
+
+    def generator_losses(self, pr, hr, stft_loss):
+        """reference solver.py:430-473,499-520"""
+        relu, l1 = torch.nn.functional.relu, torch.nn.functional.l1_loss
+        sc, mag = stft_loss(pr.squeeze(1), hr.squeeze(1))
+        fake, real = self.disc(pr), self.disc(hr)
+        w = (4.0 / (self.n_layers + 1)) / self.disc.num_D
+        feat = 0.0
+        for i in range(self.disc.num_D):
+            for j in range(len(fake[i]) - 1):
+                feat = feat + w * l1(fake[i][j], real[i][j].detach())
+        adv = sum(relu(1 - s[-1]).mean() for s in fake)
+        return {"stft": sc + mag, "adversarial": adv, "features": self.lmbda * feat}
+
+    def discriminator_loss(self, pr, hr):
+        """reference solver.py:489-497"""
+        relu = torch.nn.functional.relu
+        fake, real = self.disc(pr.detach()), self.disc(hr)
+        return sum(relu(1 + s[-1]).mean() for s in fake) + sum(relu(1 - s[-1]).mean() for s in real)
+
+    def step(self, lr_batch, hr_batch, stft_loss):
+        model = self.model
+        model.train()
+        self.zero_grad()
+        with torch.cuda.device(lr_batch.device):
+            eng = TrainEngine(model)
+            wave, _ = eng.forward(lr_batch)
+            pr = wave.detach().requires_grad_(True)
+            g_losses = self.generator_losses(pr, hr_batch, stft_loss)
+            g_total = sum(g_losses.values())
+            g_total.backward()
+            self.backward(eng, pr.grad)
+            self.opt.step(grad_scale=1.0 / self.world)
+            # discriminator step (its gradients from the generator's backward above are discarded, as disc_optimizer.zero_grad() does)
+            self.d_flat.zero_()
+            d_loss = self.discriminator_loss(pr, hr_batch)
+            d_loss.backward()
+            if self.world > 1:
+                dist.all_reduce(self.d_flat)
+                self.allreduce_bytes += self.d_flat.numel() * 4
+            self.d_opt.step(grad_scale=1.0 / self.world)
+        return {k: v.detach() for k, v in g_losses.items()} | {"discriminator": d_loss.detach()}

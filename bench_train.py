@@ -86,10 +86,17 @@ def main(args):
         dist.init_process_group("nccl", device_id=dev)
     from aero_b200 import cabi
     from aero_b200.losses import MultiResolutionSTFTLoss
-    from aero_b200.trainer import GeneratorTrainer
+    from aero_b200.trainer import GanTrainer, GeneratorTrainer
+    from aero_b200.discriminator import Discriminator
     lib = cabi.load()
     model = B.build_model(B.CONFIGS["4-16"]).to(dev).train()
-    trainer = GeneratorTrainer(model, lr=3e-4, betas=(0.9, 0.999))
+    adversarial = not os.environ.get("AERO_TRAIN_NO_GAN")
+    if adversarial:
+        torch.manual_seed(B.SEED + 1)
+        disc = Discriminator(3, 16, 4, 4).to(dev)            # reference conf/experiment/aero_*.yaml melgan_discriminator
+        trainer = GanTrainer(model, disc, lr=3e-4, betas=(0.9, 0.999))
+    else:
+        trainer = GeneratorTrainer(model, lr=3e-4, betas=(0.9, 0.999))
     mrstft = MultiResolutionSTFTLoss()
     bsz = args.batch or BATCH
     gen = torch.Generator().manual_seed(B.SEED + rank)
@@ -108,17 +115,23 @@ def main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def one_step(a, b):
+        if adversarial:
+            out = trainer.step(a, b, mrstft)
+            return out["stft"]
+        return trainer.step(a, loss_fn_for(b))
+
     warm = max(args.warmup, 3)
     losses = []
     for _ in range(warm):
-        losses.append(trainer.step(lr_d, loss_fn_for(hr_d)))
+        losses.append(one_step(lr_d, hr_d))
     barrier()
     sampler = B.ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = lib.aero_launch_count()
     ar0 = trainer.allreduce_bytes
-    ms_dev = B.timed_steps(lambda: losses.append(trainer.step(lr_d, loss_fn_for(hr_d))), args.steps, barrier)
+    ms_dev = B.timed_steps(lambda: losses.append(one_step(lr_d, hr_d)), args.steps, barrier)
     launches = lib.aero_launch_count() - l0
     ar_bytes = (trainer.allreduce_bytes - ar0) / args.steps
     sampler.paused = True
@@ -128,7 +141,7 @@ def main(args):
     marks[0].record()
     for i in range(args.steps):
         a, b = host_lr.to(dev, non_blocking=True), host_hr.to(dev, non_blocking=True)
-        loss = trainer.step(a, loss_fn_for(b))
+        loss = one_step(a, b)
         host_loss.copy_(loss.float(), non_blocking=True)
         marks[i + 1].record()
         torch.cuda.current_stream().synchronize()
@@ -148,10 +161,12 @@ def main(args):
         line = {"metric": "audio-seconds/sec training step", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (exact-fp32 SIMT tap-GEMMs for forward, dgrad and wgrad; fp64 reduction accumulators)", "data": "synthetic",
-                "config": {"workload": f"{EXP} training step (generator forward in train mode + MR-STFT loss + backward + Adam), batch {bsz}/GPU "
+                "config": {"workload": f"{EXP} training step (G + MelGAN-D + MR-STFT, Adam: reference adversarial config), batch {bsz}/GPU "
                                        f"x 2 s paired white-noise clips (BASELINE configs[3])", "config_key": "train", "global_batch": total,
                            "parallelism": f"data-parallel x{world}: flat-buffer NCCL all-reduce of the generator gradients, overlapped with backward",
-                           "adversarial": False,
+                           "adversarial": bool(adversarial),
+                           "step": ("generator forward (train) + MR-STFT + 3 MelGAN-discriminator forwards + G backward + Adam + D backward + Adam"
+                                    if adversarial else "generator forward (train) + MR-STFT + backward + Adam"),
                            "l2": "activations saved for backward (~1 GB/step) exceed the 126 MB L2; no explicit flush"},
                 "e2e": {"value": total * SECONDS / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                         "statistic": "median of per-step device times (H2D of lr+hr, step, D2H of the loss, one stream sync per step)",
