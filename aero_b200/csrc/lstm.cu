@@ -137,14 +137,16 @@ static int launch_lstm(const float* gin, const float* bias_pad, const float* whh
     return check_launch("aero_lstm_rec_fwd");
 }
 
-int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
+int lstm_tc_launch(const void* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
                    cudaStream_t st);
 }  // namespace aero
 
-extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const void* whh, void* hout,
+extern "C" int aero_lstm_rec_fwd(const void* gin_, const float* bias_pad, const void* whh, void* hout,
                                  const aero_lstm_params* p, aero_stream_t stream) {
     using namespace aero;
-    AERO_REQUIRE(gin && whh && hout && p, "aero_lstm_rec_fwd: null argument");
+    AERO_REQUIRE(gin_ && whh && hout && p, "aero_lstm_rec_fwd: null argument");
+    AERO_REQUIRE(!(p->flags & AERO_TG_A_F16) || p->precision == 1, "aero_lstm_rec_fwd: FP16 gate pre-activations need the tcgen05 recurrence");
+    const float* gin = static_cast<const float*>(gin_);
     AERO_REQUIRE(p->rows >= 1 && p->T >= 1 && p->n_win >= 1 && p->steps >= 1, "aero_lstm_rec_fwd: bad sizes");
     AERO_REQUIRE(p->in_windowed || bias_pad, "aero_lstm_rec_fwd: bias_pad required for un-windowed input");
     AERO_REQUIRE(p->n_win == 1 || (p->win_stride >= 2 && p->win_stride % 2 == 0), "aero_lstm_rec_fwd: win_stride");
@@ -152,7 +154,7 @@ extern "C" int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (p->precision == 1) {
         AERO_REQUIRE(bias_pad, "aero_lstm_rec_fwd: bias_pad required");
-        return lstm_tc_launch(gin, bias_pad, whh, hout, *p, st);
+        return lstm_tc_launch(gin_, bias_pad, whh, hout, *p, st);
     }
     switch (p->H) {
         case 12: return launch_lstm<12, 16>(gin, bias_pad, (const float*)whh, hout, *p, st);

@@ -113,9 +113,9 @@ __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
 // GPT: gates per 128-row tile.  NEW: cell-update warps (NEW/4 per TMEM lane quarter, each owning 4*SEQ/NEW sequences).
 // SEQ: sequences per CTA (8 or 16).  ROWB: bytes of K per operand row of a chunk (128 = 64 fp16, SWIZZLE_128B; 64 = 32 fp16,
 // SWIZZLE_64B).  MINB: CTAs per SM the register budget is set for.
-template <int GPT, int NEW, int SEQ, int ROWB, int MINB, typename TO>
+template <int GPT, int NEW, int SEQ, int ROWB, int MINB, typename TO, typename TG>
 __global__ void __launch_bounds__(64 + 32 * NEW, MINB)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ gin, const float* __restrict__ bias_pad,
+lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const TG* __restrict__ gin, const float* __restrict__ bias_pad,
                TO* __restrict__ hout, const aero_lstm_params p, const int nK) {
     constexpr int NM = 4 / GPT;                          // M tiles
     constexpr int CPW = 32 / GPT;                        // cells per warp
@@ -278,9 +278,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
         if (kRegPrefetch) {
 #pragma unroll
             for (int i = 0; i < kNS; ++i) {
-                const float* src = ((unsigned)(0 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+                const bool real = (unsigned)(0 - g_lo[i]) < (unsigned)g_len[i];
 #pragma unroll
-                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * gtile];
+                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = real ? ldf(gin + goff[i] + m * gtile) : bptr[m * gtile];
                 goff[i] += gstep;
             }
         }
@@ -295,18 +295,18 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
                 if (s + 1 < p.steps) {
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) {
-                        const float* src = ((unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+                        const bool real = (unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i];
 #pragma unroll
-                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = src[m * gtile];
+                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = real ? ldf(gin + goff[i] + m * gtile) : bptr[m * gtile];
                         goff[i] += gstep;
                     }
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < kNS; ++i) {
-                    const float* src = ((unsigned)(s - g_lo[i]) < (unsigned)g_len[i]) ? gin + goff[i] : bptr;
+                    const bool real = (unsigned)(s - g_lo[i]) < (unsigned)g_len[i];
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) gi[m][i] = src[m * gtile];
+                    for (int m = 0; m < NM; ++m) gi[m][i] = real ? ldf(gin + goff[i] + m * gtile) : bptr[m * gtile];
                     goff[i] += gstep;
                 }
             }
@@ -380,13 +380,20 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict
 }
 
 template <int GPT, int NEW, int SEQ, int ROWB, int MINB, typename TO>
-static void lstm_tc_go(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mW, const float* gin, const float* bias_pad, void* hout,
+static void lstm_tc_go(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mW, const void* gin, const float* bias_pad, void* hout,
                        const aero_lstm_params& p, int nK) {
-    cudaFuncSetAttribute(lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO><<<grid, 64 + 32 * NEW, smem, st>>>(mW, gin, bias_pad, static_cast<TO*>(hout), p, nK);
+    if (p.flags & AERO_TG_A_F16) {          // gate pre-activations stored in FP16
+        cudaFuncSetAttribute(lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO, __half><<<grid, 64 + 32 * NEW, smem, st>>>(mW, static_cast<const __half*>(gin), bias_pad,
+                                                                                              static_cast<TO*>(hout), p, nK);
+    } else {
+        cudaFuncSetAttribute(lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lstm_tc_kernel<GPT, NEW, SEQ, ROWB, MINB, TO, float><<<grid, 64 + 32 * NEW, smem, st>>>(mW, static_cast<const float*>(gin), bias_pad,
+                                                                                             static_cast<TO*>(hout), p, nK);
+    }
 }
 
-int lstm_tc_launch(const float* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
+int lstm_tc_launch(const void* gin, const float* bias_pad, const void* whh_r, void* hout, const aero_lstm_params& p,
                    cudaStream_t st) {
     const int H = p.H;
     if (H % 4 || H <= 32 || H > 128) {

@@ -136,6 +136,10 @@ class AeroEngine:
         # taken from the stored values.  Halves the bytes of every norm_act pass and of the GEMM writes that feed them
         # (tests/err_budget_emu.py: +6 % end-to-end error, paid for by keeping the last decoder layer's GLU output in fp32)
         self.raw16 = True
+        # precision 2 + tcgen05 LSTM: the gate pre-activations (input projections, 8H columns per frame: the widest tensors of the
+        # bottleneck) are stored in FP16 too; the recurrence adds them to its fp32 accumulators (tests/err_budget_emu.py: no
+        # measurable change of the end-to-end error)
+        self.gin16 = True
         self.lstm_tc = True         # tcgen05 LSTM recurrence (re-ordered gate layout) when precision >= 1
         self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1
@@ -458,8 +462,8 @@ class AeroEngine:
                   tc=False):
         o16 = hout.dtype == torch.float16
         p = cabi.LstmParams(rows, T, H, n_win, steps, stride, in_windowed, out_windowed,
-                            (cabi.TG_ROUND_TF32 if (self.precision >= 1 and not o16) else 0) | (cabi.TG_OUT_F16 if o16 else 0),
-                            1 if tc else 0)
+                            (cabi.TG_ROUND_TF32 if (self.precision >= 1 and not o16) else 0) | (cabi.TG_OUT_F16 if o16 else 0) |
+                            (cabi.TG_A_F16 if gin.dtype == torch.float16 else 0), 1 if tc else 0)
         cabi.check(self.lib.aero_lstm_rec_fwd(_ptr(gin), _ptr(bias_pad), _ptr(whh), _ptr(hout), C.byref(p),
                                               self._stream()), self.lib)
 
@@ -613,12 +617,13 @@ class AeroEngine:
         # (tile / lane order, FP16) for the tcgen05 recurrence
         G = 8 * H
         whh0, whh1 = (W[f"{o}.lstm0r.whh"], W[f"{o}.lstm1r.whh"]) if tc else (W[f"{o}.lstm0.whh"], W[f"{o}.lstm1.whh"])
-        gin1 = self._buf(tag + ".gin1", rows * T, G)
+        gdt = torch.float16 if (tc and self.precision == 2 and self.gin16 and h.dtype == torch.float16) else torch.float32
+        gin1 = self._buf(tag + ".gin1", rows * T, G, dtype=gdt)
         self._gemm_flat(gin1, h, W[f"{o}.lstm0.ih.w"], rows * T, H, G, bias=W[f"{o}.lstm0.b"])
         h1 = self._buf(tag + ".h1", n_seq * steps, 2 * H, dtype=self._adt(2 * H))
         self._lstm_rec(gin1, W[f"{o}.lstm0.b"], whh0, h1, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
                        stride=stride, in_windowed=0, out_windowed=1, tc=tc)
-        gin2 = self._buf(tag + ".gin2", n_seq * steps, G)
+        gin2 = self._buf(tag + ".gin2", n_seq * steps, G, dtype=gdt if h1.dtype == torch.float16 else torch.float32)
         self._gemm_flat(gin2, h1, W[f"{o}.lstm1.ih.w"], n_seq * steps, 2 * H, G, bias=W[f"{o}.lstm1.b"])
         h2 = self._buf(tag + ".h2", rows * T, 2 * H, dtype=self._adt(2 * H))
         self._lstm_rec(gin2, W[f"{o}.lstm1.b"], whh1, h2, rows=rows, T=T, H=H, n_win=n_win, steps=steps,
@@ -767,7 +772,7 @@ class AeroEngine:
                     torch.cuda.is_current_stream_capturing():
                 return self._forward(mix, return_spec, return_lr_spec)
             key = (tuple(mix.shape), self._weights_version(), self.precision, self.fp32_tags, self.lstm_tc, self.fuse_pre_ftb,
-                   self.snake, self.raw16)
+                   self.snake, self.raw16, self.gin16)
             entry = self._graphs.get(key)
             if entry is None and self.use_graph == "auto":
                 n = self._seen.get(key, 0)

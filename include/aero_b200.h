@@ -248,7 +248,8 @@ typedef struct {
     int32_t rows, T, H;
     int32_t n_win, steps, win_stride;
     int32_t in_windowed, out_windowed;
-    int32_t flags;                    /* AERO_TG_ROUND_TF32: round the stored fp32 h to TF32; AERO_TG_OUT_F16: hout is FP16 */
+    int32_t flags;                    /* AERO_TG_ROUND_TF32: round the stored fp32 h to TF32; AERO_TG_OUT_F16: hout is FP16;
+                                         AERO_TG_A_F16 (precision 1 only): gin is FP16 (bias_pad stays fp32) */
     int32_t precision;                /* 0: fp32 SIMT recurrence (layouts above);
                                          1: tcgen05 recurrence, FP16 operands (h in (-1,1), W_hh O(1): same 10-bit mantissa as TF32), fp32
                                             accumulate.  `gin` / `bias_pad` keep the layout above; only `whh` changes: FP16
@@ -257,7 +258,7 @@ typedef struct {
                                             gates (2t, 2t+1), in each group of 32 rows rows 0-15 carry gate 2t and rows 16-31 gate 2t+1
                                             of the same 16 cells (zero rows beyond H, zero columns beyond H).  H % 4 == 0, 32 < H <= 96. */
 } aero_lstm_params;
-int aero_lstm_rec_fwd(const float* gin, const float* bias_pad, const void* whh, void* hout,
+int aero_lstm_rec_fwd(const void* gin, const float* bias_pad, const void* whh, void* hout,
                       const aero_lstm_params* p, aero_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

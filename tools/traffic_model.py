@@ -70,7 +70,7 @@ class DryEngine(AeroEngine):
     def _norm_act(self, x, stats, gamma, beta, y, *, B, F_in, T, C_, groups, scope, op, F_out=None, f_off=0, residual=None, **kw):
         F_out = F_in if F_out is None else F_out
         co = C_ // 2 if op in (cabi.NA_GLU, cabi.NA_GLU_SCALE_RES) else C_
-        rd = 4.0 * B * F_out * T * C_ + (y.element_size() * B * F_out * T * co if residual is not None else 0)
+        rd = x.element_size() * B * F_out * T * C_ + (y.element_size() * B * F_out * T * co if residual is not None else 0)
         self.log.append((f"norm_act<{op}>", 0.0, rd, y.element_size() * B * F_out * T * co, 0))
         return y
 
