@@ -88,6 +88,10 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
         : "memory");
 }
 
+template <typename T> __device__ __forceinline__ T to_storage(float v);
+template <> __device__ __forceinline__ float to_storage<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half to_storage<__half>(float v) { return __float2half_rn(v); }
+
 template <int NSQ>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NSQ]);
 template <>
@@ -274,13 +278,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const TG* __restrict__ 
         // requested at the top of step s and consumed a whole step later.  GPT == 2 (two CTAs per SM, register-tight): the
         // loads stay at the top of their own step, but step s+1's lines are pulled into L2 a step ahead.
         constexpr bool kRegPrefetch = (GPT == 1);
-        float gn[kRegPrefetch ? NM : 1][kRegPrefetch ? kNS : 1];
+        // (kept in the storage type: converting an FP16 value at load time would make the load's result a dependency of the
+        // same step and forfeit the step of latency hiding)
+        TG gn[kRegPrefetch ? NM : 1][kRegPrefetch ? kNS : 1];
+        const TG* const bptr_g = nullptr;
+        (void)bptr_g;
         if (kRegPrefetch) {
 #pragma unroll
             for (int i = 0; i < kNS; ++i) {
                 const bool real = (unsigned)(0 - g_lo[i]) < (unsigned)g_len[i];
 #pragma unroll
-                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = real ? ldf(gin + goff[i] + m * gtile) : bptr[m * gtile];
+                for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = real ? gin[goff[i] + m * gtile] : to_storage<TG>(bptr[m * gtile]);
                 goff[i] += gstep;
             }
         }
@@ -290,14 +298,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const TG* __restrict__ 
 #pragma unroll
                 for (int i = 0; i < kNS; ++i) {
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) gi[m][i] = gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0];
+                    for (int m = 0; m < NM; ++m) gi[m][i] = ldf(&gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0]);
                 }
                 if (s + 1 < p.steps) {
 #pragma unroll
                     for (int i = 0; i < kNS; ++i) {
                         const bool real = (unsigned)(s + 1 - g_lo[i]) < (unsigned)g_len[i];
 #pragma unroll
-                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = real ? ldf(gin + goff[i] + m * gtile) : bptr[m * gtile];
+                        for (int m = 0; m < NM; ++m) gn[kRegPrefetch ? m : 0][kRegPrefetch ? i : 0] = real ? gin[goff[i] + m * gtile] : to_storage<TG>(bptr[m * gtile]);
                         goff[i] += gstep;
                     }
                 }

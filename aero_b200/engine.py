@@ -136,10 +136,11 @@ class AeroEngine:
         # taken from the stored values.  Halves the bytes of every norm_act pass and of the GEMM writes that feed them
         # (tests/err_budget_emu.py: +6 % end-to-end error, paid for by keeping the last decoder layer's GLU output in fp32)
         self.raw16 = True
-        # precision 2 + tcgen05 LSTM: the gate pre-activations (input projections, 8H columns per frame: the widest tensors of the
-        # bottleneck) are stored in FP16 too; the recurrence adds them to its fp32 accumulators (tests/err_budget_emu.py: no
-        # measurable change of the end-to-end error)
-        self.gin16 = True
+        # precision 2 + tcgen05 LSTM: optionally store the gate pre-activations (input projections, 8H columns per frame) in FP16
+        # too.  Accuracy-neutral (tests/err_budget_emu.py) but measured SLOWER on B200: the recurrence reads them with scalar
+        # loads (one gate of one cell per lane), and 2-byte loads cost 307 -> 336 us per H = 96 launch while the projection
+        # GEMMs gain only ~0.05 ms per step (tools/kprof.py lstm96 / lstm48, round 2) -- off.
+        self.gin16 = False
         self.lstm_tc = True         # tcgen05 LSTM recurrence (re-ordered gate layout) when precision >= 1
         self.fuse_pre_ftb = True    # encoder layer 0: evaluate FTB through the linear pre_conv (csrc/ftb_lin.cu)
         self.fp32_tags = ()         # tap-GEMM tags (prefix match) forced onto the exact-fp32 path even when precision == 1

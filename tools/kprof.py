@@ -47,13 +47,15 @@ def run_lstm(args):
     tc = args.precision >= 1
     G = 8 * H
     gin = torch.randn(rows * n_win * steps, G, device="cuda")
+    if os.environ.get("KPROF_GIN16"):
+        gin = gin.half()
     bias = torch.randn(G, device="cuda")
     whh = torch.randn(2, 4 * H, H) / math.sqrt(H)
     if tc:
         src, ok = lstm_gate_reorder(H)
         whh = lstm_whh_fp16(torch.cat([torch.where(ok[:, None], whh[d][src], torch.zeros(())) for d in range(2)], 0))
     whh = whh.cuda()
-    hout = torch.zeros(rows * T, 2 * H, device="cuda")
+    hout = torch.zeros(rows * T, 2 * H, device="cuda", dtype=torch.float16 if args.precision == 2 else torch.float32)
     ms = []
     for i in range(args.iters + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
