@@ -14,7 +14,7 @@ namespace aero {
 // with (fi, dt, slab) the tap geometry of the forward (include/aero_b200.h, aero_tapgemm_fwd).  One CTA: a 128 (k) x 64 (n)
 // tile of one slab over a strided subset of 32-pixel chunks (consecutive t of one output row); partial sums are added
 // to dW with fp32 atomics (dW is zeroed by the caller).
-constexpr int kWgK = 128, kWgN = 64, kWgP = 32;
+constexpr int kWgK = 128, kWgP = 32;
 
 struct WgradArgs {
     const float* a1;
@@ -26,16 +26,20 @@ struct WgradArgs {
     int tiles_t, k_tiles, n_tiles, vec;
 };
 
+// TN = 64: 8 x 4 outputs per thread (narrow layers);  TN = 128: 8 x 8 (the decoder's wide layers: with 8 x 4 the kernel is bound by the
+// shared-memory port -- 3 LDS.128 per 32 FMA -- not by the FMA pipe)
+template <int TN>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
+    constexpr int NJ = TN / 16;                        // n outputs per thread
     __shared__ __align__(16) float Xs[kWgP][kWgK];
-    __shared__ __align__(16) float Ys[kWgP][kWgN];
+    __shared__ __align__(16) float Ys[kWgP][TN];
     const aero_tapgemm_params& p = g.p;
     const int K = p.C1 + p.C2;
     const int kt_i = blockIdx.x % g.k_tiles, nt_i = blockIdx.x / g.k_tiles;
-    const int k0 = kt_i * kWgK, n0 = nt_i * kWgN;
+    const int k0 = kt_i * kWgK, n0 = nt_i * TN;
     const int slab = blockIdx.y;
     const int tid = threadIdx.x;
-    const int ty = tid >> 4, tx = tid & 15;            // micro tile: k = ty*8 .. +7, n = tx*4 .. +3
+    const int ty = tid >> 4, tx = tid & 15;            // micro tile: k = ty*8 .. +7, n = tx*4 .. +3 (and 64 + tx*4 .. for TN = 128)
 
     // tap geometry of this slab
     int jf = 0, dt = 0, conv_t_r = 0, conv_t_tap = 0;
@@ -46,11 +50,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
         conv_t_r = slab % p.stride_f;
         conv_t_tap = slab / p.stride_f;
     }
-    float acc[8][4];
+    float acc[8][NJ];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 
     const int64_t n_chunks = (int64_t)p.B * p.F_out * g.tiles_t;
     for (int64_t ch = blockIdx.z; ch < n_chunks; ch += gridDim.z) {
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
         if (fi < 0 || fi >= p.F_in) continue;
         const int t0 = tt * kWgP;
         __syncthreads();
-        // ---- load the activation tile [32 pixels][128 channels] and the gradient tile [32][64]
+        // ---- load the activation tile [32 pixels][128 channels] and the gradient tile [32][TN]
         for (int i = tid; i < kWgP * (kWgK / 4); i += 256) {
             const int pp = i / (kWgK / 4), c4 = (i - pp * (kWgK / 4)) * 4;
             const int t = t0 + pp, ti = t + dt;
@@ -94,8 +98,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
             }
             *reinterpret_cast<float4*>(&Xs[pp][c4]) = v;
         }
-        for (int i = tid; i < kWgP * (kWgN / 4); i += 256) {
-            const int pp = i / (kWgN / 4), c4 = (i - pp * (kWgN / 4)) * 4;
+        for (int i = tid; i < kWgP * (TN / 4); i += 256) {
+            const int pp = i / (TN / 4), c4 = (i - pp * (TN / 4)) * 4;
             const int t = t0 + pp;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t < p.T) {
@@ -113,17 +117,21 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
             *reinterpret_cast<float4*>(&Ys[pp][c4]) = v;
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int pp = 0; pp < kWgP; ++pp) {
             const float4 xa = *reinterpret_cast<const float4*>(&Xs[pp][ty * 8]);
             const float4 xb = *reinterpret_cast<const float4*>(&Xs[pp][ty * 8 + 4]);
-            const float4 yv = *reinterpret_cast<const float4*>(&Ys[pp][tx * 4]);
             const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+            float ys[NJ];
+#pragma unroll
+            for (int h = 0; h < NJ / 4; ++h) {
+                const float4 yv = *reinterpret_cast<const float4*>(&Ys[pp][h * 64 + tx * 4]);
+                ys[4 * h] = yv.x; ys[4 * h + 1] = yv.y; ys[4 * h + 2] = yv.z; ys[4 * h + 3] = yv.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xs[i], ys[j], acc[i][j]);
+                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(xs[i], ys[j], acc[i][j]);
         }
     }
 #pragma unroll
@@ -131,8 +139,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
         const int kk = k0 + ty * 8 + i;
         if (kk >= K) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int nn = n0 + tx * 4 + j;
+        for (int j = 0; j < NJ; ++j) {
+            const int nn = n0 + (j / 4) * 64 + tx * 4 + (j & 3);
             if (nn < p.N && acc[i][j] != 0.f)
                 atomicAdd(g.dw + (int64_t)nn * g.dw_sn + (int64_t)kk * g.dw_sk + (int64_t)slab * g.dw_ss, acc[i][j]);
         }
@@ -605,8 +613,9 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
     g.dw_sn = dw_sn; g.dw_sk = dw_sk; g.dw_ss = dw_ss;
     const int K = p->C1 + p->C2;
     g.tiles_t = cdiv(p->T, kWgP);
+    const int TN = p->N >= 128 ? 128 : 64;
     g.k_tiles = cdiv(K, kWgK);
-    g.n_tiles = cdiv(p->N, kWgN);
+    g.n_tiles = cdiv(p->N, TN);
     auto al4 = [](int64_t v) { return (v & 3) == 0; };
     g.vec = (p->C1 % 4 == 0) && (p->C2 % 4 == 0) && (p->N % 4 == 0) && al4(p->a1_sb) && al4(p->a1_sf) && al4(p->a1_st) && al4(p->a2_sb) &&
             al4(p->a2_sf) && al4(p->a2_st) && al4(p->o_sb) && al4(p->o_sf) && al4(p->o_st) &&
@@ -621,7 +630,8 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
     if (splits < 1) splits = 1;
     AERO_REQUIRE(nslab <= 65535, "aero_tapgemm_wgrad: too many taps");
     dim3 grid((unsigned)(g.k_tiles * g.n_tiles), (unsigned)nslab, (unsigned)splits);
-    wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+    if (TN == 128) wgrad_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+    else wgrad_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     return check_launch("aero_tapgemm_wgrad");
 }
 

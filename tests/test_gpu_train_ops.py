@@ -47,6 +47,7 @@ CONVS = [
     ("k9", dict(kt=9, pad_t=4), 16, 8, 1, 1),
     ("enc0_real", dict(kf=8, stride_f=4, pad_f=2), 48, 48, 256, 64),
     ("k9_wide", dict(kt=9, pad_t=4), 2048, 48, 1, 1),
+    ("dec_wide_n", dict(kf=3, kt=3, pad_f=1, pad_t=1), 48, 200, 4, 4),      # N >= 128: the 8 x 8 micro-tile wgrad, ragged N tile
 ]
 
 
