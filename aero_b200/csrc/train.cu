@@ -5,6 +5,7 @@
 //
 // Data gradients of every convolution are NOT here: the adjoint of a tap-GEMM is a tap-GEMM (flipped taps, transposed
 // weights, conv <-> transposed conv), so dgrad runs on aero_tapgemm_fwd itself.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace aero {
@@ -613,7 +614,10 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
     g.dw_sn = dw_sn; g.dw_sk = dw_sk; g.dw_ss = dw_ss;
     const int K = p->C1 + p->C2;
     g.tiles_t = cdiv(p->T, kWgP);
-    const int TN = p->N >= 128 ? 128 : 64;
+    // (the 8 x 8 variant, TN = 128, measured no faster on B200 -- 138.9 vs 136.7 ms per generator step -- so the narrow one serves all;
+    //  AERO_WGRAD_WIDE=1 selects it for experiments)
+    static const bool wide = getenv("AERO_WGRAD_WIDE") != nullptr;
+    const int TN = (wide && p->N >= 128) ? 128 : 64;
     g.k_tiles = cdiv(K, kWgK);
     g.n_tiles = cdiv(p->N, TN);
     auto al4 = [](int64_t v) { return (v & 3) == 0; };
