@@ -152,7 +152,7 @@ def main():
     sm = cfg.get("stats_mode", 0)
     f16 = args.precision == 2 and C1 % 8 == 0 and C2 % 8 == 0
     adt = torch.float16 if f16 else torch.float32
-    odt = torch.float16 if (args.precision == 2 and not sm and not args.out_f32) else torch.float32
+    odt = torch.float16 if (args.precision == 2 and not args.out_f32) else torch.float32      # (pre-norm outputs are FP16 too since round 2)
     a1 = tf32_round(torch.randn(B, F_in, Tt, C1)).cuda().to(adt) if C1 else None
     a2 = tf32_round(torch.randn(B, F_in, Tt, C2)).cuda().to(adt) if C2 else None
     bias = torch.randn(N).cuda()
