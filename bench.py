@@ -55,8 +55,8 @@ CONFIGS = {
 # `ncu --set full` capture summarised in profiles/
 TRAFFIC_NCU = {1: {"kernel": "tapgemm_tc_kernel<0,0,1,tf32> decoder.0.rw B=32", "bytes_per_launch": 473.8e6, "algorithmic_bytes": 513.7e6,
                    "tensor_pipe_pct": 80.8, "source": "profiles/r1_dec0rw_tc_ncu.md"},
-               2: {"kernel": "tapgemm_tc_kernel<0,0,1,f16,f32> decoder.0.rw B=32", "bytes_per_launch": 401.7e6, "algorithmic_bytes": 453.9e6,
-                   "tensor_pipe_pct": 82.2, "source": "profiles/r1_dec0rw_f16_ncu.md"}}
+               2: {"kernel": "tapgemm_tc_kernel<0,0,1,f16,f16> decoder.0.rw B=32", "bytes_per_launch": 208.2e6, "algorithmic_bytes": 256.9e6,
+                   "tensor_pipe_pct": 89.5, "source": "profiles/r2_dec0rw_f16_ncu.md"}}
 
 
 def peaks():

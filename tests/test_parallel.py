@@ -71,3 +71,30 @@ def test_two_rank_gloo_sharded_forward_matches_single_process():
     assert n_local == 2                      # rank 0 gets the extra clip of 3
     assert t == pytest.approx(2.0)           # max over ranks
     assert full.shape == ref.shape and rel_l2(full, ref) < 1e-6
+
+
+def test_trainer_flat_buffer_order_and_pieces():
+    """Host logic of aero_b200.trainer (no kernels): gradients are laid out in the order the backward pass finishes them and the
+    all-reduce pieces end at layer boundaries and tile the buffer."""
+    from aero_b200 import Aero, aero_kwargs
+    from aero_b200.trainer import GeneratorTrainer, _backward_order
+    torch.manual_seed(0)
+    m = Aero(**aero_kwargs("aero_4-16_512_256"))
+    order = _backward_order(m)
+    assert sorted(order) == sorted(n for n, _ in m.named_parameters())
+    heads = [".".join(n.split(".")[:2]) for n in order]
+    first = {h: heads.index(h) for h in dict.fromkeys(heads)}
+    want = [f"decoder.{j}" for j in (3, 2, 1, 0)] + [f"encoder.{i}" for i in (3, 2, 1, 0)]
+    assert [h for h in first if h.startswith(("decoder", "encoder"))] == want
+    tr = GeneratorTrainer.__new__(GeneratorTrainer)
+    tr.order = order
+    tr.flat = torch.zeros(sum(p.numel() for p in m.parameters()))
+    tr.offsets, off = {}, 0
+    params = dict(m.named_parameters())
+    for n in order:
+        tr.offsets[n] = (off, off + params[n].numel())
+        off += params[n].numel()
+    pieces = tr._make_pieces(4)
+    assert pieces[0][0] == 0 and pieces[-1][1] == tr.flat.numel() and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    ends = {tr.offsets[n][1] for n in order}
+    assert all(hi in ends for _, hi in pieces) and 2 <= len(pieces) <= 8
