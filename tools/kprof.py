@@ -32,6 +32,7 @@ SHAPES = {
     "enc0_rw": dict(F_out=64, N=96, C1=48, glu=1),
     "dec3_ct_in": dict(F_out=64, N=192, C1=96),
     "enc3_gin2": dict(F_out=1, N=768, C1=192, T=768 * 200 // 32),
+    "dec3_ct": dict(F_out=256, F_in=64, N=2, C1=96, mode=cabi.TAPS_CONVT, kf=8, stride_f=4, f_off=2),
 }
 
 
@@ -124,6 +125,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-stats", action="store_true")
     ap.add_argument("--out-f32", action="store_true")
+    ap.add_argument("--in-f32", action="store_true")
     args = ap.parse_args()
     torch.manual_seed(0)
     if args.shape.startswith("lstm"):
@@ -150,7 +152,7 @@ def main():
     eng._wk[w.data_ptr()] = tf32_round(w.permute(0, 2, 1).contiguous())
     eng._wh[w.data_ptr()] = pack_kmajor_fp16(w)
     sm = cfg.get("stats_mode", 0)
-    f16 = args.precision == 2 and C1 % 8 == 0 and C2 % 8 == 0
+    f16 = args.precision == 2 and C1 % 8 == 0 and C2 % 8 == 0 and not args.in_f32
     adt = torch.float16 if f16 else torch.float32
     odt = torch.float16 if (args.precision == 2 and not args.out_f32) else torch.float32      # (pre-norm outputs are FP16 too since round 2)
     a1 = tf32_round(torch.randn(B, F_in, Tt, C1)).cuda().to(adt) if C1 else None
