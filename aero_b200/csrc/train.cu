@@ -148,6 +148,76 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs g) {
     }
 }
 
+// Thin problems -- a handful of weights against up to a million pixels (the discriminator's 1 -> 16 first layer, the 96 -> 2 last
+// transposed convolution, the 2 -> 48 first one, FTB's C -> 5): the 128 x 64 tile above would be almost empty.  Here one thread owns up
+// to kWsPer weights (slab, k, n), a CTA owns a run of frames of one output row; validity of the tap's input row is decided once per
+// (weight, row), the inner loop over frames is two loads and one FMA.  Partial sums go to dW with fp32 atomics.
+constexpr int kWsPer = 8, kWsThreads = 256;
+
+__global__ void __launch_bounds__(kWsThreads) wgrad_small_kernel(const WgradArgs g, int n_out, int n_seg, int seg_len) {
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1 + p.C2, KN = K * p.N;
+    int o_n[kWsPer], o_k[kWsPer], o_dt[kWsPer], o_fa[kWsPer];
+    float acc[kWsPer];
+#pragma unroll
+    for (int i = 0; i < kWsPer; ++i) {
+        const int o = threadIdx.x + i * kWsThreads;
+        acc[i] = 0.f;
+        o_n[i] = -1; o_k[i] = 0; o_dt[i] = 0; o_fa[i] = 0;
+        if (o < n_out) {
+            const int slab = o / KN, rem = o - slab * KN;
+            o_k[i] = rem / p.N;
+            o_n[i] = rem - o_k[i] * p.N;
+            if (p.mode == AERO_TAPS_CONV) {
+                const int jf = slab / p.kt;
+                o_fa[i] = jf;
+                o_dt[i] = (slab - jf * p.kt) * p.dil_t - p.pad_t;
+            } else {
+                o_fa[i] = slab;                         // residue = slab % stride_f, tap = slab / stride_f
+            }
+        }
+    }
+    const int row = blockIdx.x / n_seg, seg = blockIdx.x - row * n_seg;
+    const int b = row / p.F_out, fo = row - b * p.F_out;
+    const int t_lo = seg * seg_len, t_hi = min(p.T, t_lo + seg_len);
+    const float* dyr = g.dy + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf;
+#pragma unroll
+    for (int i = 0; i < kWsPer; ++i) {
+        if (o_n[i] < 0) continue;
+        int fi;
+        if (p.mode == AERO_TAPS_CONV) {
+            fi = fo * p.stride_f + o_fa[i] - p.pad_f;
+        } else {
+            const int fof = fo + p.f_out_offset;
+            if (fof % p.stride_f != o_fa[i] % p.stride_f) continue;
+            fi = fof / p.stride_f - o_fa[i] / p.stride_f;
+        }
+        if (fi < 0 || fi >= p.F_in) continue;
+        const int k = o_k[i], dt = o_dt[i];
+        const float* xr;
+        int64_t xs;
+        if (k < p.C1) { xr = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + k; xs = p.a1_st; }
+        else { xr = g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (k - p.C1); xs = p.a2_st; }
+        const int lo = max(t_lo, -dt), hi = min(t_hi, p.T_in - dt);          // frames whose input frame t + dt exists
+        const float* yp = dyr + o_n[i];
+        float a0 = 0.f, a1 = 0.f;
+        int t = lo;
+        for (; t + 1 < hi; t += 2) {
+            a0 = fmaf(__ldg(xr + (int64_t)(t + dt) * xs), __ldg(yp + (int64_t)t * p.o_st), a0);
+            a1 = fmaf(__ldg(xr + (int64_t)(t + 1 + dt) * xs), __ldg(yp + (int64_t)(t + 1) * p.o_st), a1);
+        }
+        if (t < hi) a0 = fmaf(__ldg(xr + (int64_t)(t + dt) * xs), __ldg(yp + (int64_t)t * p.o_st), a0);
+        acc[i] = a0 + a1;
+    }
+#pragma unroll
+    for (int i = 0; i < kWsPer; ++i) {
+        if (o_n[i] < 0 || acc[i] == 0.f) continue;
+        const int o = threadIdx.x + i * kWsThreads;
+        const int slab = o / KN;
+        atomicAdd(g.dw + (int64_t)o_n[i] * g.dw_sn + (int64_t)o_k[i] * g.dw_sk + (int64_t)slab * g.dw_ss, acc[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------ gram
 // out[i][j] += sum_{b, m} P[b][i][m] * gate[b][m] * Q[b][j][m]   (i, j < F rows; m < M contiguous positions): the weight
 // gradient of FTB's frequency mix `freq_fc` (modules.py:296,317-320), whose contraction runs over the CONTIGUOUS axis of two
@@ -599,6 +669,9 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
     }
 }
 
+bool wgrad_tc_eligible(const aero_tapgemm_params& p, const void* a1, const void* a2, const void* dy);
+int wgrad_tc_launch(const float* a1, const float* a2, const float* dy, float* dw, const aero_tapgemm_params& p, int64_t dw_sn, int64_t dw_sk,
+                    int64_t dw_ss, cudaStream_t st);
 }  // namespace aero
 
 // ================================================================================================================ C ABI
@@ -609,6 +682,8 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
     AERO_REQUIRE(p->mode == AERO_TAPS_CONV || p->mode == AERO_TAPS_CONVT, "aero_tapgemm_wgrad: mode %d", p->mode);
     AERO_REQUIRE((p->C1 == 0 || a1) && (p->C2 == 0 || a2) && p->C1 + p->C2 >= 1 && p->N >= 1, "aero_tapgemm_wgrad: channels");
     AERO_REQUIRE(p->mode != AERO_TAPS_CONVT || (p->kt == 1 && p->kf % p->stride_f == 0), "aero_tapgemm_wgrad: transposed-conv geometry");
+    if (p->precision == 1 && wgrad_tc_eligible(*p, a1, a2, dy))        // TF32 tensor-core training mode (csrc/wgrad_tc.cu)
+        return wgrad_tc_launch(a1, a2, dy, dw, *p, dw_sn, dw_sk, dw_ss, (cudaStream_t)stream);
     WgradArgs g;
     g.a1 = a1; g.a2 = a2; g.dy = dy; g.dw = dw; g.p = *p;
     g.dw_sn = dw_sn; g.dw_sk = dw_sk; g.dw_ss = dw_ss;
@@ -626,6 +701,18 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
             ((((uintptr_t)a1 | (uintptr_t)a2 | (uintptr_t)dy) & 15) == 0);
     const int nslab = (p->mode == AERO_TAPS_CONVT) ? p->kf : p->kf * p->kt;
     const int64_t n_chunks = (int64_t)p->B * p->F_out * g.tiles_t;
+    if ((int64_t)nslab * K * p->N <= kWsPer * kWsThreads && (int64_t)p->B * p->F_out * p->T >= 4096) {
+        // few weights, many pixels: one thread per weight
+        const int64_t n_rows = (int64_t)p->B * p->F_out;
+        int n_seg = (int)cdiv((int64_t)148 * 8, n_rows);
+        if (n_seg > cdiv(p->T, 32)) n_seg = cdiv(p->T, 32);
+        if (n_seg < 1) n_seg = 1;
+        const int seg_len = cdiv(p->T, n_seg);
+        n_seg = cdiv(p->T, seg_len);
+        AERO_REQUIRE(n_rows * n_seg <= 2147483647LL, "aero_tapgemm_wgrad: grid too large");
+        wgrad_small_kernel<<<(unsigned)(n_rows * n_seg), kWsThreads, 0, (cudaStream_t)stream>>>(g, nslab * K * p->N, n_seg, seg_len);
+        return check_launch("aero_tapgemm_wgrad(small)");
+    }
     // enough CTAs to fill the GPU a few times over, never more than chunks
     int64_t tiles = (int64_t)g.k_tiles * g.n_tiles * nslab;
     int64_t splits = (148 * 6 + tiles - 1) / tiles;

@@ -58,6 +58,7 @@ class NLayerDiscriminator(nn.Module):
     def __init__(self, ndf, n_layers, downsampling_factor):
         super().__init__()
         self.specs = _layer_specs(ndf, n_layers, downsampling_factor)
+        self.train_precision = 0                                        # 1: dense convolutions in TF32 on the tensor cores
         self.model = nn.ModuleDict()
         for name, cin, cout, k, s, p, g, leaky in self.specs:
             layer, _, idx = name.partition(".")
@@ -83,6 +84,7 @@ class _DiscEngine(TrainEngine):
         self.geom = None
         self.lib = cabi.load()
         self._windows = {}
+        self.precision = int(getattr(module, "train_precision", 0))
         self._reset()
 
     def wn_weight(self, prefix, rows, length):
@@ -198,6 +200,15 @@ class Discriminator(nn.Module):
         for i in range(num_D):
             self.model[f"disc_{i}"] = NLayerDiscriminator(ndf, n_layers, downsampling_factor)
         self.downsample = nn.AvgPool1d(4, stride=2, padding=1, count_include_pad=False)
+
+    @property
+    def train_precision(self):
+        return self.model["disc_0"].train_precision
+
+    @train_precision.setter
+    def train_precision(self, v):
+        for d in self.model.values():
+            d.train_precision = int(v)
 
     def forward(self, x):
         results = []

@@ -305,6 +305,9 @@ class Aero(nn.Module):
             self._rescale_1d_convs(rescale)
 
         self._engine_obj = None
+        # training arithmetic of the convolution GEMMs (aero_b200/train_engine.py): 0 = exact fp32 (gradient-parity mode), 1 = TF32 on the
+        # tensor cores (what cuDNN does for the reference under torch.backends.cudnn.allow_tf32, PyTorch's default)
+        self.train_precision = 0
 
     # ------------------------------------------------------------------ init helpers
     @staticmethod

@@ -23,7 +23,7 @@ import torch
 
 from . import cabi
 from .cabi import ACT_NONE, NA_GELU, NA_GLU, NA_GLU_SCALE_RES, NA_NO_NORM, NA_NONE, NA_RELU, NA_SNAKE, TAPS_CONV, TAPS_CONVT
-from .engine import _ATTN_HEADS, _ATTN_NDECAY, _LSTM_MAX_STEPS, pack_taps
+from .engine import _ATTN_HEADS, _ATTN_NDECAY, _LSTM_MAX_STEPS, pack_taps, tf32_round
 
 _FTB_R, _FTB_RP = 5, 8          # FTB squeeze channels (modules.py:286) and their padded count (kernels work on channel quads)
 
@@ -49,6 +49,10 @@ class TrainEngine:
         self.geom = model.geom
         self.lib = cabi.load()
         self._windows = {}
+        # 0: exact-fp32 SIMT tap-GEMMs everywhere (the gradient-parity mode, default).  1: the convolutions' forward, data-gradient and
+        # weight-gradient GEMMs run on the tcgen05 tensor cores in TF32 (what cuDNN does for the reference under PyTorch's default
+        # torch.backends.cudnn.allow_tf32); normalisation, LSTM recurrence, attention and all reductions stay fp32 / fp64.
+        self.precision = int(getattr(model, "train_precision", 0))
         self._reset()
 
     def _reset(self):
@@ -116,9 +120,15 @@ class TrainEngine:
         o_s = o_s or (F_out * T * N, T * N, N)
         r_s = r_s or (0, 0, 0)
         return cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
-                                  ACT_NONE, 0, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 0, 0)
+                                  ACT_NONE, 0, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 1 if self.precision == 1 else 0, 0)
 
     def _gemm_call(self, p, out, w, a1=None, a2=None, bias=None, residual=None, samp_affine=None, stats=None, colscale=None):
+        if p.precision == 1:
+            # tcgen05 path: K-major TF32 twin [taps, pad4(N), K] of the packed weight [taps, K, pad4(N)]; shapes it does not take stay SIMT
+            if p.w_sb == 0 and colscale is None and w.dim() == 3 and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
+                w = tf32_round(w.permute(0, 2, 1).contiguous())
+            else:
+                p.precision = 0
         self._check(self.lib.aero_tapgemm_fwd(_ptr(a1), _ptr(a2), _ptr(w), _ptr(bias), None, _ptr(colscale), _ptr(residual),
                                               _ptr(samp_affine), _ptr(out), _ptr(stats), C.byref(p), self._stream()))
         return out

@@ -91,9 +91,12 @@ def main(args):
     lib = cabi.load()
     model = B.build_model(B.CONFIGS["4-16"]).to(dev).train()
     adversarial = not os.environ.get("AERO_TRAIN_NO_GAN")
+    train_precision = int(os.environ.get("AERO_TRAIN_PRECISION", "0"))
+    model.train_precision = train_precision
     if adversarial:
         torch.manual_seed(B.SEED + 1)
         disc = Discriminator(3, 16, 4, 4).to(dev)            # reference conf/experiment/aero_*.yaml melgan_discriminator
+        disc.train_precision = train_precision
         trainer = GanTrainer(model, disc, lr=3e-4, betas=(0.9, 0.999))
     else:
         trainer = GeneratorTrainer(model, lr=3e-4, betas=(0.9, 0.999))

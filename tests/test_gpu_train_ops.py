@@ -73,6 +73,41 @@ def test_conv_forward_wgrad_dgrad(eng, name, kw, K, N, Fi, Fo):
     assert rel_l2(e.grad(xg).view(B, Fi, T, K).cpu(), cl(x.grad)) < 1e-5
 
 
+THIN = [   # few weights, many pixels: the one-thread-per-weight wgrad kernel (csrc/train.cu, wgrad_small_kernel)
+    ("k2_to_48_k8_s4", "conv", dict(kf=8, stride_f=4, pad_f=2), 2, 48, 64, 16, 300),
+    ("c48_to_5_1x1", "conv", dict(), 48, 5, 16, 16, 200),
+    ("c12_k1x3", "conv", dict(kt=3, pad_t=1), 48, 12, 8, 8, 300),
+    ("convt_96_to_2_k8_s4", "convt", dict(kf=8, stride_f=4, f_off=2), 96, 2, 16, 64, 150),
+    ("disc_1_to_16_k15", "conv", dict(kt=15, pad_t=7), 1, 16, 1, 1, 6000),
+]
+
+
+@pytest.mark.parametrize("name,kind,kw,K,N,Fi,Fo,T", THIN, ids=[c[0] for c in THIN])
+def test_thin_layers_wgrad(eng, name, kind, kw, K, N, Fi, Fo, T):
+    e = eng
+    e._reset()
+    B = 2
+    x = rnd(B, K, Fi, T, seed=1).double().requires_grad_(True)
+    if kind == "conv":
+        cv = _Conv(**kw)
+        w = (rnd(N, K, cv.kf, cv.kt, seed=2) / math.sqrt(K * cv.kf * cv.kt)).double().requires_grad_(True)
+        ref = F.conv2d(x, w, None, stride=(cv.stride_f, 1), padding=(cv.pad_f, cv.pad_t), dilation=(1, cv.dil_t))
+    else:
+        cv = _Conv("convt", **kw)
+        w = (rnd(K, N, cv.kf, 1, seed=2) / math.sqrt(K * 2)).double().requires_grad_(True)
+        ref = F.conv_transpose2d(x, w, None, stride=(cv.stride_f, 1))[:, :, cv.f_off:cv.f_off + Fo]
+    assert ref.shape[2] == Fo
+    dy = rnd(*ref.shape, seed=4).double()
+    ref.backward(dy)
+    e.params = {"w": w.detach().float().cuda()}
+    xg = cl(x.detach().float()).cuda()
+    out = e.conv(xg, None, K, 0, "w", None, cv, B, Fi, Fo, T, N)
+    run_backward(e, out, cl(dy))
+    assert rel_l2(out.view(B, Fo, T, N).cpu(), cl(ref.detach())) < 1e-5
+    assert rel_l2(e.pg["w"].cpu(), w.grad) < 1e-5
+    assert rel_l2(e.grad(xg).view(B, Fi, T, K).cpu(), cl(x.grad)) < 1e-5
+
+
 def test_conv_two_sources_and_transposed_with_crop(eng):
     e = eng
     e._reset()
