@@ -200,13 +200,23 @@ __global__ void __launch_bounds__(kWsThreads) wgrad_small_kernel(const WgradArgs
         else { xr = g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (k - p.C1); xs = p.a2_st; }
         const int lo = max(t_lo, -dt), hi = min(t_hi, p.T_in - dt);          // frames whose input frame t + dt exists
         const float* yp = dyr + o_n[i];
-        float a0 = 0.f, a1 = 0.f;
+        // eight independent load pairs in flight per thread: the loop is bound by L2 latency, not by arithmetic
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = 0.f;
         int t = lo;
-        for (; t + 1 < hi; t += 2) {
-            a0 = fmaf(__ldg(xr + (int64_t)(t + dt) * xs), __ldg(yp + (int64_t)t * p.o_st), a0);
-            a1 = fmaf(__ldg(xr + (int64_t)(t + 1 + dt) * xs), __ldg(yp + (int64_t)(t + 1) * p.o_st), a1);
+        for (; t + 7 < hi; t += 8) {
+            float xv[8], yv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                xv[u] = __ldg(xr + (int64_t)(t + u + dt) * xs);
+                yv[u] = __ldg(yp + (int64_t)(t + u) * p.o_st);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = fmaf(xv[u], yv[u], a[u]);
         }
-        if (t < hi) a0 = fmaf(__ldg(xr + (int64_t)(t + dt) * xs), __ldg(yp + (int64_t)t * p.o_st), a0);
+        for (; t < hi; ++t) a[0] = fmaf(__ldg(xr + (int64_t)(t + dt) * xs), __ldg(yp + (int64_t)t * p.o_st), a[0]);
+        const float a0 = (a[0] + a[1]) + (a[2] + a[3]), a1 = (a[4] + a[5]) + (a[6] + a[7]);
         acc[i] = a0 + a1;
     }
 #pragma unroll

@@ -156,6 +156,158 @@ __global__ void __launch_bounds__(256) gconv_wgrad_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// MelGAN's own shape -- k = 41, stride 4, pad 20, 4 input channels per group, 4 or 16 outputs per group -- register-tiled: the generic
+// kernels above spend two shared-memory loads per FMA; these keep the input window (forward) / the gradient window (dgrad) of four
+// consecutive steps in registers and read the weights as one float4 per 16 FMAs.
+constexpr int kG4K = 41, kG4S = 4, kG4Pad = 20, kG4Cpg = 4;
+constexpr int kG4Co = 64;                      // output channels per CTA
+constexpr int kG4T = 64;                       // forward: output steps per CTA
+constexpr int kG4Wl = kG4Cpg * kG4K;           // 164 weights per output channel
+constexpr int kG4Ws = 68;                      // forward weight tile [164][68]: rows 16-byte aligned, stores 4-way conflicted at worst
+constexpr int kG4Xw = 300;                     // forward input rows [channel][300 steps]: 4 rows apart = 16 banks apart
+
+// forward: thread = 4 consecutive output channels (one group) x 4 consecutive output steps
+__global__ void __launch_bounds__(256) gconv41_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          float* __restrict__ y, const GconvP p) {
+    extern __shared__ __align__(16) float sm[];
+    const int opg = p.Cout / p.groups;
+    const int co0 = blockIdx.x * kG4Co, to0 = blockIdx.y * kG4T, b = blockIdx.z;
+    const int g0 = co0 / opg;
+    const int nch = (kG4Co / opg) * kG4Cpg;                           // input channels of this tile (16 or 64)
+    float* ws = sm;                                                   // [164][68]
+    float* xs = sm + kG4Wl * kG4Ws;                                   // [nch][300]
+    for (int i = threadIdx.x; i < kG4Co * kG4Wl; i += 256) {
+        const int cl = i / kG4Wl, e = i - cl * kG4Wl;
+        ws[e * kG4Ws + cl] = w[(int64_t)co0 * kG4Wl + i];
+    }
+    constexpr int win = (kG4T - 1) * kG4S + kG4K;                     // 293
+    const int ti0 = to0 * kG4S - kG4Pad;
+    for (int i = threadIdx.x; i < kG4Xw * nch; i += 256) {
+        const int tt = i / nch, c = i - tt * nch;
+        const int ti = ti0 + tt;
+        xs[c * kG4Xw + tt] = (tt < win && ti >= 0 && ti < p.Tin) ? x[((int64_t)b * p.Tin + ti) * p.Cin + g0 * kG4Cpg + c] : 0.f;
+    }
+    __syncthreads();
+    const int cq = threadIdx.x & 15, tq = threadIdx.x >> 4;
+    const int cl = 4 * cq, tl0 = 4 * tq;
+    const int gl = cl / opg;
+    float acc[4][4];
+    {
+        const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + co0 + cl) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc[u][0] = bv.x; acc[u][1] = bv.y; acc[u][2] = bv.z; acc[u][3] = bv.w; }
+    }
+#pragma unroll 1
+    for (int c = 0; c < kG4Cpg; ++c) {
+        float xw[56];                                                 // steps 16 tq .. 16 tq + 55 of input channel (gl, c)
+        const float* xr = xs + (gl * kG4Cpg + c) * kG4Xw + kG4S * tl0;
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + 4 * i);
+            xw[4 * i] = v.x; xw[4 * i + 1] = v.y; xw[4 * i + 2] = v.z; xw[4 * i + 3] = v.w;
+        }
+        const float* wr = ws + (c * kG4K) * kG4Ws + cl;
+#pragma unroll
+        for (int j = 0; j < kG4K; ++j) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + j * kG4Ws);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float xv = xw[kG4S * u + j];
+                acc[u][0] = fmaf(xv, wv.x, acc[u][0]);
+                acc[u][1] = fmaf(xv, wv.y, acc[u][1]);
+                acc[u][2] = fmaf(xv, wv.z, acc[u][2]);
+                acc[u][3] = fmaf(xv, wv.w, acc[u][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int to = to0 + tl0 + u;
+        if (to < p.Tout)
+            *reinterpret_cast<float4*>(y + ((int64_t)b * p.Tout + to) * p.Cout + co0 + cl) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    }
+}
+
+// data gradient.  With ti = 4 m + r:  dx[4m + r][c] = sum_{q < opg} sum_{i} dy[m + 5 - i][q] * w[q][c][r + 4 i]   (i = 0 .. 10, j = r + 4i <= 40)
+// thread = (group, residue r, 4 consecutive m) x the group's 4 input channels; the 14-step gradient window of one output channel sits in
+// registers, the weights are read as float4 over c.
+constexpr int kG4Dw = 164;                     // per-output-channel weights, re-laid as [j][c]
+// pad that makes a per-group stride = 16 (mod 32) floats: two neighbouring groups then occupy opposite halves of the 32 banks
+__host__ __device__ inline int g4_skew(int base) { return (48 - base % 32) % 32; }
+__global__ void __launch_bounds__(256) gconv41_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                                            const GconvP p, const int m_cta, const int ds_w) {
+    extern __shared__ __align__(16) float sm[];
+    const int opg = p.Cout / p.groups;
+    const int ngl = kG4Co / opg;                                      // groups per CTA (4 or 16)
+    const int co0 = blockIdx.x * kG4Co, m0c = blockIdx.y * m_cta, b = blockIdx.z;
+    const int g0 = co0 / opg;
+    const int gstride_w = opg * kG4Dw + g4_skew(opg * kG4Dw);
+    float* ws = sm;                                                   // [ngl][opg][41][4] (+ skew)
+    float* ds = sm + ngl * gstride_w;                                 // [64 output channels][ds_w steps] (+ skew per group)
+    const int gstride_d = opg * ds_w + g4_skew(opg * ds_w);
+    for (int i = threadIdx.x; i < kG4Co * kG4Wl; i += 256) {
+        const int cl = i / kG4Wl, e = i - cl * kG4Wl;                 // e = c * 41 + j
+        const int c = e / kG4K, j = e - c * kG4K;
+        const int gl = cl / opg, q = cl - gl * opg;
+        ws[gl * gstride_w + q * kG4Dw + j * 4 + c] = w[(int64_t)co0 * kG4Wl + i];
+    }
+    // gradient steps m0c - 5 .. m0c + m_cta + 8 (ds index 0 = step m0c - 5)
+    const int to_base = m0c - 5;
+    for (int i = threadIdx.x; i < ds_w * kG4Co; i += 256) {
+        const int tt = i / kG4Co, cl = i - tt * kG4Co;
+        const int to = to_base + tt;
+        const int gl = cl / opg, q = cl - gl * opg;
+        ds[gl * gstride_d + q * ds_w + tt] = (to >= 0 && to < p.Tout) ? dy[((int64_t)b * p.Tout + to) * p.Cout + co0 + cl] : 0.f;
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 3, gl = (threadIdx.x >> 2) % ngl, mb = threadIdx.x / (4 * ngl);
+    const int ml = 4 * mb;                                            // first m of this thread, relative to m0c
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[u][c] = 0.f;
+    const int ntap = (r == 0) ? 11 : 10;
+#pragma unroll 1
+    for (int q = 0; q < opg; ++q) {
+        float dw_[16];                                                // steps (m0 - 5) .. (m0 + 10) of output channel (gl, q)
+        const float* dr = ds + gl * gstride_d + q * ds_w + ml;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(dr + 4 * i);
+            dw_[4 * i] = v.x; dw_[4 * i + 1] = v.y; dw_[4 * i + 2] = v.z; dw_[4 * i + 3] = v.w;
+        }
+        const float* wr = ws + gl * gstride_w + q * kG4Dw + r * 4;
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+            if (i < ntap) {
+                const float4 wv = *reinterpret_cast<const float4*>(wr + 16 * i);        // j = r + 4 i
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float dv = dw_[u + 10 - i];                 // step m0 + u + 5 - i
+                    acc[u][0] = fmaf(dv, wv.x, acc[u][0]);
+                    acc[u][1] = fmaf(dv, wv.y, acc[u][1]);
+                    acc[u][2] = fmaf(dv, wv.z, acc[u][2]);
+                    acc[u][3] = fmaf(dv, wv.w, acc[u][3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int ti = kG4S * (m0c + ml + u) + r;
+        if (ti < p.Tin)
+            *reinterpret_cast<float4*>(dx + ((int64_t)b * p.Tin + ti) * p.Cin + (g0 + gl) * kG4Cpg) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    }
+}
+
+static bool gconv41_ok(const GconvP& p) {
+    if (p.k != kG4K || p.stride != kG4S || p.pad != kG4Pad || p.Cin != p.groups * kG4Cpg || p.Cout % kG4Co) return false;
+    const int opg = p.Cout / p.groups;
+    return opg == 4 || opg == 16;
+}
+
 // weight normalisation, one CTA per output channel (row):  w = g * v / ||v||
 __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
                                                               float* __restrict__ norms, int len) {
@@ -221,6 +373,14 @@ extern "C" int aero_gconv1d_fwd(const float* x, const float* w, const float* bia
     const GconvP p{B, Tin, Tout, Cin, Cout, groups, k, stride, pad};
     int rc = gconv_check(p);
     if (rc != AERO_OK) return rc;
+    if (gconv41_ok(p)) {
+        const int nch = (kG4Co / (Cout / groups)) * kG4Cpg;
+        const size_t smem4 = sizeof(float) * ((size_t)kG4Wl * kG4Ws + (size_t)nch * kG4Xw);
+        cudaFuncSetAttribute(gconv41_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+        dim3 grid4(Cout / kG4Co, cdiv(Tout, kG4T), B);
+        gconv41_fwd_kernel<<<grid4, 256, smem4, (cudaStream_t)stream>>>(x, w, bias, y, p);
+        return check_launch("aero_gconv1d_fwd(k41)");
+    }
     const size_t smem = gconv_smem(p, 0);
     cudaFuncSetAttribute(gconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(cdiv(Cout, kGcCo), cdiv(Tout, kGcT), B);
@@ -236,6 +396,16 @@ extern "C" int aero_gconv1d_dgrad(const float* dy, const float* w, float* dx, in
     int rc = gconv_check(p);
     if (rc != AERO_OK) return rc;
     const int opg = Cout / groups;
+    if (gconv41_ok(p)) {
+        const int ngl = kG4Co / opg;
+        const int m_cta = 4 * (256 / (4 * ngl));                          // 64 (opg 16) or 16 (opg 4) values of m = ti / 4 per CTA
+        const int ds_w = m_cta + 20;                                      // steps m0 - 5 .. m0 + m_cta + 14; 84 / 36: transposing stores 4-way conflicted
+        const size_t smem4 = sizeof(float) * ((size_t)ngl * (opg * kG4Dw + g4_skew(opg * kG4Dw)) + (size_t)ngl * (opg * ds_w + g4_skew(opg * ds_w)));
+        cudaFuncSetAttribute(gconv41_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+        dim3 grid4(Cout / kG4Co, cdiv(cdiv(Tin, kG4S), m_cta), B);
+        gconv41_dgrad_kernel<<<grid4, 256, smem4, (cudaStream_t)stream>>>(dy, w, dx, p, m_cta, ds_w);
+        return check_launch("aero_gconv1d_dgrad(k41)");
+    }
     const int gt = kGcCo / opg > 0 ? kGcCo / opg : 1;
     const int rows = (kGdT + k) / stride + 2;
     const size_t smem = gconv_smem(p, rows) + sizeof(float) * (size_t)rows * kGcCo;

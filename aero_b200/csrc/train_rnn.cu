@@ -146,36 +146,50 @@ __global__ void __launch_bounds__(4 * H) lstm_bwd_kernel(const float* __restrict
         seq_k[q] = seq_id[q] - seq_row[q] * p.n_win;
     }
     const int half = p.win_stride / 2;
+    // inputs of one step of one cell item; loaded one step ahead so that the HBM / L2 latency hides behind the mat-vec
+    struct StepIn { float ig, fg, gg, og, c, c_prev, dh_ext; };
+    auto load_step = [&](int s, int q) -> StepIn {
+        StepIn v = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (s < 0 || !seq_ok[q]) return v;
+        const int pos = dir ? p.steps - 1 - s : s;
+        const int pos_prev = dir ? pos + 1 : pos - 1;              // position processed one step earlier (s - 1)
+        const int j = item_j[q];
+        if (p.out_windowed) {
+            v.dh_ext = dhout[((int64_t)seq_id[q] * p.steps + pos) * 2 * H + dir * H + j];
+        } else {
+            const int frame = seq_k[q] * p.win_stride + pos;
+            const int lo = (seq_k[q] == 0) ? 0 : half;
+            const int hi = (seq_k[q] == p.n_win - 1) ? p.steps : p.steps - half;
+            if (pos >= lo && pos < hi && frame < p.T) v.dh_ext = dhout[((int64_t)seq_row[q] * p.T + frame) * 2 * H + dir * H + j];
+        }
+        const int64_t wpos = ((int64_t)seq_id[q] * p.steps + pos) * 2 + dir;
+        const float* gd = gates_s + wpos * G + j;
+        v.ig = gd[0]; v.fg = gd[H]; v.gg = gd[2 * H]; v.og = gd[3 * H];
+        v.c = c_s[wpos * H + j];
+        v.c_prev = (s > 0) ? c_s[(((int64_t)seq_id[q] * p.steps + pos_prev) * 2 + dir) * H + j] : 0.f;
+        return v;
+    };
+    StepIn cur[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) cur[q] = load_step(p.steps - 1, q);
     __syncthreads();
     for (int s = p.steps - 1; s >= 0; --s) {
         const int pos = dir ? p.steps - 1 - s : s;
-        const int pos_prev = dir ? pos + 1 : pos - 1;              // position processed one step earlier (s - 1)
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int n = item_n[q], j = item_j[q];
             float d_ig = 0.f, d_fg = 0.f, d_gg = 0.f, d_og = 0.f;
             if (seq_ok[q]) {
-                float dh = dhr[n * H + j];
-                if (p.out_windowed) {
-                    dh += dhout[((int64_t)seq_id[q] * p.steps + pos) * 2 * H + dir * H + j];
-                } else {
-                    const int frame = seq_k[q] * p.win_stride + pos;
-                    const int lo = (seq_k[q] == 0) ? 0 : half;
-                    const int hi = (seq_k[q] == p.n_win - 1) ? p.steps : p.steps - half;
-                    if (pos >= lo && pos < hi && frame < p.T) dh += dhout[((int64_t)seq_row[q] * p.T + frame) * 2 * H + dir * H + j];
-                }
-                const int64_t wpos = ((int64_t)seq_id[q] * p.steps + pos) * 2 + dir;
-                const float* gd = gates_s + wpos * G + j;
-                const float ig = gd[0], fg = gd[H], gg = gd[2 * H], og = gd[3 * H];
-                const float c = c_s[wpos * H + j];
-                const float c_prev = (s > 0) ? c_s[(((int64_t)seq_id[q] * p.steps + pos_prev) * 2 + dir) * H + j] : 0.f;
-                const float th = tanhf(c);
+                const float dh = dhr[n * H + j] + cur[q].dh_ext;
+                const float ig = cur[q].ig, fg = cur[q].fg, gg = cur[q].gg, og = cur[q].og;
+                const float th = tanhf(cur[q].c);
                 const float dc = dh * og * (1.0f - th * th) + dc_state[q];
                 d_og = dh * th * og * (1.0f - og);
                 d_ig = dc * gg * ig * (1.0f - ig);
-                d_fg = dc * c_prev * fg * (1.0f - fg);
+                d_fg = dc * cur[q].c_prev * fg * (1.0f - fg);
                 d_gg = dc * ig * (1.0f - gg * gg);
                 dc_state[q] = dc * fg;
+                const int64_t wpos = ((int64_t)seq_id[q] * p.steps + pos) * 2 + dir;
                 float* dd = dgin_w + wpos * G + j;
                 dd[0] = d_ig; dd[H] = d_fg; dd[2 * H] = d_gg; dd[3 * H] = d_og;
             }
@@ -183,6 +197,8 @@ __global__ void __launch_bounds__(4 * H) lstm_bwd_kernel(const float* __restrict
             ds[0] = d_ig; ds[H] = d_fg; ds[2 * H] = d_gg; ds[3 * H] = d_og;
         }
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < Q; ++q) cur[q] = load_step(s - 1, q);          // issued now, consumed after the mat-vec
         if (s > 0) {
             float acc[Q];
 #pragma unroll
@@ -240,6 +256,28 @@ static int launch_lstm_bwd(const float* dhout, const float* gates_s, const float
     return check_launch("aero_lstm_bwd");
 }
 
+// Sequences per CTA: 16 when that still gives every SM a CTA, else fewer -- a training batch has a few hundred windows, and a CTA's step
+// time is dominated by streaming W_hh from shared memory whatever NT is, so spreading the windows over more SMs is nearly free.
+static int pick_nt(const aero_lstm_params& p, int nt_max) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_seq = p.rows * p.n_win;
+    int nt = nt_max;
+    while (nt > 4 && cdiv(n_seq, nt) * 2 < num_sms) nt >>= 1;
+    return nt;
+}
+
+#define AERO_LSTM_NT_DISPATCH(FN, H_, NTMAX, ...)                          \
+    switch (pick_nt(*p, NTMAX)) {                                          \
+        case 16: return FN<H_, (NTMAX >= 16 ? 16 : NTMAX)>(__VA_ARGS__);   \
+        case 8: return FN<H_, 8>(__VA_ARGS__);                             \
+        default: return FN<H_, 4>(__VA_ARGS__);                            \
+    }
+
 }  // namespace aero
 
 extern "C" int aero_lstm_train_fwd(const float* gin, const float* bias_pad, const float* whh, float* hout, float* gates_s, float* c_s,
@@ -252,10 +290,10 @@ extern "C" int aero_lstm_train_fwd(const float* gin, const float* bias_pad, cons
     AERO_REQUIRE(p->n_win == 1 || (p->win_stride >= 2 && p->win_stride % 2 == 0), "aero_lstm_train_fwd: win_stride");
     cudaStream_t st = (cudaStream_t)stream;
     switch (p->H) {
-        case 12: return launch_lstm_train_fwd<12, 16>(gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st);
-        case 24: return launch_lstm_train_fwd<24, 16>(gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st);
-        case 48: return launch_lstm_train_fwd<48, 16>(gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st);
-        case 96: return launch_lstm_train_fwd<96, 16>(gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st);
+        case 12: AERO_LSTM_NT_DISPATCH(launch_lstm_train_fwd, 12, 16, gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st)
+        case 24: AERO_LSTM_NT_DISPATCH(launch_lstm_train_fwd, 24, 16, gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st)
+        case 48: AERO_LSTM_NT_DISPATCH(launch_lstm_train_fwd, 48, 16, gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st)
+        case 96: AERO_LSTM_NT_DISPATCH(launch_lstm_train_fwd, 96, 16, gin, bias_pad, whh, hout, gates_s, c_s, h_s, *p, st)
         default:
             set_error("aero_lstm_train_fwd: hidden size %d not instantiated (12, 24, 48, 96)", p->H);
             return AERO_ERR_UNSUPPORTED;
@@ -269,10 +307,10 @@ extern "C" int aero_lstm_bwd(const float* dhout, const float* gates_s, const flo
     AERO_REQUIRE(p->rows >= 1 && p->T >= 1 && p->n_win >= 1 && p->steps >= 1, "aero_lstm_bwd: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     switch (p->H) {
-        case 12: return launch_lstm_bwd<12, 16>(dhout, gates_s, c_s, whh, dgin_w, *p, st);
-        case 24: return launch_lstm_bwd<24, 16>(dhout, gates_s, c_s, whh, dgin_w, *p, st);
-        case 48: return launch_lstm_bwd<48, 16>(dhout, gates_s, c_s, whh, dgin_w, *p, st);
-        case 96: return launch_lstm_bwd<96, 8>(dhout, gates_s, c_s, whh, dgin_w, *p, st);
+        case 12: AERO_LSTM_NT_DISPATCH(launch_lstm_bwd, 12, 16, dhout, gates_s, c_s, whh, dgin_w, *p, st)
+        case 24: AERO_LSTM_NT_DISPATCH(launch_lstm_bwd, 24, 16, dhout, gates_s, c_s, whh, dgin_w, *p, st)
+        case 48: AERO_LSTM_NT_DISPATCH(launch_lstm_bwd, 48, 16, dhout, gates_s, c_s, whh, dgin_w, *p, st)
+        case 96: AERO_LSTM_NT_DISPATCH(launch_lstm_bwd, 96, 8, dhout, gates_s, c_s, whh, dgin_w, *p, st)
         default:
             set_error("aero_lstm_bwd: hidden size %d not instantiated (12, 24, 48, 96)", p->H);
             return AERO_ERR_UNSUPPORTED;

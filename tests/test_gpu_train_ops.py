@@ -664,3 +664,37 @@ def test_mrstft_loss_gradient_matches_autograd():
     print(f"mrstft: sc {float(sc):.6f} ({float(sc_t):.6f}) mag {float(mag):.6f} ({float(mag_t):.6f}); grad rel_l2 {rel_l2(xg.grad.cpu(), xd.grad):.2e}")
     assert abs(float(sc) - float(sc_t)) < 2e-5 * float(sc_t) and abs(float(mag) - float(mag_t)) < 1e-4 * float(mag_t)
     assert rel_l2(xg.grad.cpu(), xd.grad) < 5e-4          # (sign() of the log-magnitude term flips where the two magnitudes agree to fp32)
+
+
+@pytest.mark.parametrize("Cin,Cout,groups,Tin", [(16, 64, 4, 1030), (64, 256, 16, 515), (256, 1024, 64, 259), (1024, 1024, 256, 77),
+                                                 (8, 32, 2, 300)])
+def test_melgan_grouped_conv_kernels(Cin, Cout, groups, Tin):
+    """aero_gconv1d_{fwd,dgrad,wgrad} (k = 41, stride 4, pad 20: the register-tiled MelGAN kernels where C_out is a multiple of 64, the
+    generic ones otherwise) against F.conv1d under autograd in fp64; ragged lengths (neither T_out nor T_in a tile multiple)."""
+    import ctypes as C
+    lib = cabi.load()
+    B, k, stride, pad = 2, 41, 4, 20
+    x = rnd(B, Cin, Tin, seed=1).double().requires_grad_(True)
+    w = (rnd(Cout, Cin // groups, k, seed=2) / math.sqrt(k * Cin // groups)).double().requires_grad_(True)
+    b = rnd(Cout, seed=3).double()
+    ref = F.conv1d(x, w, b, stride=stride, padding=pad, groups=groups)
+    Tout = ref.shape[-1]
+    dy = rnd(*ref.shape, seed=4).double()
+    ref.backward(dy)
+    dev = torch.device("cuda")
+    xg = x.detach().float().permute(0, 2, 1).contiguous().to(dev)               # [B, T, C]
+    wg, bg = w.detach().float().contiguous().to(dev), b.float().to(dev)
+    dyg = dy.float().permute(0, 2, 1).contiguous().to(dev)
+    y = torch.empty(B, Tout, Cout, device=dev)
+    dx = torch.full((B, Tin, Cin), float("nan"), device=dev)
+    dw = torch.zeros_like(wg)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    args = (B, Tin, Tout, Cin, Cout, groups, k, stride, pad)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    cabi.check(lib.aero_gconv1d_fwd(P(xg), P(wg), P(bg), P(y), *args, st), lib)
+    cabi.check(lib.aero_gconv1d_dgrad(P(dyg), P(wg), P(dx), *args, st), lib)
+    cabi.check(lib.aero_gconv1d_wgrad(P(xg), P(dyg), P(dw), *args, st), lib)
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu().permute(0, 2, 1), ref.detach()) < 1e-5
+    assert rel_l2(dx.cpu().permute(0, 2, 1), x.grad) < 1e-5
+    assert rel_l2(dw.cpu(), w.grad) < 1e-5
