@@ -297,6 +297,80 @@ __global__ void __launch_bounds__(256) tapgemm_thin_n_kernel(const TapGemmArgs g
     }
 }
 
+// thin-N over a long K with few pixels (the discriminator's 1024 -> 1 output layer: 3072-term dot products for a thousand pixels): one
+// WARP per pixel, lanes stride the channels, weights straight from L2 (coalesced float4s), shuffle reduction.
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) tapgemm_thin_n_warp_kernel(const TapGemmArgs g) {
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1 + p.C2;
+    const int lane = threadIdx.x & 31;
+    const int64_t npix = (int64_t)p.B * p.F_out * p.T;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float* W = static_cast<const float*>(g.w);
+    const bool wide = g.ldw > 4;
+    for (int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += nwarps) {
+        const int t = (int)(pix % p.T);
+        const int64_t row = pix / p.T;
+        const int fo = (int)(row % p.F_out), b = (int)(row / p.F_out);
+        float acc[kThinN];
+#pragma unroll
+        for (int n = 0; n < kThinN; ++n) acc[n] = 0.f;
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+            int fi, dt, slab;
+            if (p.mode == AERO_TAPS_CONV) {
+                const int jf = tap / p.kt, jt = tap - jf * p.kt;
+                fi = fo * p.stride_f + jf - p.pad_f; dt = jt * p.dil_t - p.pad_t; slab = tap;
+            } else {
+                const int fof = fo + p.f_out_offset;
+                fi = fof / p.stride_f - tap; dt = 0; slab = fof % p.stride_f + tap * p.stride_f;
+            }
+            const int ti = t + dt;
+            if (fi < 0 || fi >= p.F_in || ti < 0 || ti >= p.T_in) continue;
+            for (int src = 0; src < 2; ++src) {
+                const int Cs = src ? p.C2 : p.C1;
+                if (Cs == 0) continue;
+                const TA* a = src ? static_cast<const TA*>(g.a2) + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (int64_t)ti * p.a2_st
+                                  : static_cast<const TA*>(g.a1) + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + (int64_t)ti * p.a1_st;
+                const float* wc = W + ((int64_t)slab * K + (src ? p.C1 : 0)) * g.ldw;
+                for (int c = lane * 4; c < Cs; c += 128) {
+                    const float4 av = ld4(a + c);
+                    const float avs[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wc + (int64_t)(c + u) * g.ldw);
+                        acc[0] = fmaf(avs[u], w0.x, acc[0]); acc[1] = fmaf(avs[u], w0.y, acc[1]);
+                        acc[2] = fmaf(avs[u], w0.z, acc[2]); acc[3] = fmaf(avs[u], w0.w, acc[3]);
+                        if (wide) {
+                            const float4 w1 = *reinterpret_cast<const float4*>(wc + (int64_t)(c + u) * g.ldw + 4);
+                            acc[4] = fmaf(avs[u], w1.x, acc[4]); acc[5] = fmaf(avs[u], w1.y, acc[5]);
+                            acc[6] = fmaf(avs[u], w1.z, acc[6]); acc[7] = fmaf(avs[u], w1.w, acc[7]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < kThinN; ++n) acc[n] = warp_sum(acc[n]);
+        if (lane != 0) continue;
+        float sa = 1.f, sb = 0.f;
+        if (g.samp_affine) { sa = g.samp_affine[2 * b]; sb = g.samp_affine[2 * b + 1]; }
+        TO* op = static_cast<TO*>(g.out) + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf + (int64_t)t * p.o_st;
+        const TO* rp = g.residual ? static_cast<const TO*>(g.residual) + (int64_t)b * p.r_sb + (int64_t)fo * p.r_sf + (int64_t)t * p.r_st : nullptr;
+#pragma unroll
+        for (int n = 0; n < kThinN; ++n) {
+            if (n < p.N) {
+                float x = acc[n] + (g.bias ? g.bias[n] : 0.f);
+                if (p.act == AERO_ACT_GELU) x = gelu_exact(x);
+                else if (p.act == AERO_ACT_RELU) x = fmaxf(x, 0.f);
+                if (rp) x += ldf(rp + n);
+                x = x * sa + sb;
+                if ((p.flags & 1) && sizeof(TO) == 4) x = round_tf32_rna(x);
+                stf(op + n, x);
+            }
+        }
+    }
+}
+
 // thin-K (K <= 4, single tap: pre_conv 2->48): a thread owns one quad of output columns (its weights and bias stay in
 // registers) and walks over pixels; consecutive lanes = consecutive column quads of one pixel -> 16-byte coalesced stores.
 template <typename TA, typename TO>
@@ -411,6 +485,11 @@ static int tapgemm_simt_launch_t(const TapGemmArgs& g, cudaStream_t st) {
         if (blocks > 148 * 16) blocks = 148 * 16;
         tapgemm_thin_convt_kernel<TA, TO><<<blocks, 256, smem, st>>>(a, a_lo, n_a);
         return check_launch("aero_tapgemm_fwd(thin-convt)");
+    }
+    if (plain && p.N <= kThinN && g.vec_a && (int64_t)nslab * (p.C1 + p.C2) >= 1024 && (int64_t)p.B * p.F_out * p.T <= 148 * 64) {
+        const int64_t npix = (int64_t)p.B * p.F_out * p.T;           // long dot products, few pixels: a warp per pixel
+        tapgemm_thin_n_warp_kernel<TA, TO><<<(unsigned)cdiv(npix, (int64_t)8), 256, 0, st>>>(a);
+        return check_launch("aero_tapgemm_fwd(thin-n, warp per pixel)");
     }
     if (plain && p.N <= kThinN && g.vec_a && (size_t)nslab * (p.C1 + p.C2) * kThinN * 4 <= 96 * 1024) {
         const size_t smem = (size_t)nslab * (p.C1 + p.C2) * kThinN * 4;

@@ -340,6 +340,74 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     }
 }
 
+// The same reduction for 16-byte-aligned rows (N % 4 == 0): a thread owns 4 columns (one float4 per row), four rows in flight per thread,
+// row -> (outer, inner) by carries instead of a 64-bit division per element.  This is the form every bias / statistics gradient of the
+// training step takes; it runs at HBM speed where the scalar kernel above reaches a fifth of it.
+template <typename OUT>
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ x, const float* __restrict__ z, OUT* out1, OUT* out2,
+                                                      int N, int64_t n_inner, int64_t inner_s, int64_t n_outer, int64_t outer_s,
+                                                      int64_t seg_sx, int64_t seg_so) {
+    __shared__ float4 s1[8][32], s2[8][32];
+    const int col = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int seg = blockIdx.z;
+    const int64_t rows = n_inner * n_outer;
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+    if (col < N) {
+        const float* xb = x + (int64_t)seg * seg_sx + col;
+        const float* zb = z ? z + (int64_t)seg * seg_sx + col : nullptr;
+        const int64_t step = (int64_t)gridDim.y * 8;
+        int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y;
+        int64_t o = r / n_inner, i = r - o * n_inner;
+        const int64_t d_o = step / n_inner, d_i = step - d_o * n_inner;
+        auto advance = [&]() {
+            r += step; i += d_i; o += d_o;
+            if (i >= n_inner) { i -= n_inner; ++o; }
+        };
+        while (r + 3 * step < rows) {
+            float4 v[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t off = o * outer_s + i * inner_s;
+                v[u] = *reinterpret_cast<const float4*>(xb + off);
+                if (zb) w[u] = *reinterpret_cast<const float4*>(zb + off);
+                advance();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a1.x += v[u].x; a1.y += v[u].y; a1.z += v[u].z; a1.w += v[u].w;
+                if (zb) { a2.x = fmaf(v[u].x, w[u].x, a2.x); a2.y = fmaf(v[u].y, w[u].y, a2.y); a2.z = fmaf(v[u].z, w[u].z, a2.z); a2.w = fmaf(v[u].w, w[u].w, a2.w); }
+            }
+        }
+        for (; r < rows; advance()) {
+            const int64_t off = o * outer_s + i * inner_s;
+            const float4 v = *reinterpret_cast<const float4*>(xb + off);
+            a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+            if (zb) {
+                const float4 w = *reinterpret_cast<const float4*>(zb + off);
+                a2.x = fmaf(v.x, w.x, a2.x); a2.y = fmaf(v.y, w.y, a2.y); a2.z = fmaf(v.z, w.z, a2.z); a2.w = fmaf(v.w, w.w, a2.w);
+            }
+        }
+    }
+    s1[threadIdx.y][threadIdx.x] = a1;
+    s2[threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < N) {
+        float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 p1 = s1[k][threadIdx.x], p2 = s2[k][threadIdx.x];
+            t1.x += p1.x; t1.y += p1.y; t1.z += p1.z; t1.w += p1.w;
+            t2.x += p2.x; t2.y += p2.y; t2.z += p2.z; t2.w += p2.w;
+        }
+        const float e1[4] = {t1.x, t1.y, t1.z, t1.w}, e2[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (out1) atomicAdd(out1 + (int64_t)seg * seg_so + col + u, (OUT)e1[u]);
+            if (out2) atomicAdd(out2 + (int64_t)seg * seg_so + col + u, (OUT)e2[u]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------ add
 __global__ void __launch_bounds__(256) add_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, float alpha) {
     const int64_t n4 = n >> 2;
@@ -742,6 +810,23 @@ extern "C" int aero_colsum(const float* x, const float* z, void* out1, void* out
     using namespace aero;
     AERO_REQUIRE(x && (out1 || out2) && N >= 1 && n_inner >= 1 && n_outer >= 1 && n_seg >= 1 && n_seg <= 65535, "aero_colsum: bad argument");
     const int64_t rows = n_inner * n_outer;
+    if (N % 4 == 0 && inner_stride % 4 == 0 && outer_stride % 4 == 0 && seg_stride_x % 4 == 0 &&
+        ((((uintptr_t)x) | ((uintptr_t)z)) & 15) == 0) {
+        const int xt = cdiv(N, 128);
+        int64_t ys = (rows + 8 * 16 - 1) / (8 * 16);                   // at least 16 rows per thread
+        const int64_t cap4 = (int64_t)148 * 8 / ((int64_t)xt * n_seg) + 1;
+        if (ys > cap4) ys = cap4;
+        if (ys < 1) ys = 1;
+        if (ys > 65535) ys = 65535;
+        dim3 grid4((unsigned)xt, (unsigned)ys, (unsigned)n_seg), block4(32, 8);
+        if (out_double)
+            colsum4_kernel<double><<<grid4, block4, 0, (cudaStream_t)stream>>>(x, z, (double*)out1, (double*)out2, N, n_inner, inner_stride,
+                                                                              n_outer, outer_stride, seg_stride_x, seg_stride_out);
+        else
+            colsum4_kernel<float><<<grid4, block4, 0, (cudaStream_t)stream>>>(x, z, (float*)out1, (float*)out2, N, n_inner, inner_stride,
+                                                                             n_outer, outer_stride, seg_stride_x, seg_stride_out);
+        return check_launch("aero_colsum");
+    }
     int64_t ysplit = (rows + 8 * 64 - 1) / (8 * 64);
     const int64_t cap = (int64_t)148 * 16 / (cdiv(N, 32) * (int64_t)n_seg) + 1;
     if (ysplit > cap) ysplit = cap;

@@ -362,6 +362,15 @@ class TrainEngine:
     def _freq_mix(self, x, Wfc, gate, B, Fq, M):
         """out[b][f'][m] = gate[b][m] * sum_f Wfc[f'][f] x[b][f][m]  (a tap-GEMM whose 'weights' are the activations)."""
         out = self._new(B * Fq * M)
+        if self.precision == 1 and Fq >= 8 and Fq % 4 == 0 and M % 4 == 0:
+            # TF32 mode: contraction over the row axis on the tensor cores, activations as the MN-major operand (AERO_TAPS_MIX, as the
+            # inference engine does); the weight is its own K-major form [F', F]
+            p = self._tg(B=B, F_out=1, T=M, N=Fq, C1=Fq, mode=cabi.TAPS_MIX, a1_s=(Fq * M, 0, M), o_s=(Fq * M, 0, M),
+                         cs_s=(M, 0) if gate is not None else (0, 0))
+            p.precision = 1
+            self._check(self.lib.aero_tapgemm_fwd(_ptr(x), None, _ptr(tf32_round(Wfc.contiguous())), None, None, _ptr(gate), None, None, _ptr(out),
+                                                  None, C.byref(p), self._stream()))
+            return out
         p = self._tg(B=B, F_out=1, T=Fq, T_in=Fq, N=M, C1=Fq, a1_s=(0, 0, Fq), w_sb=Fq * M, o_s=(Fq * M, 0, M),
                      cs_s=(M, 0) if gate is not None else (0, 0))
         self._gemm_call(p, out, x, a1=Wfc.contiguous(), colscale=gate)

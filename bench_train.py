@@ -91,7 +91,8 @@ def main(args):
     lib = cabi.load()
     model = B.build_model(B.CONFIGS["4-16"]).to(dev).train()
     adversarial = not os.environ.get("AERO_TRAIN_NO_GAN")
-    train_precision = int(os.environ.get("AERO_TRAIN_PRECISION", "0"))
+    env_precision = os.environ.get("AERO_TRAIN_PRECISION")
+    train_precision = int(env_precision or "0")
     model.train_precision = train_precision
     if adversarial:
         torch.manual_seed(B.SEED + 1)
@@ -151,9 +152,25 @@ def main(args):
     barrier()
     per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     ms_e2e = B.median(per_step)
+    # the other arithmetic mode of the same step, device-timed the same way (exact fp32 <-> TF32 tensor-core GEMMs)
+    other = 1 - train_precision if train_precision in (0, 1) and env_precision is None else None
+    ms_other = None
+    if other is not None:
+        model.train_precision = other
+        if adversarial:
+            disc.train_precision = other
+        for _ in range(3):
+            one_step(lr_d, hr_d)
+        barrier()
+        ms_other = B.timed_steps(lambda: one_step(lr_d, hr_d), args.steps, barrier)
+        model.train_precision = train_precision
+        if adversarial:
+            disc.train_precision = train_precision
     sampler.stop_flag = True
     from aero_b200.parallel import reduce_max
     ms_dev, ms_e2e = reduce_max(ms_dev, dev), reduce_max(ms_e2e, dev)
+    if ms_other is not None:
+        ms_other = reduce_max(ms_other, dev)
     if rank == 0:
         pk = B.peaks()
         total = bsz * world
@@ -163,11 +180,13 @@ def main(args):
         first, last = float(losses[0]), float(losses[-1])
         line = {"metric": "audio-seconds/sec training step", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (exact-fp32 SIMT tap-GEMMs for forward, dgrad and wgrad; fp64 reduction accumulators)", "data": "synthetic",
+                "dtype": ("f32 (exact-fp32 SIMT tap-GEMMs for forward, dgrad and wgrad; fp64 reduction accumulators)" if train_precision == 0 else
+                          "tf32 tensor-core GEMMs (tcgen05: forward, dgrad, wgrad of the convolutions), fp32 everything else, fp64 reduction accumulators"),
+                "data": "synthetic",
                 "config": {"workload": f"{EXP} training step (G + MelGAN-D + MR-STFT, Adam: reference adversarial config), batch {bsz}/GPU "
                                        f"x 2 s paired white-noise clips (BASELINE configs[3])", "config_key": "train", "global_batch": total,
                            "parallelism": f"data-parallel x{world}: flat-buffer NCCL all-reduce of the generator gradients, overlapped with backward",
-                           "adversarial": bool(adversarial),
+                           "adversarial": bool(adversarial), "train_precision": train_precision,
                            "step": ("generator forward (train) + MR-STFT + 3 MelGAN-discriminator forwards + G backward + Adam + D backward + Adam"
                                     if adversarial else "generator forward (train) + MR-STFT + backward + Adam"),
                            "l2": "activations saved for backward (~1 GB/step) exceed the 126 MB L2; no explicit flush"},
@@ -179,8 +198,16 @@ def main(args):
                 "roofline": {"bound": "tensor", "kernel": "whole step (forward + dgrad + wgrad tap-GEMMs dominate)", "achieved": step_tflops,
                              "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": step_tflops / pk["bf16_tflops"],
                              "frac_of_fp32_simt_peak": step_tflops / fp32_peak, "fp32_simt_peak": fp32_peak,
-                             "note": "the training step runs on exact-fp32 SIMT kernels (gradient parity first); its distance to the tensor-core "
-                                     "roofline is the cost of not yet having TF32/FP16 wgrad / dgrad paths", "traffic": None}}
+                             "note": ("the default training step runs on exact-fp32 SIMT kernels (gradient parity first); `other_mode` is the same step "
+                                      "with the convolution GEMMs on the tensor cores in TF32") if train_precision == 0 else
+                                     "convolution GEMMs on tcgen05 in TF32; LSTM recurrence, attention, normalisation and the grouped discriminator "
+                                     "convolutions are fp32 SIMT", "traffic": None}}
+        if ms_other is not None:
+            line["other_mode"] = {"train_precision": other, "ms_per_step": ms_other, "value": total * SECONDS / (ms_other * 1e-3), "unit": "audio-s/s",
+                                  "what": ("model.train_precision = 1: the convolutions' forward / dgrad / wgrad GEMMs in TF32 on tcgen05 (what cuDNN does for "
+                                           "the reference under PyTorch's default allow_tf32); gradient deviation from the fp64 reference 5e-2 .. 7e-2 "
+                                           "against 1e-3 .. 5e-3 in the exact mode (tests/test_gpu_train_tc.py)") if other == 1 else
+                                          "model.train_precision = 0: exact-fp32 SIMT GEMMs (the gradient-parity mode)"}
         if not args.no_cpu_baseline and world == 1:
             os.sched_setaffinity(0, range(os.cpu_count() or 1))
             threads = min(B.physical_cores(), 32)

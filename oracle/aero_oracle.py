@@ -155,7 +155,7 @@ def lstm_stack(x, sd, prefix, layers, explicit=False):
     if not explicit:
         H = sd[names[1]].shape[1]
         zeros = x.new_zeros(2 * layers, x.shape[1], H)
-        out, _, _ = torch.lstm(x, (zeros, zeros), [sd[n] for n in names], True, layers, 0.0, False, True, False)
+        out, _, _ = torch.lstm(x, (zeros, zeros), [sd[n] for n in names], True, layers, 0.0, BN_TRAIN, True, False)   # train flag: cuDNN needs it for backward; dropout is 0
         return out
     for l in range(layers):
         p = [sd[n] for n in names[8 * l:8 * l + 8]]

@@ -136,8 +136,10 @@ def test_wgrad_tc_against_simt_kernel_directly():
 @pytest.mark.parametrize("case", ["t1_4-16_hop256", "t3_11-44_stereo"])
 def test_generator_gradients_tf32_mode_against_fp64_golden(golden_dir, case):
     """Whole-model gradients in the TF32 mode against the committed fp64 golden of the reference (tests/golden/make_golden_train.py).
-    The bar is what TF32 arithmetic through ~60 chained GEMMs supports: the step direction (all gradients as one vector) within 1e-2,
-    no parameter beyond 1e-1 (the exact-fp32 mode's bars on the same files: 1e-3 / 5e-3 and 5e-2, tests/test_gpu_train.py)."""
+    This network's gradient is badly conditioned (GroupNorm / BatchNorm backward subtract projections of nearly equal size, ReLU kinks
+    behind BatchNorm: its own fp32 run is 1.3e-3 .. 2.9e-3 from its fp64 run), so 2^-11 operand errors surface as a few percent: measured
+    4.9e-2 .. 7.4e-2 for all gradients as one vector, the same as the reference algorithm under PyTorch's default cuDNN TF32 (next test).
+    Bars: forward output 2e-3, all gradients together 1e-1, no parameter beyond 0.5 (a wrong kernel gives O(1) on everything upstream)."""
     import os
     import numpy as np
     from util import trained_like_, weights_digest, white_noise
@@ -161,5 +163,84 @@ def test_generator_gradients_tf32_mode_against_fp64_golden(golden_dir, case):
     for err, name, rms in rows[:6]:
         print(f"   {err:.3e}  {name}  (ref rms {rms:.3e})")
     assert e_out < 2e-3
-    assert total < 1e-2, total
-    assert rows[0][0] < 1e-1, rows[:5]
+    assert total < 1e-1, total
+    assert rows[0][0] < 0.5, rows[:5]
+
+
+def _total_deviation(grads, g):
+    """All gradients as one vector against the golden samples (the `total` of test_gpu_train.grad_report), from a name -> tensor map."""
+    import numpy as np
+    num = den = 0.0
+    for name, got_t in grads.items():
+        ref = torch.from_numpy(g["g_val/" + name]).double()
+        idx = torch.from_numpy(g["g_idx/" + name].astype(np.int64))
+        got = got_t.detach().reshape(-1).cpu().double()[idx]
+        scale = got_t.numel() / ref.numel()
+        num += scale * float((got - ref).pow(2).sum())
+        den += scale * float(ref.pow(2).sum())
+    return (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("case", ["t1_4-16_hop256"])
+def test_tf32_mode_is_as_accurate_as_the_reference_under_pytorchs_default_tf32(golden_dir, case):
+    """Calibration of the TF32 training mode.  The reference trains on a GPU with PyTorch's defaults, i.e. cuDNN convolutions and the
+    cuDNN LSTM in TF32 (torch.backends.cudnn.allow_tf32 = True).  The oracle (the reference's algorithm as torch functional code) is run
+    here on the GPU under exactly those defaults and its gradients are measured against the fp64 golden; this library's TF32 mode must
+    not deviate more than 1.5x as much -- i.e. switching it on costs no more accuracy than the reference's own default arithmetic."""
+    import os
+    import numpy as np
+    from util import trained_like_, white_noise
+    from test_gpu_train import cotangent
+    from oracle import aero_oracle as O
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    torch.manual_seed(SEED)
+    m = Aero(**aero_kwargs(str(g["exp"])))
+    m.load_state_dict(trained_like_(m.state_dict()))
+    mix = white_noise((int(g["B"]), m.in_channels, int(g["L"]))).cuda()
+    R = cotangent(tuple(int(v) for v in g["out_shape"]), SEED).cuda()
+    names = [n for n, _ in m.named_parameters()]
+
+    def oracle_grads(allow_tf32):
+        sd = {k: (v.clone().cuda().requires_grad_(k in names) if v.dtype.is_floating_point else v.clone().cuda()) for k, v in m.state_dict().items()}
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = allow_tf32
+        O.BN_TRAIN = True
+        try:
+            out = O.aero_forward(sd, m.geom, mix)
+            ((out * R).sum() / out.numel()).backward()
+        finally:
+            O.BN_TRAIN = False
+            torch.backends.cudnn.allow_tf32 = old
+        return {k: sd[k].grad for k in names if sd[k].grad is not None}
+
+    dev_ref_tf32 = _total_deviation(oracle_grads(True), g)
+    dev_ref_fp32 = _total_deviation(oracle_grads(False), g)
+    mm = m.cuda().train()
+    devs = {}
+    for prec in (0, 1):
+        mm.train_precision = prec
+        mm.zero_grad(set_to_none=True)
+        out = mm(mix)
+        ((out * R).sum() / out.numel()).backward()
+        devs[prec] = _total_deviation({n: p.grad for n, p in mm.named_parameters()}, g)
+    torch.cuda.synchronize()
+    print(f"{case}: all-gradient deviation from the fp64 golden -- reference algorithm on this GPU: fp32 {dev_ref_fp32:.3e}, PyTorch-default TF32 "
+          f"{dev_ref_tf32:.3e}; this library: exact mode {devs[0]:.3e}, TF32 mode {devs[1]:.3e}")
+    assert devs[0] < 5e-3
+    assert devs[1] < 1.5 * max(dev_ref_tf32, 1e-3) or devs[1] < 1e-2, (devs, dev_ref_tf32)
+
+
+@pytest.mark.parametrize("Fq,M", [(8, 1504), (16, 3000), (64, 4808), (256, 2004)])
+def test_gated_frequency_mix_tf32(eng, Fq, M):
+    """FTB's frequency mix out[b][f'][m] = gate[b][m] * sum_f W[f'][f] x[b][f][m] on the tensor cores (AERO_TAPS_MIX) against fp64."""
+    e = eng
+    e._reset()
+    B = 2
+    x, Wfc, gate = rnd(B, Fq, M, seed=1), rnd(Fq, Fq, seed=2) / math.sqrt(Fq), rnd(B, M, seed=3)
+    ref = torch.einsum("gf,bfm->bgm", Wfc.double(), x.double()) * gate.double()[:, None, :]
+    out = e._freq_mix(x.cuda().reshape(-1), Wfc.cuda(), gate.cuda().reshape(-1), B, Fq, M)
+    un = e._freq_mix(x.cuda().reshape(-1), Wfc.cuda(), None, B, Fq, M)
+    torch.cuda.synchronize()
+    err = rel_l2(out.view(B, Fq, M).cpu(), ref)
+    assert 1e-6 < err < TOL, err
+    assert rel_l2(un.view(B, Fq, M).cpu(), torch.einsum("gf,bfm->bgm", Wfc.double(), x.double())) < TOL
