@@ -228,6 +228,23 @@ __global__ void __launch_bounds__(kWsThreads) wgrad_small_kernel(const WgradArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------ weight repack
+// [taps][K][ldn] (N contiguous: the SIMT tap-GEMM layout) -> [taps][ldn][K] (K contiguous: the tcgen05 layout), rounded to TF32
+// (round-to-nearest, ties away: cvt.rna) -- the training step repacks every weight it uses, every step, so this is one launch instead
+// of a transpose, an add and a mask.
+__global__ void __launch_bounds__(256) pack_kmajor_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int ldn) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z, k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* src = w + (int64_t)tap * K * ldn;
+    float* dst = out + (int64_t)tap * K * ldn;
+    for (int r = ty; r < 32; r += 8)
+        tile[r][tx] = (k0 + r < K && n0 + tx < ldn) ? src[(int64_t)(k0 + r) * ldn + n0 + tx] : 0.f;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (n0 + r < ldn && k0 + tx < K) dst[(int64_t)(n0 + r) * K + k0 + tx] = round_tf32_rna(tile[tx][r]);
+}
+
 // ------------------------------------------------------------------------------------------------------------ gram
 // out[i][j] += sum_{b, m} P[b][i][m] * gate[b][m] * Q[b][j][m]   (i, j < F rows; m < M contiguous positions): the weight
 // gradient of FTB's frequency mix `freq_fc` (modules.py:296,317-320), whose contraction runs over the CONTIGUOUS axis of two
@@ -802,6 +819,14 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
     if (TN == 128) wgrad_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     else wgrad_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     return check_launch("aero_tapgemm_wgrad");
+}
+
+extern "C" int aero_pack_kmajor_tf32(const float* w, float* out, int32_t taps, int32_t K, int32_t ldn, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(w && out && taps >= 1 && taps <= 65535 && K >= 1 && ldn >= 1, "aero_pack_kmajor_tf32: bad argument");
+    dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(ldn, 32), (unsigned)taps);
+    pack_kmajor_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, out, K, ldn);
+    return check_launch("aero_pack_kmajor_tf32");
 }
 
 extern "C" int aero_colsum(const float* x, const float* z, void* out1, void* out2, int32_t out_double, int32_t N, int64_t n_inner,

@@ -302,6 +302,64 @@ __global__ void __launch_bounds__(256) gconv41_dgrad_kernel(const float* __restr
     }
 }
 
+// weight gradient: thread = one (output channel, input channel of its group) pair, all 41 taps in registers; per 4 output steps it
+// loads one float4 of the gradient and a 56-step input window (14 float4s) for 656 FMAs.  Split over (batch, time tiles) with fp32 atomics.
+constexpr int kG4Dy = 68;                      // gradient tile rows [64 channels][68 steps]
+__global__ void __launch_bounds__(256) gconv41_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                                            const GconvP p, const int chunks) {
+    extern __shared__ __align__(16) float sm[];
+    const int opg = p.Cout / p.groups;
+    const int co0 = blockIdx.x * kG4Co;
+    const int g0 = co0 / opg;
+    const int nch = (kG4Co / opg) * kG4Cpg;
+    float* dys = sm;                                                  // [64][68]
+    float* xs = sm + kG4Co * kG4Dy;                                   // [nch][300]
+    const int cl = threadIdx.x >> 2, c = threadIdx.x & 3;
+    const int gl = cl / opg;
+    float acc[kG4K];
+#pragma unroll
+    for (int j = 0; j < kG4K; ++j) acc[j] = 0.f;
+    constexpr int win = (kG4T - 1) * kG4S + kG4K;
+    const int tiles_t = (p.Tout + kG4T - 1) / kG4T;
+    const int n_tiles = p.B * tiles_t;
+    for (int tile = blockIdx.y; tile < n_tiles; tile += chunks) {
+        const int b = tile / tiles_t, to0 = (tile - b * tiles_t) * kG4T;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kG4T * kG4Co; i += 256) {
+            const int tl = i / kG4Co, q = i - tl * kG4Co;
+            dys[q * kG4Dy + tl] = (to0 + tl < p.Tout) ? dy[((int64_t)b * p.Tout + to0 + tl) * p.Cout + co0 + q] : 0.f;
+        }
+        const int ti0 = to0 * kG4S - kG4Pad;
+        for (int i = threadIdx.x; i < kG4Xw * nch; i += 256) {
+            const int tt = i / nch, ch = i - tt * nch;
+            const int ti = ti0 + tt;
+            xs[ch * kG4Xw + tt] = (tt < win && ti >= 0 && ti < p.Tin) ? x[((int64_t)b * p.Tin + ti) * p.Cin + g0 * kG4Cpg + ch] : 0.f;
+        }
+        __syncthreads();
+        const float* dr = dys + cl * kG4Dy;
+        const float* xr = xs + (gl * kG4Cpg + c) * kG4Xw;
+#pragma unroll 1
+        for (int tq = 0; tq < kG4T / 4; ++tq) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dr + 4 * tq);
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            float xw[56];
+#pragma unroll
+            for (int i = 0; i < 14; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + 16 * tq + 4 * i);
+                xw[4 * i] = v.x; xw[4 * i + 1] = v.y; xw[4 * i + 2] = v.z; xw[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < kG4K; ++j) acc[j] = fmaf(dv[u], xw[kG4S * u + j], acc[j]);
+        }
+    }
+    float* out = dw + ((int64_t)(co0 + cl) * kG4Cpg + c) * kG4K;
+#pragma unroll
+    for (int j = 0; j < kG4K; ++j)
+        if (acc[j] != 0.f) atomicAdd(out + j, acc[j]);
+}
+
 static bool gconv41_ok(const GconvP& p) {
     if (p.k != kG4K || p.stride != kG4S || p.pad != kG4Pad || p.Cin != p.groups * kG4Cpg || p.Cout % kG4Co) return false;
     const int opg = p.Cout / p.groups;
@@ -422,6 +480,18 @@ extern "C" int aero_gconv1d_wgrad(const float* x, const float* dy, float* dw, in
     const GconvP p{B, Tin, Tout, Cin, Cout, groups, k, stride, pad};
     int rc = gconv_check(p);
     if (rc != AERO_OK) return rc;
+    if (gconv41_ok(p)) {
+        const int nch = (kG4Co / (Cout / groups)) * kG4Cpg;
+        const size_t smem4 = sizeof(float) * ((size_t)kG4Co * kG4Dy + (size_t)nch * kG4Xw);
+        cudaFuncSetAttribute(gconv41_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+        const int n_tiles4 = B * cdiv(Tout, kG4T);
+        int chunks4 = (148 * 4) / (Cout / kG4Co) + 1;
+        if (chunks4 > n_tiles4) chunks4 = n_tiles4;
+        if (chunks4 > 65535) chunks4 = 65535;
+        dim3 grid4(Cout / kG4Co, chunks4);
+        gconv41_wgrad_kernel<<<grid4, 256, smem4, (cudaStream_t)stream>>>(x, dy, dw, p, chunks4);
+        return check_launch("aero_gconv1d_wgrad(k41)");
+    }
     const int cpg = Cin / groups;
     AERO_REQUIRE(kGcCo * cpg <= 512, "aero_gconv1d_wgrad: at most 8 input channels per group");
     const size_t smem = gconv_smem(p, 0);

@@ -126,7 +126,9 @@ class TrainEngine:
         if p.precision == 1:
             # tcgen05 path: K-major TF32 twin [taps, pad4(N), K] of the packed weight [taps, K, pad4(N)]; shapes it does not take stay SIMT
             if p.w_sb == 0 and colscale is None and w.dim() == 3 and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
-                w = tf32_round(w.permute(0, 2, 1).contiguous())
+                wk = torch.empty(w.shape[0], w.shape[2], w.shape[1], device=w.device, dtype=torch.float32)
+                self._check(self.lib.aero_pack_kmajor_tf32(_ptr(w), _ptr(wk), w.shape[0], w.shape[1], w.shape[2], self._stream()))
+                w = wk
             else:
                 p.precision = 0
         self._check(self.lib.aero_tapgemm_fwd(_ptr(a1), _ptr(a2), _ptr(w), _ptr(bias), None, _ptr(colscale), _ptr(residual),

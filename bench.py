@@ -207,7 +207,7 @@ def pick_cpu_threads(cfg_key):
     n = physical_cores()
     seen = {}
     for c in sorted({n, min(n, 32), min(n, 16)}, reverse=True):
-        t = _probe(cfg_key, c, 4, 1, 1, 150)
+        t = _probe(cfg_key, c, 4, 1, 1, 90)
         if t:
             seen[c] = t[0]
     if not seen:
@@ -224,13 +224,14 @@ def run_reference(args, cfg, rank, world):
     threads, probes = pick_cpu_threads(args.config)
     batch = cfg["batch"]
     per_clip = (probes[threads] / 4) if threads in probes else 1.0
-    # keep the workload's own batch; only if (steps + warmup) forwards of it would run past ~10 minutes, shrink the sample
-    if per_clip * batch * (args.steps + args.warmup) > 600.0:
-        batch = max(1, int(600.0 / (per_clip * (args.steps + args.warmup))))
+    # keep the workload's own batch; only if (steps + warmup) forwards of it would run past ~4 minutes, shrink the sample (the whole arm,
+    # thread probes and the single-thread B=1 line included, then ends in about 6 minutes on this pool's hosts)
+    if per_clip * batch * (args.steps + args.warmup) > 240.0:
+        batch = max(1, int(240.0 / (per_clip * (args.steps + args.warmup))))
     times = cpu_forward_times(cfg, batch, threads, args.steps, args.warmup)
     dt = sum(times) / len(times)
     val = batch * cfg["seconds"] / dt
-    one = _probe(args.config, 1, 1, 3, 1, 300)
+    one = _probe(args.config, 1, 1, 3, 1, 120)
     line = {"impl": "reference", "metric": "audio-seconds/sec forward", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_step_median": median(times) * 1e3,
             "higher_is_better": True, "scaling": "weak",
@@ -465,7 +466,7 @@ def main():
             # `--impl reference` runs): the workload's own batch, all physical cores, 1 warm-up, median of 3
             cb = B if args.config == "4-16" else max(1, B // 4)
             ts = _probe(args.config, threads, cb, 3, 1, 600)
-            one = _probe(args.config, 1, 1, 3, 1, 300) if args.config == "4-16" else None
+            one = _probe(args.config, 1, 1, 3, 1, 120) if args.config == "4-16" else None
             line["cpu_baseline"] = {"value": (cb * secs / median(ts)) if ts else None, "unit": "audio-s/s", "cores": threads,
                                     "kind": "port",
                                     "host_cores": {"logical": os.cpu_count(), "physical": physical_cores()},

@@ -315,6 +315,9 @@ int aero_stft_loss_bwd(const float* z_est, const float* z_ref, const double* sum
  * geometry of aero_tapgemm_fwd for `p` (mode AERO_TAPS_CONV or AERO_TAPS_CONVT; A = channel concat of a1, a2).  dY is addressed
  * with p->o_sb / o_sf / o_st; element (n, k, slab) of dW lives at dw + n*dw_sn + k*dw_sk + slab*dw_ss (so the gradient can be
  * written straight into PyTorch's [N][K][kf][kt] or ConvTranspose [K][N][kf][1] parameter layout).  The caller zeroes dW.
+ * p->precision: 0 = exact fp32 (SIMT; a one-thread-per-weight kernel when the layer has at most 2048 weights); 1 = TF32 on the
+ * tensor cores (csrc/wgrad_tc.cu: both operands MN-major through TMA, split over the pixel axis, fp32 atomics) where the shape allows
+ * (N >= 16, K >= 16, channel counts and strides multiples of 4, 16-byte aligned bases), exact fp32 otherwise.
  * Replaces the cuDNN wgrad kernels behind autograd of nn.Conv2d / ConvTranspose2d / Conv1d / Linear. */
 int aero_tapgemm_wgrad(const float* a1, const float* a2, const float* dy, float* dw, const aero_tapgemm_params* p,
                        int64_t dw_sn, int64_t dw_sk, int64_t dw_ss, aero_stream_t stream);
@@ -392,6 +395,10 @@ int aero_gconv1d_wgrad(const float* x, const float* dy, float* dw, int32_t B, in
 int aero_weight_norm_fwd(const float* v, const float* g, float* w, int32_t rows, int32_t len, aero_stream_t stream);
 int aero_weight_norm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t rows, int32_t len,
                          aero_stream_t stream);
+
+/* Weight repack for the TF32 training mode: w [taps][K][ldn] (the aero_tapgemm_fwd precision-0 layout, ldn = N rounded up to 4) ->
+ * out [taps][ldn][K] (the precision-1 layout), every element rounded to TF32 (round to nearest, ties away). */
+int aero_pack_kmajor_tf32(const float* w, float* out, int32_t taps, int32_t K, int32_t ldn, aero_stream_t stream);
 
 /* Fused multi-tensor Adam (torch.optim.Adam semantics, no amsgrad / weight decay; reference train.py:83).  chunk_table: device
  * array of n_chunks records {float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64 count}; one CTA per
