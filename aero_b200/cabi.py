@@ -99,7 +99,9 @@ SYMBOLS = {
     "aero_norm_act_train_fwd": (C.c_int, [vp] * 8 + [C.POINTER(NormActParams), vp]),
     "aero_norm_act_train_bwd": (C.c_int, [vp] * 13 + [i32, C.POINTER(NormActParams), vp]),
     "aero_adam_step": (C.c_int, [vp, i32, f32, f32, f32, f32, i32, f32, vp]),
-    "aero_pack_kmajor_tf32": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "aero_pack_kmajor_tf32": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
+    "aero_split_tf32": (C.c_int, [vp, vp, vp, i64, vp]),
+    "aero_tapgemm_wgrad_tc_eligible": (C.c_int, [C.POINTER(TapGemmParams), vp, vp, vp]),
     "aero_gconv1d_fwd": (C.c_int, [vp, vp, vp, vp] + [i32] * 9 + [vp]),
     "aero_gconv1d_dgrad": (C.c_int, [vp, vp, vp] + [i32] * 9 + [vp]),
     "aero_gconv1d_wgrad": (C.c_int, [vp, vp, vp] + [i32] * 9 + [vp]),

@@ -232,17 +232,42 @@ __global__ void __launch_bounds__(kWsThreads) wgrad_small_kernel(const WgradArgs
 // [taps][K][ldn] (N contiguous: the SIMT tap-GEMM layout) -> [taps][ldn][K] (K contiguous: the tcgen05 layout), rounded to TF32
 // (round-to-nearest, ties away: cvt.rna) -- the training step repacks every weight it uses, every step, so this is one launch instead
 // of a transpose, an add and a mask.
-__global__ void __launch_bounds__(256) pack_kmajor_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int ldn) {
+__global__ void __launch_bounds__(256) pack_kmajor_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, float* __restrict__ out_lo,
+                                                               int K, int ldn) {
     __shared__ float tile[32][33];
     const int tap = blockIdx.z, k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float* src = w + (int64_t)tap * K * ldn;
-    float* dst = out + (int64_t)tap * K * ldn;
     for (int r = ty; r < 32; r += 8)
         tile[r][tx] = (k0 + r < K && n0 + tx < ldn) ? src[(int64_t)(k0 + r) * ldn + n0 + tx] : 0.f;
     __syncthreads();
     for (int r = ty; r < 32; r += 8)
-        if (n0 + r < ldn && k0 + tx < K) dst[(int64_t)(n0 + r) * K + k0 + tx] = round_tf32_rna(tile[tx][r]);
+        if (n0 + r < ldn && k0 + tx < K) {
+            const float v = tile[tx][r], hi = round_tf32_rna(v);
+            const int64_t o = (int64_t)tap * K * ldn + (int64_t)(n0 + r) * K + k0 + tx;
+            out[o] = hi;
+            if (out_lo) out_lo[o] = round_tf32_rna(v - hi);          // v - hi is exact in fp32; its TF32 rounding leaves 2^-22 |v|
+        }
+}
+
+// x = hi + lo with hi = TF32(x) (round to nearest) and lo = TF32(x - hi): the operand split of the 3xTF32 GEMM (three tensor-core products
+// hi*hi + hi*lo + lo*hi reproduce the fp32 product to ~2^-22)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        float4 h, l;
+        h.x = round_tf32_rna(v.x); h.y = round_tf32_rna(v.y); h.z = round_tf32_rna(v.z); h.w = round_tf32_rna(v.w);
+        l.x = round_tf32_rna(v.x - h.x); l.y = round_tf32_rna(v.y - h.y); l.z = round_tf32_rna(v.z - h.z); l.w = round_tf32_rna(v.w - h.w);
+        reinterpret_cast<float4*>(hi)[i] = h;
+        reinterpret_cast<float4*>(lo)[i] = l;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) {
+            const float h = round_tf32_rna(x[i]);
+            hi[i] = h;
+            lo[i] = round_tf32_rna(x[i] - h);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------------------ gram
@@ -821,12 +846,27 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
     return check_launch("aero_tapgemm_wgrad");
 }
 
-extern "C" int aero_pack_kmajor_tf32(const float* w, float* out, int32_t taps, int32_t K, int32_t ldn, aero_stream_t stream) {
+extern "C" int aero_pack_kmajor_tf32(const float* w, float* out, float* out_lo, int32_t taps, int32_t K, int32_t ldn, aero_stream_t stream) {
     using namespace aero;
     AERO_REQUIRE(w && out && taps >= 1 && taps <= 65535 && K >= 1 && ldn >= 1, "aero_pack_kmajor_tf32: bad argument");
     dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(ldn, 32), (unsigned)taps);
-    pack_kmajor_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, out, K, ldn);
+    pack_kmajor_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, out, out_lo, K, ldn);
     return check_launch("aero_pack_kmajor_tf32");
+}
+
+extern "C" int aero_split_tf32(const float* x, float* hi, float* lo, int64_t n, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(x && hi && lo && n >= 1, "aero_split_tf32: bad argument");
+    AERO_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "aero_split_tf32: 16-byte aligned buffers");
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+    return check_launch("aero_split_tf32");
+}
+
+extern "C" int aero_tapgemm_wgrad_tc_eligible(const aero_tapgemm_params* p, const float* a1, const float* a2, const float* dy) {
+    return p && aero::wgrad_tc_eligible(*p, a1, a2, dy) ? 1 : 0;
 }
 
 extern "C" int aero_colsum(const float* x, const float* z, void* out1, void* out2, int32_t out_double, int32_t N, int64_t n_inner,

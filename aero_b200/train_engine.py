@@ -49,9 +49,12 @@ class TrainEngine:
         self.geom = model.geom
         self.lib = cabi.load()
         self._windows = {}
-        # 0: exact-fp32 SIMT tap-GEMMs everywhere (the gradient-parity mode, default).  1: the convolutions' forward, data-gradient and
-        # weight-gradient GEMMs run on the tcgen05 tensor cores in TF32 (what cuDNN does for the reference under PyTorch's default
-        # torch.backends.cudnn.allow_tf32); normalisation, LSTM recurrence, attention and all reductions stay fp32 / fp64.
+        # Arithmetic of the convolutions' forward, data-gradient and weight-gradient GEMMs (normalisation, LSTM recurrence, attention and
+        # all reductions are fp32 / fp64 in every mode):
+        #   0  exact-fp32 SIMT tap-GEMMs (the original gradient-parity mode);
+        #   1  TF32 on the tcgen05 tensor cores (what cuDNN does for the reference under PyTorch's default cudnn.allow_tf32);
+        #   3  "3xTF32": every operand split into hi + lo TF32 halves, three tensor-core products hi*hi + hi*lo + lo*hi summed in fp32 --
+        #      fp32-grade results (~2^-22 per product) at tensor-core speed.
         self.precision = int(getattr(model, "train_precision", 0))
         self._reset()
 
@@ -120,20 +123,95 @@ class TrainEngine:
         o_s = o_s or (F_out * T * N, T * N, N)
         r_s = r_s or (0, 0, 0)
         return cabi.TapGemmParams(B, F_out, T, N, F_in, T_in, C1, C2, mode, kf, kt, stride_f, pad_f, dil_t, pad_t, f_off,
-                                  ACT_NONE, 0, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, 1 if self.precision == 1 else 0, 0)
+                                  ACT_NONE, 0, stats_mode, groups, *a1_s, *a2_s, w_sb, *o_s, *r_s, *cs_s, self.precision if self.precision in (1, 3) else 0, 0)
 
-    def _gemm_call(self, p, out, w, a1=None, a2=None, bias=None, residual=None, samp_affine=None, stats=None, colscale=None):
-        if p.precision == 1:
+    def _gemm_call(self, p, out, w, a1=None, a2=None, bias=None, residual=None, samp_affine=None, stats=None, colscale=None, halves=None):
+        """aero_tapgemm_fwd in the engine's arithmetic mode.  halves: optional dict id(tensor) -> (hi, lo) of operands already split."""
+        if p.precision in (1, 3):
             # tcgen05 path: K-major TF32 twin [taps, pad4(N), K] of the packed weight [taps, K, pad4(N)]; shapes it does not take stay SIMT
-            if p.w_sb == 0 and colscale is None and w.dim() == 3 and self.lib.aero_tapgemm_tc_eligible(C.byref(p)):
-                wk = torch.empty(w.shape[0], w.shape[2], w.shape[1], device=w.device, dtype=torch.float32)
-                self._check(self.lib.aero_pack_kmajor_tf32(_ptr(w), _ptr(wk), w.shape[0], w.shape[1], w.shape[2], self._stream()))
-                w = wk
-            else:
+            ok = p.w_sb == 0 and colscale is None and w.dim() == 3 and bool(self.lib.aero_tapgemm_tc_eligible(C.byref(p)))
+            if ok and p.precision == 3:
+                ok = self._splittable(a1, p.C1, p.a1_sb, p.a1_sf, p.a1_st, p) and self._splittable(a2, p.C2, p.a2_sb, p.a2_sf, p.a2_st, p)
+            if not ok:
                 p.precision = 0
+            elif p.precision == 3:
+                return self._gemm3(p, out, w, a1, a2, bias, residual, samp_affine, stats, halves)
+            else:
+                w, _ = self._pack_kmajor(w, False)
+        self._launch_gemm(p, out, w, a1, a2, bias, residual, samp_affine, stats, colscale)
+        return out
+
+    def _launch_gemm(self, p, out, w, a1, a2, bias, residual, samp_affine, stats, colscale=None):
         self._check(self.lib.aero_tapgemm_fwd(_ptr(a1), _ptr(a2), _ptr(w), _ptr(bias), None, _ptr(colscale), _ptr(residual),
                                               _ptr(samp_affine), _ptr(out), _ptr(stats), C.byref(p), self._stream()))
+
+    def _pack_kmajor(self, w, with_lo):
+        wk = torch.empty(w.shape[0], w.shape[2], w.shape[1], device=w.device, dtype=torch.float32)
+        wl = torch.empty_like(wk) if with_lo else None
+        self._check(self.lib.aero_pack_kmajor_tf32(_ptr(w), _ptr(wk), _ptr(wl), w.shape[0], w.shape[1], w.shape[2], self._stream()))
+        return wk, wl
+
+    @staticmethod
+    def _splittable(t, C_, sb, sf, st, p):
+        """Can operand t (a flat buffer addressed with these strides) be replaced by its element-wise hi / lo copies?"""
+        if t is None or C_ == 0:
+            return True
+        extent = (p.B - 1) * max(sb, 0) + (p.F_in - 1) * max(sf, 0) + (p.T_in - 1) * max(st, 0) + C_
+        return t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() % 16 == 0 and extent <= t.numel()
+
+    def _halves(self, t, cache=None):
+        """(hi, lo) with hi = TF32(t), lo = TF32(t - hi), element-wise over the whole buffer."""
+        if t is None:
+            return None, None
+        if cache is not None and id(t) in cache:
+            return cache[id(t)]
+        hi, lo = torch.empty_like(t), torch.empty_like(t)
+        self._check(self.lib.aero_split_tf32(_ptr(t), _ptr(hi), _ptr(lo), t.numel(), self._stream()))
+        if cache is not None:
+            cache[id(t)] = (hi, lo)
+        return hi, lo
+
+    def _gemm3(self, p, out, w, a1, a2, bias, residual, samp_affine, stats, halves):
+        """3xTF32: out = A_lo W_hi (+ residual) -> + A_hi W_lo -> + A_hi W_hi + bias, the epilogue (statistics, per-sample affine) on the
+        last pass; the small terms go first so that they are not absorbed."""
+        p.precision = 1
+        wh, wl = self._pack_kmajor(w, True)
+        h1, l1 = self._halves(a1, halves)
+        h2, l2 = self._halves(a2, halves)
+        t1, t2 = torch.empty_like(out), torch.empty_like(out)
+        pp = cabi.TapGemmParams.from_buffer_copy(p)
+        pp.stats_mode, pp.groups = 0, 1
+        if residual is None:
+            pp.r_sb = pp.r_sf = pp.r_st = 0
+        self._launch_gemm(pp, t1, wh, l1, l2, None, residual, None, None)
+        pp.r_sb, pp.r_sf, pp.r_st = p.o_sb, p.o_sf, p.o_st
+        self._launch_gemm(pp, t2, wl, h1, h2, None, t1, None, None)
+        p.r_sb, p.r_sf, p.r_st = p.o_sb, p.o_sf, p.o_st
+        self._launch_gemm(p, out, wh, h1, h2, bias, t2, samp_affine, stats)
         return out
+
+    def _wgrad_call(self, x1, x2, dy, gw, pw, sn, sk, ss, halves=None):
+        """aero_tapgemm_wgrad in the engine's arithmetic mode (dW accumulates: the three 3xTF32 products simply add up)."""
+        lib = self.lib
+
+        def launch(a, b_, d):
+            self._check(lib.aero_tapgemm_wgrad(_ptr(a), _ptr(b_), _ptr(d), _ptr(gw), C.byref(pw), sn, sk, ss, self._stream()))
+        if pw.precision == 3:
+            pw.precision = 1
+            o_ext = (pw.B - 1) * pw.o_sb + (pw.F_out - 1) * pw.o_sf + (pw.T - 1) * pw.o_st + pw.N
+            ok = bool(lib.aero_tapgemm_wgrad_tc_eligible(C.byref(pw), _ptr(x1), _ptr(x2), _ptr(dy))) and \
+                self._splittable(x1, pw.C1, pw.a1_sb, pw.a1_sf, pw.a1_st, pw) and self._splittable(x2, pw.C2, pw.a2_sb, pw.a2_sf, pw.a2_st, pw) and \
+                dy.is_contiguous() and o_ext <= dy.numel()
+            if ok:
+                h1, l1 = self._halves(x1, halves)
+                h2, l2 = self._halves(x2, halves)
+                dh, dl = self._halves(dy, halves)
+                launch(l1, l2, dh)
+                launch(h1, h2, dl)
+                launch(h1, h2, dh)
+                return
+            pw.precision = 0
+        launch(x1, x2, dy)
 
     def _colsum(self, x, out1, N, n_inner, inner_s, z=None, out2=None, n_outer=1, outer_s=0, n_seg=1, seg_sx=0, seg_so=0):
         dbl = (out1 if out1 is not None else out2).dtype == torch.float64
@@ -191,7 +269,8 @@ class TrainEngine:
             gw = self.pgrad(wname).view(w4.shape) if direct else torch.zeros_like(w4, memory_format=torch.contiguous_format)
             sn, sk = (gw.stride(0), gw.stride(1)) if cv.kind == "conv" else (gw.stride(1), gw.stride(0))
             pw = self._tg(**geo)
-            self._check(self.lib.aero_tapgemm_wgrad(_ptr(x1), _ptr(x2), _ptr(dy), _ptr(gw), C.byref(pw), sn, sk, 1, self._stream()))
+            halves = {} if self.precision == 3 else None          # dy is split once for the weight and the data gradient
+            self._wgrad_call(x1, x2, dy, gw, pw, sn, sk, 1, halves)
             if w_back is not None:
                 w_back(gw)
             elif wslice is not None:
@@ -225,7 +304,7 @@ class TrainEngine:
                     pd = self._tg(B=B, F_out=F_in, T=T, N=cs, C1=N, F_in=F_out, mode=TAPS_CONV, kf=cv.kf, stride_f=cv.stride_f,
                                   pad_f=cv.f_off, a1_s=os_)
                 dx = self._new(B * F_in * Ti * cs)
-                self._gemm_call(pd, dx, wd, a1=dy)
+                self._gemm_call(pd, dx, wd, a1=dy, halves=halves)
                 self.acc(src, dx)
         self.tape.append(bwd)
         self.keep.append((x1, x2, out, residual))

@@ -396,9 +396,16 @@ int aero_weight_norm_fwd(const float* v, const float* g, float* w, int32_t rows,
 int aero_weight_norm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int32_t rows, int32_t len,
                          aero_stream_t stream);
 
-/* Weight repack for the TF32 training mode: w [taps][K][ldn] (the aero_tapgemm_fwd precision-0 layout, ldn = N rounded up to 4) ->
- * out [taps][ldn][K] (the precision-1 layout), every element rounded to TF32 (round to nearest, ties away). */
-int aero_pack_kmajor_tf32(const float* w, float* out, int32_t taps, int32_t K, int32_t ldn, aero_stream_t stream);
+/* Weight repack for the tensor-core training modes: w [taps][K][ldn] (the aero_tapgemm_fwd precision-0 layout, ldn = N rounded up to
+ * 4) -> out [taps][ldn][K] (the precision-1 layout), every element rounded to TF32 (round to nearest, ties away); out_lo (optional) gets
+ * TF32(w - out) in the same layout.
+ * aero_split_tf32: the same two-term split of an activation tensor, hi = TF32(x), lo = TF32(x - hi).  Three TF32 tensor-core products
+ * hi*hi + hi*lo + lo*hi, summed in fp32, reproduce the fp32 product to ~2^-22 ("3xTF32"): the training engine's fp32-grade tensor-core
+ * mode issues aero_tapgemm_fwd / aero_tapgemm_wgrad three times on these halves (aero_b200/train_engine.py, precision 3).
+ * aero_tapgemm_wgrad_tc_eligible: 1 when aero_tapgemm_wgrad with p->precision = 1 would run on the tensor cores. */
+int aero_pack_kmajor_tf32(const float* w, float* out, float* out_lo, int32_t taps, int32_t K, int32_t ldn, aero_stream_t stream);
+int aero_split_tf32(const float* x, float* hi, float* lo, int64_t n, aero_stream_t stream);
+int aero_tapgemm_wgrad_tc_eligible(const aero_tapgemm_params* p, const float* a1, const float* a2, const float* dy);
 
 /* Fused multi-tensor Adam (torch.optim.Adam semantics, no amsgrad / weight decay; reference train.py:83).  chunk_table: device
  * array of n_chunks records {float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64 count}; one CTA per
