@@ -93,6 +93,7 @@ SYMBOLS = {
     "aero_tapgemm_wgrad": (C.c_int, [vp, vp, vp, vp, C.POINTER(TapGemmParams), i64, i64, i64, vp]),
     "aero_colsum": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i64, i64, i64, i32, i64, i64, vp]),
     "aero_add": (C.c_int, [vp, vp, i64, f32, vp]),
+    "aero_add_f64": (C.c_int, [vp, vp, i64, vp]),
     "aero_gram": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, i64, i64, i64, vp]),
     "aero_bcast_add": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "aero_scale_rows": (C.c_int, [vp, vp, vp, i32, i64, i32, vp]),

@@ -463,6 +463,11 @@ __global__ void __launch_bounds__(256) add_kernel(float* __restrict__ dst, const
         for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) dst[i] = fmaf(alpha, src[i], dst[i]);
 }
 
+// dst (fp32) += src (fp64): the last step of every bias / affine / statistics gradient (fp64 column sums into the fp32 parameter gradient)
+__global__ void __launch_bounds__(256) add_f64_kernel(float* __restrict__ dst, const double* __restrict__ src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] += (float)src[i];
+}
+
 // ------------------------------------------------------------------------------------------------------------ norm + act (training)
 // y = act(norm(x)):  norm = GroupNorm (scope 1: per sample and channel group over all rows; scope 2: per (b, f) row, one
 // group), BatchNorm with batch statistics (scope 3: per channel over every pixel of the batch) or none (AERO_NA_NO_NORM).
@@ -950,6 +955,16 @@ extern "C" int aero_add(float* dst, const float* src, int64_t n, float alpha, ae
     if (blocks < 1) blocks = 1;
     add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n, alpha);
     return check_launch("aero_add");
+}
+
+extern "C" int aero_add_f64(float* dst, const double* src, int64_t n, aero_stream_t stream) {
+    using namespace aero;
+    AERO_REQUIRE(dst && src && n >= 0, "aero_add_f64: bad argument");
+    if (n == 0) return AERO_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    add_f64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    return check_launch("aero_add_f64");
 }
 
 static int na_train_check(const aero_norm_act_params* p) {

@@ -260,7 +260,7 @@ int wgrad_tc_launch(const float* a1, const float* a2, const float* dy, float* dw
     g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int stage_bytes = kWtATile + (g.BN / 32) * 4096;
     const int fixed = (int)sizeof(WgradTcShared) + 1024;
-    g.stages = (200 * 1024 - fixed) / stage_bytes;
+    g.stages = (226 * 1024 - fixed) / stage_bytes;
     if (g.stages > kWtMaxStages) g.stages = kWtMaxStages;
     if (g.stages < 2) g.stages = 2;
     const size_t smem = (size_t)g.stages * stage_bytes + fixed;
@@ -273,13 +273,23 @@ int wgrad_tc_launch(const float* a1, const float* a2, const float* dy, float* dw
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // split the pixel axis until the grid fills the GPU about twice; a split keeps at least 8 chunks so that the atomics stay a small
-    // fraction of the work
-    int64_t splits = cdiv((int64_t)2 * num_sms, items);
+    // split the pixel axis: one CTA per SM is resident (the pipeline takes the shared memory), so the grid should be a whole number of
+    // waves.  Among the split counts that give 2 .. 6 waves pick the one with the fullest last wave; a split keeps at least 8 chunks so
+    // that the atomics stay a small fraction of the work.
     const int64_t max_splits = n_chunks / 8 > 0 ? n_chunks / 8 : 1;
-    if (splits > max_splits) splits = max_splits;
-    if (splits > 65535) splits = 65535;
-    if (splits < 1) splits = 1;
+    int64_t lo = cdiv((int64_t)2 * num_sms, items), hi = cdiv((int64_t)6 * num_sms, items);
+    if (lo > max_splits) lo = max_splits;
+    if (hi > max_splits) hi = max_splits;
+    if (hi > 65535) hi = 65535;
+    if (lo < 1) lo = 1;
+    if (hi < lo) hi = lo;
+    int64_t splits = lo;
+    double best_eff = 0.0;
+    for (int64_t sp = lo; sp <= hi; ++sp) {
+        const int64_t ctas = items * sp;
+        const double eff = (double)ctas / (double)(cdiv(ctas, (int64_t)num_sms) * num_sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; splits = sp; }      // prefer fewer splits unless clearly fuller
+    }
     g.splits = (int)splits;
     g.d_tt = g.splits % g.tiles_t;
     const int d_row = g.splits / g.tiles_t;

@@ -117,7 +117,7 @@ class _DiscEngine(TrainEngine):
             w_back(gw)
             gb = self._new(Cout, zero=True, dtype=torch.float64)
             self._colsum(dy, gb, Cout, B * Tout, Cout)
-            self.pgrad(prefix + ".bias").add_(gb.float())
+            self._add_f64(self.pgrad(prefix + ".bias"), gb)
             if id(x) not in self.no_grad:
                 dx = self._new(B * Tin * Cin)
                 self._check(lib.aero_gconv1d_dgrad(_ptr(dy), _ptr(w), _ptr(dx), *args, self._stream()))

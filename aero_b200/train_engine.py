@@ -66,6 +66,7 @@ class TrainEngine:
         self.no_grad = set()   # ids of activations that need no gradient (the input spectrogram)
         self._sink = None      # optional name -> preallocated gradient tensor
         self.marks = []        # (tape length, layer tag) after each encoder / decoder layer of the forward
+        self._zpool = {}       # dtype -> [zeroed buffer, bump offset] (see _new)
 
     # ------------------------------------------------------------------ plumbing
     def _device(self):
@@ -75,7 +76,28 @@ class TrainEngine:
         return C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
 
     def _new(self, *shape, zero=False, dtype=torch.float32):
-        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self._device())
+        if not zero:
+            return torch.empty(shape, dtype=dtype, device=self._device())
+        # zeroed accumulators (fp64 statistics / column sums, small fp32 gradients): bump-allocated from one buffer zeroed once per step --
+        # a step needs ~900 of them, and a memset launch each costs more host time than the kernels that fill them
+        n = 1
+        for d in shape:
+            n *= int(d)
+        pool = self._zpool.get(dtype)
+        if pool is None and dtype in (torch.float32, torch.float64):
+            pool = self._zpool[dtype] = [torch.zeros(1 << 20, dtype=dtype, device=self._device()), 0]
+        if pool is None or n > (1 << 18) or pool[1] + n > pool[0].numel():
+            return torch.zeros(shape, dtype=dtype, device=self._device())
+        t = pool[0][pool[1]:pool[1] + n].view(shape)
+        pool[1] += (n + 63) & ~63                                  # 256-byte granules keep every carve-out 16-byte aligned
+        return t
+
+    def _add_f64(self, dst, src):
+        """dst (fp32 parameter gradient) += src (fp64 sums), one launch."""
+        if dst.is_contiguous() and src.is_contiguous() and src.dtype == torch.float64 and dst.numel() == src.numel():
+            self._check(self.lib.aero_add_f64(_ptr(dst), _ptr(src), dst.numel(), self._stream()))
+        else:
+            dst.add_(src.float().view_as(dst))
 
     def _check(self, rc):
         cabi.check(rc, self.lib)
@@ -283,7 +305,7 @@ class TrainEngine:
                 if b_back is not None:
                     b_back(gb.float())
                 else:
-                    self.pgrad(bname).add_(gb.float())
+                    self._add_f64(self.pgrad(bname), gb)
             # ---- data gradients: the adjoint tap-GEMM reads dy (with the forward's output strides)
             for src, lo, cs in ((x1, 0, C1), (x2, C1, C2)):
                 if src is None or cs == 0 or id(src) in self.no_grad:
@@ -353,8 +375,8 @@ class TrainEngine:
                 g_back(dgamma.float())
                 b_back(dbeta.float())
             elif not no_norm:
-                self.pgrad(gname).add_(dgamma.float())
-                self.pgrad(bname).add_(dbeta.float())
+                self._add_f64(self.pgrad(gname), dgamma)
+                self._add_f64(self.pgrad(bname), dbeta)
             if scale:
                 self.pgrad(scale).add_(dscale.float().view_as(self.pgrad(scale)))
             if snake:

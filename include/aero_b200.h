@@ -339,6 +339,8 @@ int aero_bcast_add(float* x, const float* addend, int32_t B, int32_t F, int32_t 
 int aero_scale_rows(const float* x, float* y, const float* s, int32_t B, int64_t per_sample, int32_t s_stride, aero_stream_t stream);
 /* dst[i] += alpha * src[i] (gradient accumulation where a tensor has several consumers). */
 int aero_add(float* dst, const float* src, int64_t n, float alpha, aero_stream_t stream);
+/* dst[i] += (float) src[i]: fp64 column sums into an fp32 parameter gradient. */
+int aero_add_f64(float* dst, const double* src, int64_t n, aero_stream_t stream);
 
 /* Normalisation + activation, training form (nothing folded, fp32): y = act(norm(x)) with
  *   scope 1 / 2: GroupNorm as in aero_norm_act_fwd;  scope 3: BatchNorm with BATCH statistics, stats = [C][2] fp64 {sum, sumsq}

@@ -117,6 +117,49 @@ def run_stft(args):
         print(f"{name}: B={B} {nbytes/1e6:.1f} MB  best {min(ms)*1e3:.1f} us -> {nbytes/min(ms)/1e6:.1f} GB/s")
 
 
+def run_wgrad(args):
+    """Weight gradient of one conv shape, as the training engine launches it (fp32 operands, dW in PyTorch's parameter layout)."""
+    import ctypes as C
+    lib = cabi.load()
+    cfg = dict(SHAPES[args.shape])
+    B, Tt = args.batch, cfg.pop("T", T)
+    F_out, N, C1 = cfg.pop("F_out"), cfg.pop("N"), cfg.pop("C1")
+    C2, F_in = cfg.get("C2", 0), cfg.get("F_in", F_out)
+    mode, kf, kt = cfg.get("mode", cabi.TAPS_CONV), cfg.get("kf", 1), cfg.get("kt", 1)
+    K = C1 + C2
+    a1 = torch.randn(B, F_in, Tt, C1, device="cuda") if C1 else None
+    a2 = torch.randn(B, F_in, Tt, C2, device="cuda") if C2 else None
+    dy = torch.randn(B, F_out, Tt, N, device="cuda")
+    conv = mode == cabi.TAPS_CONV
+    gw = torch.zeros((N, K, kf, kt) if conv else (K, N, kf, 1), device="cuda")
+    sn, sk = (gw.stride(0), gw.stride(1)) if conv else (gw.stride(1), gw.stride(0))
+
+    def cl(F, C_):
+        return (F * Tt * C_, Tt * C_, C_)
+    p = cabi.TapGemmParams(B, F_out, Tt, N, F_in, Tt, C1, C2, mode, kf, kt, cfg.get("stride_f", 1), cfg.get("pad_f", 0), 1, cfg.get("pad_t", 0),
+                           cfg.get("f_off", 0), cabi.ACT_NONE, 0, 0, 1, *(cl(F_in, C1) if C1 else (0, 0, 0)), *(cl(F_in, C2) if C2 else (0, 0, 0)), 0,
+                           *cl(F_out, N), 0, 0, 0, 0, 0, args.precision, 0)
+    ntaps = kf * kt if conv else kf // cfg["stride_f"]
+    flops = 2.0 * B * F_out * Tt * N * K * ntaps
+    nbytes = sum(t.numel() * 4 for t in (a1, a2, dy) if t is not None)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ms = []
+    for i in range(args.iters + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cabi.check(lib.aero_tapgemm_wgrad(P(a1), P(a2), P(dy), P(gw), C.byref(p), sn, sk, 1, st), lib)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    best = min(ms)
+    print(f"{args.shape} wgrad: precision {args.precision} B={B} {flops/1e9:.1f} GFLOP  best {best*1e3:.1f} us  median {sorted(ms)[len(ms)//2]*1e3:.1f} us"
+          f"  -> {flops/best/1e9:.1f} TFLOP/s; operands {nbytes/1e6:.0f} MB once = {nbytes/best/1e6:.0f} GB/s")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("shape", choices=sorted(SHAPES) + ["lstm96", "lstm48", "stft", "attn96", "attn48"])
@@ -126,6 +169,7 @@ def main():
     ap.add_argument("--no-stats", action="store_true")
     ap.add_argument("--out-f32", action="store_true")
     ap.add_argument("--in-f32", action="store_true")
+    ap.add_argument("--wgrad", action="store_true", help="time aero_tapgemm_wgrad of the shape (precision 0 = SIMT, 1 = tcgen05 TF32)")
     args = ap.parse_args()
     torch.manual_seed(0)
     if args.shape.startswith("lstm"):
@@ -134,6 +178,8 @@ def main():
         return run_stft(args)
     if args.shape.startswith("attn"):
         return run_attn(args)
+    if args.wgrad:
+        return run_wgrad(args)
     m = Aero(**aero_kwargs("aero_4-16_512_256")).eval().cuda()
     eng = AeroEngine(m)
     eng.precision = args.precision
