@@ -2,7 +2,7 @@
 """Per-launch roofline of one forward: algorithmic HBM bytes (read / written, from the storage types the engine actually
 picks) and FLOPs of every launch, from a dry run of the host sequence on CPU (B = 1, scaled), joined with an ncu launch list.
 
-    python tools/traffic_model.py gpurun_out/launches_r1n.csv > profiles/r1n_roofline_per_launch.md
+    python tools/traffic_model.py gpurun_out/launches_r2_final.csv > profiles/r2_roofline_per_launch.md
 
 Roofline time of a launch = max(read / R, written / W, (read + written) / C, flops / P) with the bandwidths measured on this
 pool's B200 (read-only 5.55, write-only 3.88, copy 6.49 TB/s) and P = the measured cuBLAS bf16 rate for the kind::f16 GEMMs."""
@@ -145,9 +145,9 @@ def main():
         last = [sg for sg in segs if len(sg) == max(len(s_) for s_ in segs)][-1]
         assert len(last) == len(log), (len(last), len(log))
         meas = last
-    print("# r1n: per-launch roofline of the final forward (aero_4-16_512_64, B=32 x 2 s, engine precision 2)\n")
+    print("# Per-launch roofline of the forward (aero_4-16_512_64, B=32 x 2 s, engine precision 2), launch list `" + os.path.basename(sys.argv[1]) + "`\n")
     print("Algorithmic bytes / FLOPs per launch from `tools/traffic_model.py` (dry run of the host sequence with the storage types the engine")
-    print("picks), measured times from `profiles/r1n_launches_final.md`.  Roofline time = max(read / 5.55 TB/s, written / 3.88 TB/s,")
+    print("picks), measured times from the ncu launch list of the same build (`profiles/r2_launches.md`).  Roofline time = max(read / 5.55 TB/s, written / 3.88 TB/s,")
     print(f"(read + written) / 6.49 TB/s, FLOP / {P_TENSOR/1e12:.0f} TFLOP/s): the bandwidths are this pool's measured read-only / write-only / copy")
     print("figures, the tensor rate is the driver's sustained cuBLAS bf16 number.  ncu times are cold-cache and serialised: ratios below ~1.3 are at")
     print("the roofline; the LSTM rows are latency-bound by construction (200 dependent steps), attention is exp/issue-bound.\n")
