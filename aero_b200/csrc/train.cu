@@ -228,6 +228,68 @@ __global__ void __launch_bounds__(kWsThreads) wgrad_small_kernel(const WgradArgs
     }
 }
 
+// The same for layers with at most 8 output channels (96 -> 2 transposed convolution, FTB's C -> 5): a thread owns up to four (slab, k)
+// pairs and ALL n of them, so that consecutive lanes read consecutive input channels (one 128-byte line per warp and frame) and the few
+// gradient values of a frame are one broadcast load for the whole warp.
+constexpr int kWtnItems = 4, kWtnN = 8;
+__global__ void __launch_bounds__(kWsThreads) wgrad_thin_n_kernel(const WgradArgs g, int n_items, int n_seg, int seg_len) {
+    const aero_tapgemm_params& p = g.p;
+    const int K = p.C1 + p.C2;
+    const int row = blockIdx.x / n_seg, seg = blockIdx.x - row * n_seg;
+    const int b = row / p.F_out, fo = row - b * p.F_out;
+    const int t_lo = seg * seg_len, t_hi = min(p.T, t_lo + seg_len);
+    const float* dyr = g.dy + (int64_t)b * p.o_sb + (int64_t)fo * p.o_sf;
+#pragma unroll 1
+    for (int i = 0; i < kWtnItems; ++i) {
+        const int it = threadIdx.x + i * kWsThreads;
+        if (it >= n_items) break;
+        const int slab = it / K, k = it - slab * K;
+        int fi, dt = 0;
+        if (p.mode == AERO_TAPS_CONV) {
+            const int jf = slab / p.kt;
+            fi = fo * p.stride_f + jf - p.pad_f;
+            dt = (slab - jf * p.kt) * p.dil_t - p.pad_t;
+        } else {
+            const int fof = fo + p.f_out_offset;
+            if (fof % p.stride_f != slab % p.stride_f) continue;
+            fi = fof / p.stride_f - slab / p.stride_f;
+        }
+        if (fi < 0 || fi >= p.F_in) continue;
+        const float* xr;
+        int64_t xs;
+        if (k < p.C1) { xr = g.a1 + (int64_t)b * p.a1_sb + (int64_t)fi * p.a1_sf + k; xs = p.a1_st; }
+        else { xr = g.a2 + (int64_t)b * p.a2_sb + (int64_t)fi * p.a2_sf + (k - p.C1); xs = p.a2_st; }
+        const int lo = max(t_lo, -dt), hi = min(t_hi, p.T_in - dt);
+        float acc[kWtnN];
+#pragma unroll
+        for (int n = 0; n < kWtnN; ++n) acc[n] = 0.f;
+        int t = lo;
+        for (; t + 3 < hi; t += 4) {                                     // four frames in flight
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = __ldg(xr + (int64_t)(t + u + dt) * xs);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* yp = dyr + (int64_t)(t + u) * p.o_st;
+#pragma unroll
+                for (int n = 0; n < kWtnN; ++n)
+                    if (n < p.N) acc[n] = fmaf(xv[u], __ldg(yp + n), acc[n]);
+            }
+        }
+        for (; t < hi; ++t) {
+            const float xv = __ldg(xr + (int64_t)(t + dt) * xs);
+            const float* yp = dyr + (int64_t)t * p.o_st;
+#pragma unroll
+            for (int n = 0; n < kWtnN; ++n)
+                if (n < p.N) acc[n] = fmaf(xv, __ldg(yp + n), acc[n]);
+        }
+        float* out = g.dw + (int64_t)k * g.dw_sk + (int64_t)slab * g.dw_ss;
+#pragma unroll
+        for (int n = 0; n < kWtnN; ++n)
+            if (n < p.N && acc[n] != 0.f) atomicAdd(out + (int64_t)n * g.dw_sn, acc[n]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------ weight repack
 // [taps][K][ldn] (N contiguous: the SIMT tap-GEMM layout) -> [taps][ldn][K] (K contiguous: the tcgen05 layout), rounded to TF32
 // (round-to-nearest, ties away: cvt.rna) -- the training step repacks every weight it uses, every step, so this is one launch instead
@@ -835,6 +897,10 @@ extern "C" int aero_tapgemm_wgrad(const float* a1, const float* a2, const float*
         const int seg_len = cdiv(p->T, n_seg);
         n_seg = cdiv(p->T, seg_len);
         AERO_REQUIRE(n_rows * n_seg <= 2147483647LL, "aero_tapgemm_wgrad: grid too large");
+        if (p->N <= kWtnN && K >= 16 && nslab * K <= kWtnItems * kWsThreads) {
+            wgrad_thin_n_kernel<<<(unsigned)(n_rows * n_seg), kWsThreads, 0, (cudaStream_t)stream>>>(g, nslab * K, n_seg, seg_len);
+            return check_launch("aero_tapgemm_wgrad(thin n)");
+        }
         wgrad_small_kernel<<<(unsigned)(n_rows * n_seg), kWsThreads, 0, (cudaStream_t)stream>>>(g, nslab * K * p->N, n_seg, seg_len);
         return check_launch("aero_tapgemm_wgrad(small)");
     }
