@@ -158,6 +158,7 @@ class _DiscEngine(TrainEngine):
 
     @torch.no_grad()
     def backward(self, grads):
+        self._sync_stream()
         for (y, To, c), gy in zip(self._outs, grads):
             if gy is not None:
                 self.acc(y, gy.contiguous().float().reshape(-1).clone())

@@ -67,13 +67,27 @@ class TrainEngine:
         self._sink = None      # optional name -> preallocated gradient tensor
         self.marks = []        # (tape length, layer tag) after each encoder / decoder layer of the forward
         self._zpool = {}       # dtype -> [zeroed buffer, bump offset] (see _new)
+        self._st = None        # cached stream handle (see _stream)
+        self._dev = None
 
     # ------------------------------------------------------------------ plumbing
     def _device(self):
-        return next(self.model.parameters()).device
+        d = self._dev
+        if d is None:
+            d = self._dev = next(self.model.parameters()).device
+        return d
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+        # looked up once per pass (forward / backward each start from _sync_stream): a step makes ~3000 launches and
+        # torch.cuda.current_stream() costs more host time than most of them take on the GPU
+        st = self._st
+        if st is None:
+            st = self._st = C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+        return st
+
+    def _sync_stream(self):
+        """Re-read the caller's current stream (start of a forward or backward pass)."""
+        self._st = None
 
     def _new(self, *shape, zero=False, dtype=torch.float32):
         if not zero:
@@ -785,6 +799,7 @@ class TrainEngine:
         grad_sink(name) -> zeroed tensor to accumulate that parameter's gradient into (else fresh tensors);
         on_layer_done(tag) is called when every gradient of layer `tag` ("decoder.3", ..., "encoder.0") is final."""
         self._sink = grad_sink
+        self._sync_stream()
         lib, g = self.lib, self.geom
         h, B, Cout, T, Fq, out_len = self._final
         dz = self.istft_adjoint(d_wave, B, Cout, T, Fq, out_len) if d_wave is not None else None
