@@ -1,7 +1,8 @@
 // Training-side kernels of the AERO generator: weight gradients of the tap-GEMM, column
 // reductions (bias / BatchNorm statistics / embedding gradients), GroupNorm / BatchNorm + activation forward (training
-// form: nothing folded) and backward, fused multi-tensor Adam.  All fp32 (the training engine keeps fp32 storage: the
-// gradient-parity bar is 1e-3 against reference autograd).  Contracts: include/aero_b200.h, "Training".
+// form: nothing folded) and backward, fused multi-tensor Adam, operand preparation for the tensor-core modes (weight repack,
+// hi / lo TF32 split).  All fp32 storage (the gradient-parity bar is 1e-3 against reference autograd); the tensor-core weight
+// gradient lives in wgrad_tc.cu.  Contracts: include/aero_b200.h, "Training".
 //
 // Data gradients of every convolution are NOT here: the adjoint of a tap-GEMM is a tap-GEMM (flipped taps, transposed
 // weights, conv <-> transposed conv), so dgrad runs on aero_tapgemm_fwd itself.

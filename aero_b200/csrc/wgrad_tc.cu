@@ -7,7 +7,8 @@
 // 32 channels x 32 consecutive frames of one (b, f) row, written with SWIZZLE_128B_ATOM_32B, is 8 K-atoms (4 frames x 128 B) of one
 // 32-channel M atom.  No transposition pass, no im2col: the tap shift is the box coordinate, borders and tails are TMA zero fill.
 //
-//   D (TMEM)  : 128 lanes = 128 output channels n, BN <= 256 fp32 columns = input channels k of ONE source tensor
+//   D (TMEM)  : 128 lanes = 128 output channels n, BN <= 256 fp32 columns = input channels k (32-channel boxes taken from the
+//               concatenation of the two source tensors of a skip connection; a box never straddles them)
 //   A (smem)  : dY tile  [32 frames][128 n]  = 4 boxes, 16 KB
 //   B (smem)  : act tile [32 frames][BN k]   = BN/32 boxes
 // One CTA owns one (slab, n-tile, k-tile) and a strided subset of the 32-frame chunks (split-K over pixels); warp 0 = TMA producer,
@@ -150,8 +151,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant
         int iters = 0;
         WtWalker w;
         for (w.init(g, split); !w.done(g); w.next(g)) {
-            int fi;
-            if (!w.input_row(p, jf, r, tapi, fi)) continue;
+            int fi_unused;
+            if (!w.input_row(p, jf, r, tapi, fi_unused)) continue;         // same enumeration as the producer
             mbar_wait(&sh->full[stage], phase);
             tcgen05_fence_after();
             if (elect_one()) {
